@@ -1,0 +1,188 @@
+// oracle/oracle.cpp -- TEST INFRASTRUCTURE ONLY.
+// C ABI over HOST pointers for the CPU restatement of the reference algorithm (oracle_*.hpp).
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+// this library; the product path (libifadv_b200.so) never does.
+// dtype: 0 = Float32, 1 = Float64.  Directions, sweep order (dirO) and cell indices are 1-based as in
+// the Julia reference; perdir is a bit mask (bit j-1 set <=> j ∈ perdir).
+#include "oracle_flow.hpp"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace orc;
+
+#define DISPATCH(dtype, ...)       \
+  do {                             \
+    if ((dtype) == 0) {            \
+      using T = float;             \
+      __VA_ARGS__;                 \
+    } else if ((dtype) == 1) {     \
+      using T = double;            \
+      __VA_ARGS__;                 \
+    } else                         \
+      return -2;                   \
+  } while (0)
+
+static inline I3 mkI(int D, const int64_t* I) { return I3{{I[0], I[1], D == 3 ? I[2] : 1}}; }
+
+extern "C" {
+
+int orc_num_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+int orc_get_intercept(int dtype, int D, const double* n, double g, double* out) {
+  DISPATCH(dtype, {
+    T nn[3] = {(T)n[0], (T)n[1], D == 3 ? (T)n[2] : T(0)};
+    *out = (double)getInterceptD<T>(D, nn, (T)g);
+  });
+  return 0;
+}
+int orc_get_volume_fraction(int dtype, int D, const double* n, double b, double* out) {
+  DISPATCH(dtype, {
+    T nn[3] = {(T)n[0], (T)n[1], D == 3 ? (T)n[2] : T(0)};
+    *out = (double)getVolumeFractionD<T>(D, nn, (T)b);
+  });
+  return 0;
+}
+int orc_limiter(int dtype, int lam, double u, double c, double d, double* out) {
+  DISPATCH(dtype, { *out = (double)limiter<T>(lam, (T)u, (T)c, (T)d); });
+  return 0;
+}
+int orc_normal(int dtype, int D, const int64_t* Ng, int scheme, void* f, void* nhat, const int64_t* I) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, {
+    SF<T> ff{(T*)f, &g};
+    VF<T> nh{(T*)nhat, &g};
+    normalScheme<T>(scheme, D, ff, nh, mkI(D, I));
+  });
+  return 0;
+}
+int orc_vof_flux_face(int dtype, int D, const int64_t* Ng, void* ff, void* f, void* alpha, void* nhat, double dl, int d,
+                      const int64_t* IFace, void* rhouf, double lr) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, {
+    getVOFFlux_face<T>(g, SF<T>{(T*)ff, &g}, SF<T>{(T*)f, &g}, SF<T>{(T*)alpha, &g}, VF<T>{(T*)nhat, &g}, (T)dl, d - 1, mkI(D, IFace),
+                       VF<T>{(T*)rhouf, &g}, (T)lr);
+  });
+  return 0;
+}
+int orc_bcf(int dtype, int D, const int64_t* Ng, void* f, unsigned perdir) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, BCf<T>(g, SF<T>{(T*)f, &g}, perdir));
+  return 0;
+}
+int orc_bcv1d(int dtype, int D, const int64_t* Ng, void* f, int d, unsigned perdir) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, BCv1D<T>(g, SF<T>{(T*)f, &g}, d - 1, perdir));
+  return 0;
+}
+int orc_bcv(int dtype, int D, const int64_t* Ng, void* f, unsigned perdir) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, BCv<T>(g, VF<T>{(T*)f, &g}, perdir));
+  return 0;
+}
+int orc_bcvof(int dtype, int D, const int64_t* Ng, void* f, void* alpha, void* nhat, unsigned perdir) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, BCVOF<T>(g, SF<T>{(T*)f, &g}, SF<T>{(T*)alpha, &g}, VF<T>{(T*)nhat, &g}, perdir));
+  return 0;
+}
+int orc_bc_vec(int dtype, int D, const int64_t* Ng, void* a, const double* A, int saveexit, unsigned perdir) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, {
+    T AA[3] = {(T)A[0], (T)A[1], D == 3 ? (T)A[2] : T(0)};
+    BC_vec<T>(g, VF<T>{(T*)a, &g}, AA, saveexit != 0, perdir);
+  });
+  return 0;
+}
+int orc_clean_wisp(int dtype, int D, const int64_t* Ng, void* f) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, cleanWisp<T>(g, SF<T>{(T*)f, &g}, 10 * std::numeric_limits<T>::epsilon()));
+  return 0;
+}
+int orc_u2rhou(int dtype, int D, const int64_t* Ng, void* rhou, void* u, void* f, double lr) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, u2rhou<T>(g, VF<T>{(T*)rhou, &g}, VF<T>{(T*)u, &g}, SF<T>{(T*)f, &g}, (T)lr));
+  return 0;
+}
+int orc_rhou2u(int dtype, int D, const int64_t* Ng, void* u, void* rhou, void* f, double lr) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, rhou2u<T>(g, VF<T>{(T*)u, &g}, VF<T>{(T*)rhou, &g}, SF<T>{(T*)f, &g}, (T)lr));
+  return 0;
+}
+int orc_f2face(int dtype, int D, const int64_t* Ng, void* fFace, void* fCen, unsigned perdir) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, f2face<T>(g, VF<T>{(T*)fFace, &g}, SF<T>{(T*)fCen, &g}, perdir));
+  return 0;
+}
+int orc_apply_vof_samples(int dtype, int D, const int64_t* Ng, void* f, void* alpha, void* nhat, const void* sc, const void* sp,
+                          const void* sm) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, applyVOF_samples<T>(g, SF<T>{(T*)f, &g}, SF<T>{(T*)alpha, &g}, VF<T>{(T*)nhat, &g}, (const T*)sc, (const T*)sp,
+                                      (const T*)sm));
+  return 0;
+}
+int orc_reconstruct_interface(int dtype, int D, const int64_t* Ng, void* f, void* alpha, void* nhat, int scheme, unsigned perdir) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, reconstructInterface<T>(g, SF<T>{(T*)f, &g}, SF<T>{(T*)alpha, &g}, VF<T>{(T*)nhat, &g}, scheme, perdir));
+  return 0;
+}
+int orc_get_vof_flux(int dtype, int D, const int64_t* Ng, void* ff, void* f, void* alpha, void* nhat, void* u, void* u0, double dt, int d,
+                     void* rhouf, double lr) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, getVOFFlux<T>(g, SF<T>{(T*)ff, &g}, SF<T>{(T*)f, &g}, SF<T>{(T*)alpha, &g}, VF<T>{(T*)nhat, &g}, VF<T>{(T*)u, &g},
+                                VF<T>{(T*)u0, &g}, (T)dt, d - 1, VF<T>{(T*)rhouf, &g}, (T)lr));
+  return 0;
+}
+
+// advectVOF!  (src/advection.jl:34).  report may be NULL.
+int orc_advect_vof(int dtype, int D, const int64_t* Ng, void* f, void* ff, void* alpha, void* nhat, void* u, void* u0, double dt,
+                   int8_t* cbar, void* rhouf, double lr, int scheme, unsigned perdir, const int* dirO, FillReport* rep) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, return advectVOF<T>(g, (T*)f, (T*)ff, (T*)alpha, (T*)nhat, (T*)u, (T*)u0, (T)dt, cbar, (T*)rhouf, (T)lr, scheme, perdir,
+                                      dirO, rep));
+  return 0;
+}
+// advectVOFρuu!  (src/flow.jl:165).  uStar may alias nhat and dilaU may alias alpha (flow.jl:157-160).
+int orc_advect_vof_rhouu(int dtype, int D, const int64_t* Ng, void* f, void* ff, void* alpha, void* nhat, void* u, void* u0, double dt,
+                         int8_t* cbar, void* rhou, void* r, void* Phi, void* rhouf, void* uStar, void* uOld, void* dilaU, void* drho,
+                         double lr, int limiter_id, int scheme, const double* uBC, unsigned perdir, int exitBC, const int* dirO,
+                         FillReport* rep) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, {
+    T A[3] = {(T)uBC[0], (T)uBC[1], D == 3 ? (T)uBC[2] : T(0)};
+    return advectVOFrhouu<T>(g, (T*)f, (T*)ff, (T*)alpha, (T*)nhat, (T*)u, (T*)u0, (T)dt, cbar, (T*)rhou, (T*)r, (T*)Phi, (T*)rhouf,
+                             (T*)uStar, (T*)uOld, (T*)dilaU, (T*)drho, (T)lr, limiter_id, scheme, A, perdir, exitBC != 0, dirO, rep);
+  });
+  return 0;
+}
+// MPCFL (src/flow.jl:262).  mu<=0 / eta<=0 / gnorm<=0 disable the corresponding limit.
+int orc_mpcfl(int dtype, int D, const int64_t* Ng, void* u, void* sigma, double nu, double mu, double lam_mu, double lam_rho, double eta,
+              double gnorm, double dt_max, double safety, double* out) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, {
+    *out = (double)MPCFL<T>(g, VF<T>{(T*)u, &g}, SF<T>{(T*)sigma, &g}, (T)nu, (T)mu, (T)lam_mu, (T)lam_rho, (T)eta, (T)gnorm, (T)dt_max,
+                            (T)safety);
+  });
+  return 0;
+}
+// sum(f[inside(f)]) in Float64
+int orc_sum_inside(int dtype, int D, const int64_t* Ng, const void* f, double* out) {
+  Grid g = make_grid(D, Ng);
+  double s = 0;
+  Range r = r_inside(g);
+  DISPATCH(dtype, {
+    const T* p = (const T*)f;
+    for (int64_t k = r.lo[2]; k <= r.hi[2]; ++k)
+      for (int64_t j = r.lo[1]; j <= r.hi[1]; ++j)
+        for (int64_t i = r.lo[0]; i <= r.hi[0]; ++i) s += (double)p[lin(g, I3{{i, j, k}})];
+  });
+  *out = s;
+  return 0;
+}
+
+}  // extern "C"

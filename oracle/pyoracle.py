@@ -1,0 +1,242 @@
+"""ctypes driver for the CPU oracle (oracle/liboracle.so) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may import this
+module.  Arrays are numpy arrays in Fortran (column-major) order with the Julia shapes of the reference:
+scalar fields (N1+2, N2+2[, N3+2]); vector fields (..., D) with the component index slowest.
+Indices, directions and dirO are 1-based like the Julia reference; perdir is a tuple of 1-based directions.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+NORMAL_SCHEMES = {"WH": 0, "WY": 1, "Column": 2, "PCD": 3, "SLIC": 4, "MYC": 5, "Y": 6, "CD": 7, "XYLIC": 8}
+LIMITERS = {"upwind": 0, "minmod": 1, "Koren": 2, "vanAlbada1": 3, "Sweby": 4, "superbee": 5, "TVDcen": 6, "TVDdown": 7,
+            "quick": 8, "vanLeer": 9, "cds": 10}
+
+
+class FillReport(C.Structure):
+    _fields_ = [("maxf", C.c_double), ("minf", C.c_double), ("argmax", C.c_int64 * 3), ("argmin", C.c_int64 * 3),
+                ("dir", C.c_int), ("status", C.c_int)]
+
+
+def build(force: bool = False) -> None:
+    """Compile liboracle.so / liboracle_omp.so with the committed Makefile (g++ only, a few seconds)."""
+    need = force or not all(os.path.exists(os.path.join(_HERE, n)) for n in ("liboracle.so", "liboracle_omp.so"))
+    if not need:
+        srcs = [os.path.join(_HERE, n) for n in ("oracle.cpp", "oracle_core.hpp", "oracle_fields.hpp", "oracle_flow.hpp")]
+        newest = max(os.path.getmtime(s) for s in srcs)
+        need = any(os.path.getmtime(os.path.join(_HERE, n)) < newest for n in ("liboracle.so", "liboracle_omp.so"))
+    if need:
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+
+
+_libs = {}
+
+
+def lib(omp: bool = False):
+    name = "liboracle_omp.so" if omp else "liboracle.so"
+    if name not in _libs:
+        path = os.path.join(_HERE, name)
+        if not os.path.exists(path):
+            build()
+        _libs[name] = C.CDLL(path)
+    return _libs[name]
+
+
+def mask(perdir) -> int:
+    m = 0
+    for j in perdir:
+        m |= 1 << (int(j) - 1)
+    return m
+
+
+def _dt(a) -> int:
+    if a.dtype == np.float32:
+        return 0
+    if a.dtype == np.float64:
+        return 1
+    raise TypeError(a.dtype)
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.flags.f_contiguous, "oracle arrays must be Fortran-ordered"
+    return C.c_void_p(a.ctypes.data)
+
+
+def _ng(f):
+    D = f.ndim
+    return D, (C.c_int64 * 3)(*(list(f.shape) + [1] * (3 - D)))
+
+
+def _i3(I):
+    I = list(I)
+    return (C.c_int64 * 3)(*(I + [1] * (3 - len(I))))
+
+
+def zeros(shape, dtype):
+    return np.zeros(shape, dtype=dtype, order="F")
+
+
+def farr(x, dtype=None):
+    return np.asfortranarray(np.array(x, dtype=dtype))
+
+
+# ---- scalar KAT entry points ---------------------------------------------------------------------
+def getIntercept(n, g, dtype=np.float64) -> float:
+    out = C.c_double()
+    nn = (C.c_double * 3)(*(list(map(float, n)) + [0.0] * (3 - len(n))))
+    lib().orc_get_intercept(0 if dtype == np.float32 else 1, len(n), nn, C.c_double(float(g)), C.byref(out))
+    return out.value
+
+
+def getVolumeFraction(n, b, dtype=np.float64) -> float:
+    out = C.c_double()
+    nn = (C.c_double * 3)(*(list(map(float, n)) + [0.0] * (3 - len(n))))
+    lib().orc_get_volume_fraction(0 if dtype == np.float32 else 1, len(n), nn, C.c_double(float(b)), C.byref(out))
+    return out.value
+
+
+def limiter(name, u, c, d, dtype=np.float64) -> float:
+    out = C.c_double()
+    lib().orc_limiter(0 if dtype == np.float32 else 1, LIMITERS[name], C.c_double(u), C.c_double(c), C.c_double(d), C.byref(out))
+    return out.value
+
+
+# ---- field entry points --------------------------------------------------------------------------
+def normal(scheme, f, nhat, I):
+    D, ng = _ng(f)
+    lib().orc_normal(_dt(f), D, ng, NORMAL_SCHEMES[scheme], _p(f), _p(nhat), _i3(I))
+
+
+def getVOFFlux_face(ff, f, alpha, nhat, dl, d, IFace, rhouf, lr):
+    D, ng = _ng(f)
+    lib().orc_vof_flux_face(_dt(f), D, ng, _p(ff), _p(f), _p(alpha), _p(nhat), C.c_double(dl), int(d), _i3(IFace), _p(rhouf),
+                            C.c_double(lr))
+
+
+def BCf(f, perdir=()):
+    D, ng = _ng(f)
+    lib().orc_bcf(_dt(f), D, ng, _p(f), mask(perdir))
+
+
+def BCv1D(f, d, perdir=()):
+    D, ng = _ng(f)
+    lib().orc_bcv1d(_dt(f), D, ng, _p(f), int(d), mask(perdir))
+
+
+def BCv(v, perdir=()):
+    D, ng = _ng(v[..., 0])
+    lib().orc_bcv(_dt(v), D, ng, _p(v), mask(perdir))
+
+
+def BCVOF(f, alpha, nhat, perdir=()):
+    D, ng = _ng(f)
+    lib().orc_bcvof(_dt(f), D, ng, _p(f), _p(alpha), _p(nhat), mask(perdir))
+
+
+def BC(a, A, saveexit=False, perdir=()):
+    """WaterLily.BC!(a,A,saveexit,perdir) for a constant tuple A."""
+    D, ng = _ng(a[..., 0])
+    AA = (C.c_double * 3)(*(list(map(float, A)) + [0.0] * (3 - len(A))))
+    lib().orc_bc_vec(_dt(a), D, ng, _p(a), AA, int(bool(saveexit)), mask(perdir))
+
+
+def cleanWisp(f):
+    D, ng = _ng(f)
+    lib().orc_clean_wisp(_dt(f), D, ng, _p(f))
+
+
+def u2rhou(rhou, u, f, lr, omp=False):
+    D, ng = _ng(f)
+    lib(omp).orc_u2rhou(_dt(f), D, ng, _p(rhou), _p(u), _p(f), C.c_double(lr))
+
+
+def rhou2u(u, rhou, f, lr):
+    D, ng = _ng(f)
+    lib().orc_rhou2u(_dt(f), D, ng, _p(u), _p(rhou), _p(f), C.c_double(lr))
+
+
+def f2face(fFace, fCen, perdir=()):
+    D, ng = _ng(fCen)
+    lib().orc_f2face(_dt(fCen), D, ng, _p(fFace), _p(fCen), mask(perdir))
+
+
+def applyVOF(f, alpha, nhat, sdf):
+    """applyVOF!(f,α,n̂,InterfaceSDF) (VOFutil.jl:9-37); `sdf` maps an array of shape (..., D) of
+    positions to signed distances and is evaluated here in f's dtype like the Julia closure would be."""
+    D, ng = _ng(f)
+    T = f.dtype.type
+    idx = np.indices(f.shape).astype(f.dtype)  # 0-based index i  <->  Julia I=i+1, centre loc(0,I)=I-1.5
+    xc = np.stack([idx[k] + T(1) - T(1.5) for k in range(D)], axis=-1).astype(f.dtype)
+    dx = T(0.01)
+    sc = np.asfortranarray(np.asarray(sdf(xc), dtype=f.dtype))
+    sp = zeros(f.shape + (D,), f.dtype)
+    sm = zeros(f.shape + (D,), f.dtype)
+    for i in range(D):
+        e = np.zeros(D, dtype=f.dtype)
+        e[i] = dx
+        sp[..., i] = np.asarray(sdf((xc + e).astype(f.dtype)), dtype=f.dtype)
+        sm[..., i] = np.asarray(sdf((xc - e).astype(f.dtype)), dtype=f.dtype)
+    lib().orc_apply_vof_samples(_dt(f), D, ng, _p(f), _p(alpha), _p(nhat), _p(sc), _p(sp), _p(sm))
+
+
+def reconstructInterface(f, alpha, nhat, scheme="WH", perdir=()):
+    D, ng = _ng(f)
+    lib().orc_reconstruct_interface(_dt(f), D, ng, _p(f), _p(alpha), _p(nhat), NORMAL_SCHEMES[scheme], mask(perdir))
+
+
+def getVOFFlux(ff, f, alpha, nhat, u, u0, dt, d, rhouf, lr):
+    D, ng = _ng(f)
+    lib().orc_get_vof_flux(_dt(f), D, ng, _p(ff), _p(f), _p(alpha), _p(nhat), _p(u), _p(u0), C.c_double(dt), int(d), _p(rhouf),
+                           C.c_double(lr))
+
+
+def advectVOF(f, ff, alpha, nhat, u, u0, dt, cbar, rhouf, lr, scheme="WH", perdir=(), dirO=None, omp=False):
+    """advectVOF!(f,fᶠ,α,n̂,u,u⁰,Δt,c̄,ρuf,λρ,normalScheme; perdir,dirO)  -> (status, FillReport)"""
+    D, ng = _ng(f)
+    dirO = tuple(dirO) if dirO is not None else tuple(range(1, D + 1))
+    rep = FillReport()
+    st = lib(omp).orc_advect_vof(_dt(f), D, ng, _p(f), _p(ff), _p(alpha), _p(nhat), _p(u), _p(u0), C.c_double(dt),
+                                 C.c_void_p(cbar.ctypes.data), _p(rhouf), C.c_double(lr), NORMAL_SCHEMES[scheme], mask(perdir),
+                                 (C.c_int * 3)(*(list(dirO) + [0] * (3 - D))), C.byref(rep))
+    return st, rep
+
+
+def advectVOFrhouu(f, ff, alpha, nhat, u, u0, dt, cbar, rhou, r, Phi, rhouf, uStar, uOld, dilaU, drho, lr, limiter="Koren",
+                   scheme="WH", uBC=(0, 0, 0), perdir=(), exitBC=False, dirO=None, omp=False):
+    """advectVOFρuu!(...) (flow.jl:165)  -> (status, FillReport).  uStar may be nhat, dilaU may be alpha."""
+    D, ng = _ng(f)
+    dirO = tuple(dirO) if dirO is not None else tuple(range(1, D + 1))
+    rep = FillReport()
+    A = (C.c_double * 3)(*(list(map(float, uBC))[:D] + [0.0] * (3 - D)))
+    st = lib(omp).orc_advect_vof_rhouu(_dt(f), D, ng, _p(f), _p(ff), _p(alpha), _p(nhat), _p(u), _p(u0), C.c_double(dt),
+                                       C.c_void_p(cbar.ctypes.data), _p(rhou), _p(r), _p(Phi), _p(rhouf), _p(uStar), _p(uOld),
+                                       _p(dilaU), _p(drho), C.c_double(lr), LIMITERS[limiter], NORMAL_SCHEMES[scheme], A,
+                                       mask(perdir), int(bool(exitBC)), (C.c_int * 3)(*(list(dirO) + [0] * (3 - D))), C.byref(rep))
+    return st, rep
+
+
+def MPCFL(u, sigma, nu=0.0, mu=0.0, lam_mu=1e-2, lam_rho=1e-3, eta=0.0, gnorm=0.0, dt_max=1.0, safety=0.8) -> float:
+    D, ng = _ng(sigma)
+    out = C.c_double()
+    lib().orc_mpcfl(_dt(u), D, ng, _p(u), _p(sigma), C.c_double(nu), C.c_double(mu), C.c_double(lam_mu), C.c_double(lam_rho),
+                    C.c_double(eta), C.c_double(gnorm), C.c_double(dt_max), C.c_double(safety), C.byref(out))
+    return out.value
+
+
+def sum_inside(f) -> float:
+    D, ng = _ng(f)
+    out = C.c_double()
+    lib().orc_sum_inside(_dt(f), D, ng, _p(f), C.byref(out))
+    return out.value
+
+
+def num_threads(omp=True) -> int:
+    return lib(omp).orc_num_threads()
