@@ -1,0 +1,129 @@
+/* include/ifadv.h -- C ABI of libifadv_b200.so: the B200-native (sm_100a) VOF + CMOM advection path of
+ * InterfaceAdvection.jl.  This is the drop-in boundary: a Julia package extension (julia/IntfAdvB200Ext.jl,
+ * see INTEGRATION.md) `ccall`s these entry points in place of the KernelAbstractions `@loop` kernels that
+ * ext/IntfAdvCUDAExt.jl enables today.  Plain pointers and sizes only; no torch / CUDA.jl types.
+ *
+ * Conventions (identical to the reference's arrays, SURVEY.md §8 "Conventions for sizes"):
+ *   - arrays are column-major with ONE ghost layer per side: scalar field extents Ng = N .+ 2,
+ *     vector field (Ng..., D) with the component index slowest (SoA);
+ *   - u[I,d] lives on the lower d-face of cell I;
+ *   - directions, sweep orders (dirO) and reported cell indices are 1-based like Julia;
+ *   - perdir_mask has bit (j-1) set iff direction j is periodic;
+ *   - dtype: IFADV_F32 = Float32, IFADV_F64 = Float64; scalars cross the ABI as double and are rounded to T;
+ *   - every pointer named in a *_dev / plain entry point is a DEVICE pointer borrowed for the call;
+ *     all work is enqueued on the caller's stream (a cudaStream_t passed as void*); no device-wide sync;
+ *   - return value: 0 ok; >0 advisory (bit0 overfill, bit1 underfill; only evaluated when report != NULL);
+ *     <0 fatal: -1 NaN in f, -2 invalid argument / unsupported combination, -3 CUDA error, -4 comm error.
+ *
+ * Preconditions shared with the reference's call sites: f, u, u0 carry valid ghost values (BCf!/BC! applied,
+ * as they always are inside MPFMomStep!, flow.jl:61-92).
+ */
+#ifndef IFADV_H
+#define IFADV_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ifadv_ctx ifadv_ctx;
+
+enum { IFADV_F32 = 0, IFADV_F64 = 1 };
+
+/* normalScheme function identity -> enum (src/normalEstimation.jl) */
+enum {
+  IFADV_NS_WH = 0,     /* getInterfaceNormal_WH!     :105-154 (default) */
+  IFADV_NS_WY = 1,     /* getInterfaceNormal_WY!     :35-68  */
+  IFADV_NS_COLUMN = 2, /* getInterfaceNormal_Column! :75-97  */
+  IFADV_NS_PCD = 3,    /* getInterfaceNormal_PCD!    :161-165 */
+  IFADV_NS_SLIC = 4,   /* getInterfaceNormal_SLIC!   :172-176 */
+  IFADV_NS_MYC = 5,    /* getInterfaceNormal_MYC!    :185-202 */
+  IFADV_NS_YOUNGS = 6, /* getInterfaceNormal_Y!      :232-247 */
+  IFADV_NS_CD = 7,     /* getInterfaceNormal_CD!     :266-270 */
+  IFADV_NS_XYLIC = 8   /* getInterfaceNormal_XYLIC!  :279-283 */
+};
+/* limiter λ(u,c,d) function identity -> enum (src/flow.jl:5-15; 8-10 are WaterLily's) */
+enum {
+  IFADV_LIM_UPWIND = 0, IFADV_LIM_MINMOD = 1, IFADV_LIM_KOREN = 2, IFADV_LIM_VANALBADA1 = 3, IFADV_LIM_SWEBY = 4,
+  IFADV_LIM_SUPERBEE = 5, IFADV_LIM_TVDCEN = 6, IFADV_LIM_TVDDOWN = 7, IFADV_LIM_QUICK = 8, IFADV_LIM_VANLEER = 9,
+  IFADV_LIM_CDS = 10
+};
+/* flags */
+enum {
+  IFADV_NO_RHOUF = 1 /* advect_vof: do not materialise ρuf (the un-normalised mass flux `advect!` users may read) */
+};
+
+/* replaces reportFillError's findmax/findmin (src/advection.jl:145-149).  Filled only when passed non-NULL
+ * (the call then synchronises the stream). */
+typedef struct {
+  double maxf, minf;             /* extreme values of f after the worst (or last) directional sweep, before cleanWisp! */
+  int64_t argmax[3], argmin[3];  /* 1-based cell index (approximate tie-breaking) */
+  int dir;                       /* 1-based sweep direction the values belong to */
+  int status;                    /* same bits as the return value */
+} ifadv_report;
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+/* One context per (device, grid, dtype).  Owns reduction buffers and the pinned report; NOT the fields.
+ * Ng: array extents INCLUDING ghosts (N .+ 2), Ng[2] ignored for D == 2. */
+int ifadv_create(ifadv_ctx** ctx, int D, const int64_t Ng[3], int dtype, int device);
+int ifadv_destroy(ifadv_ctx* ctx);
+const char* ifadv_last_error(const ifadv_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t ifadv_launch_count(const ifadv_ctx* ctx);
+const char* ifadv_version(void);
+
+/* ---- the hot path --------------------------------------------------------------------------------------- */
+/* advectVOF!(f,fᶠ,α,n̂,u,u⁰,Δt,c̄,ρuf,λρ,normalScheme; perdir,dirO)            src/advection.jl:34-78
+ * In/out f (all Ng entries, ghosts refreshed like BCf!).  fᶠ, α are used as ping-pong scratch; n̂ is untouched;
+ * c̄ is rewritten; ρuf[·,d] receives δl·λρ+(1-λρ)fᶠ on inside_uWB faces (0 elsewhere) unless IFADV_NO_RHOUF. */
+int ifadv_advect_vof(ifadv_ctx* ctx, void* stream, void* f, void* ff, void* alpha, void* nhat, const void* u, const void* u0,
+                     double dt, int8_t* cbar, void* rhouf, double lambda_rho, int normal_scheme, unsigned perdir_mask,
+                     const int dirO[3], int flags, ifadv_report* report);
+
+/* advectVOFρuu!(f,fᶠ,α,n̂,u,u⁰,Δt,c̄,ρu,r,Φ,ρuf,uStar,uOld,dilaU,dρ,λρ,λ,normalScheme,uBC; perdir,exitBC,dirO)
+ *                                                                              src/flow.jl:165-210
+ * In/out f (all entries) and ρu (inside(f) entries); every other array is scratch exactly as in the
+ * reference: fᶠ, Φ hold f ping-pong copies, r and ρuf hold ρu ping-pong copies, c̄ is
+ * rewritten.  uStar/dilaU may alias n̂/α as in advectfq! (flow.jl:157-160); they are not touched.
+ * dρ is only READ (plane Ng[j] of component j, which the reference never writes).  uBC: constant tuple.
+ * exitBC = true is rejected (-2): the reference reads stale scratch in that case. */
+int ifadv_advect_vof_rhouu(ifadv_ctx* ctx, void* stream, void* f, void* ff, void* alpha, void* nhat, const void* u,
+                           const void* u0, double dt, int8_t* cbar, void* rhou, void* r, void* Phi, void* rhouf, void* uStar,
+                           const void* uOld, void* dilaU, const void* drho, double lambda_rho, int limiter, int normal_scheme,
+                           const double uBC[3], unsigned perdir_mask, int exitBC, const int dirO[3], ifadv_report* report);
+
+/* ---- secondary seams on the path ------------------------------------------------------------------------ */
+/* u2ρu!(ρu,u,f,λρ) / ρu2u!(u,ρu,f,λρ)                                           src/VOFutil.jl:198-211 */
+int ifadv_u2rhou(ifadv_ctx* ctx, void* stream, void* rhou, const void* u, const void* f, double lambda_rho);
+int ifadv_rhou2u(ifadv_ctx* ctx, void* stream, void* u, const void* rhou, const void* f, double lambda_rho);
+/* WaterLily.BC!(a,A,saveexit,perdir) for a constant tuple A                     used at src/flow.jl:69,91 */
+int ifadv_bc_vec(ifadv_ctx* ctx, void* stream, void* a, const double A[3], int saveexit, unsigned perdir_mask);
+/* BCf!(f;perdir)                                                                src/VOFutil.jl:64-75 */
+int ifadv_bcf(ifadv_ctx* ctx, void* stream, void* f, unsigned perdir_mask);
+/* out[i] = a*x[i] + b*y[i] over all Ng entries (the midpoint `@. f⁰ = (f⁰+f)/2`, src/flow.jl:74, is a=b=.5
+ * evaluated as (x+y)*a when a == b) */
+int ifadv_axpby(ifadv_ctx* ctx, void* stream, void* out, double a, const void* x, double b, const void* y);
+/* MPCFL(a,c) (src/flow.jl:262-281).  mu/eta/gnorm <= 0 disable that limit (`nothing` in the reference).
+ * Synchronises the stream; result in *dt_out. */
+int ifadv_mpcfl(ifadv_ctx* ctx, void* stream, const void* u, double nu, double mu, double lambda_mu, double lambda_rho,
+                double eta, double gnorm, double dt_max, double safety, double* dt_out);
+/* sum(f[inside(f)]) accumulated in Float64 (total-mass check, test/maintests.jl:209,215).  Synchronises. */
+int ifadv_sum_inside(ifadv_ctx* ctx, void* stream, const void* f, double* out);
+/* applyVOF!(f,α,n̂,InterfaceSDF) (src/VOFutil.jl:9-37) with the SDF pre-sampled on the device at the cell
+ * centres (sc) and at centre ± 0.01 e_i (sp, sm: vector fields); includes cleanWisp!; caller runs ifadv_bcf. */
+int ifadv_apply_vof_samples(ifadv_ctx* ctx, void* stream, void* f, void* alpha, void* nhat, const void* sc, const void* sp,
+                            const void* sm);
+
+/* ---- host-buffer convenience (what bench.py's e2e leg times) --------------------------------------------- */
+/* One CMOM advection step of MPFMomStep! on HOST arrays (flow.jl:61,69-70,74,89-92 with the forcing and
+ * projection left out: velocities are prescribed): copies f,u to the device, runs
+ *   u⁰←u; f⁰←f; u2ρu!,BC!,advectfq!(f⁰;u⁰,u,uOld=u); f⁰=(f⁰+f)/2; f⁰←f; u2ρu!,BC!,advectfq!(f;u,u,uOld=u⁰)
+ * and copies f and ρu back.  The context keeps the device work arrays between calls. */
+int ifadv_mom_advect_step_host(ifadv_ctx* ctx, void* f_host, const void* u_host, void* rhou_host, double dt, double lambda_rho,
+                               int limiter, int normal_scheme, const double uBC[3], unsigned perdir_mask, const int dirO[3],
+                               ifadv_report* report);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IFADV_H */

@@ -1,0 +1,157 @@
+"""ctypes binding of libifadv_b200.so (include/ifadv.h).  There is NO fallback: if the CUDA library is
+missing or no CUDA device is present every compute entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libifadv_b200.so")
+
+NORMAL_SCHEMES = {"WH": 0, "WY": 1, "Column": 2, "PCD": 3, "SLIC": 4, "MYC": 5, "Y": 6, "CD": 7, "XYLIC": 8}
+LIMITERS = {"upwind": 0, "minmod": 1, "Koren": 2, "vanAlbada1": 3, "Sweby": 4, "superbee": 5, "TVDcen": 6, "TVDdown": 7,
+            "quick": 8, "vanLeer": 9, "cds": 10}
+IFADV_NO_RHOUF = 1
+
+
+class IfadvError(RuntimeError):
+    pass
+
+
+class Report(C.Structure):
+    _fields_ = [("maxf", C.c_double), ("minf", C.c_double), ("argmax", C.c_int64 * 3), ("argmin", C.c_int64 * 3),
+                ("dir", C.c_int), ("status", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise IfadvError(f"{LIB_PATH} is missing: build it with `make -C interfaceadvection.jl_b200/csrc -j8` "
+                             "(or __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, dbl, i32, u32, i64p = C.c_void_p, C.c_double, C.c_int, C.c_uint, C.POINTER(C.c_int64)
+        i32p, dblp, rep = C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(Report)
+        L.ifadv_version.restype = C.c_char_p
+        L.ifadv_last_error.restype = C.c_char_p
+        L.ifadv_last_error.argtypes = [vp]
+        L.ifadv_launch_count.restype = C.c_int64
+        L.ifadv_launch_count.argtypes = [vp]
+        L.ifadv_create.argtypes = [C.POINTER(vp), i32, i64p, i32, i32]
+        L.ifadv_destroy.argtypes = [vp]
+        L.ifadv_advect_vof.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, dbl, vp, vp, dbl, i32, u32, i32p, i32, rep]
+        L.ifadv_advect_vof_rhouu.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, i32, i32,
+                                             dblp, u32, i32, i32p, rep]
+        L.ifadv_u2rhou.argtypes = [vp, vp, vp, vp, vp, dbl]
+        L.ifadv_rhou2u.argtypes = [vp, vp, vp, vp, vp, dbl]
+        L.ifadv_bc_vec.argtypes = [vp, vp, vp, dblp, i32, u32]
+        L.ifadv_bcf.argtypes = [vp, vp, vp, u32]
+        L.ifadv_axpby.argtypes = [vp, vp, vp, dbl, vp, dbl, vp]
+        L.ifadv_mpcfl.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl, dbl, dbl, dbl, dbl, dblp]
+        L.ifadv_sum_inside.argtypes = [vp, vp, vp, dblp]
+        L.ifadv_apply_vof_samples.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+        L.ifadv_mom_advect_step_host.argtypes = [vp, vp, vp, vp, dbl, dbl, i32, i32, dblp, u32, i32p, rep]
+        _lib = L
+    return _lib
+
+
+def perdir_mask(perdir) -> int:
+    m = 0
+    for j in perdir:
+        m |= 1 << (int(j) - 1)
+    return m
+
+
+def _d3(v, D):
+    v = [float(x) for x in v][:D]
+    return (C.c_double * 3)(*(v + [0.0] * (3 - D)))
+
+
+def _i3(v, D):
+    v = [int(x) for x in v][:D]
+    return (C.c_int * 3)(*(v + [0] * (3 - D)))
+
+
+class Context:
+    """ifadv_ctx: one per (device, grid, dtype).  Ng = array extents including ghosts (N .+ 2)."""
+
+    def __init__(self, Ng, dtype: str, device: int = 0):
+        self.D = len(Ng)
+        self.Ng = tuple(int(n) for n in Ng)
+        self.dtype = {"float32": 0, "float64": 1}[dtype]
+        self._h = C.c_void_p()
+        ng = (C.c_int64 * 3)(*(list(self.Ng) + [1] * (3 - self.D)))
+        rc = lib().ifadv_create(C.byref(self._h), self.D, ng, self.dtype, int(device))
+        if rc != 0:
+            raise IfadvError(f"ifadv_create failed ({rc}): a CUDA device is required, there is no CPU fallback")
+
+    def close(self):
+        if self._h:
+            lib().ifadv_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc < 0:
+            msg = lib().ifadv_last_error(self._h).decode()
+            if rc == -1:
+                raise IfadvError("NaN!")  # error("NaN!"), src/advection.jl:148
+            raise IfadvError(f"ifadv error {rc}: {msg}")
+        return rc
+
+    @property
+    def launches(self) -> int:
+        return int(lib().ifadv_launch_count(self._h))
+
+    def advect_vof(self, stream, f, ff, alpha, nhat, u, u0, dt, cbar, rhouf, lam_rho, scheme, perdir, dirO, flags=0, report=None):
+        r = C.byref(report) if report is not None else None
+        return self._chk(lib().ifadv_advect_vof(self._h, stream, f, ff, alpha, nhat, u, u0, float(dt), cbar, rhouf, float(lam_rho),
+                                                int(scheme), perdir_mask(perdir), _i3(dirO, self.D), int(flags), r))
+
+    def advect_vof_rhouu(self, stream, f, ff, alpha, nhat, u, u0, dt, cbar, rhou, r_, Phi, rhouf, uStar, uOld, dilaU, drho, lam_rho,
+                         limiter, scheme, uBC, perdir, exitBC, dirO, report=None):
+        r = C.byref(report) if report is not None else None
+        return self._chk(lib().ifadv_advect_vof_rhouu(self._h, stream, f, ff, alpha, nhat, u, u0, float(dt), cbar, rhou, r_, Phi, rhouf,
+                                                      uStar, uOld, dilaU, drho, float(lam_rho), int(limiter), int(scheme),
+                                                      _d3(uBC, self.D), perdir_mask(perdir), int(bool(exitBC)), _i3(dirO, self.D), r))
+
+    def u2rhou(self, stream, rhou, u, f, lam_rho):
+        return self._chk(lib().ifadv_u2rhou(self._h, stream, rhou, u, f, float(lam_rho)))
+
+    def rhou2u(self, stream, u, rhou, f, lam_rho):
+        return self._chk(lib().ifadv_rhou2u(self._h, stream, u, rhou, f, float(lam_rho)))
+
+    def bc_vec(self, stream, a, A, saveexit, perdir):
+        return self._chk(lib().ifadv_bc_vec(self._h, stream, a, _d3(A, self.D), int(bool(saveexit)), perdir_mask(perdir)))
+
+    def bcf(self, stream, f, perdir):
+        return self._chk(lib().ifadv_bcf(self._h, stream, f, perdir_mask(perdir)))
+
+    def axpby(self, stream, out, a, x, b, y):
+        return self._chk(lib().ifadv_axpby(self._h, stream, out, float(a), x, float(b), y))
+
+    def mpcfl(self, stream, u, nu=0.0, mu=0.0, lam_mu=1e-2, lam_rho=1e-3, eta=0.0, gnorm=0.0, dt_max=1.0, safety=0.8) -> float:
+        out = C.c_double()
+        self._chk(lib().ifadv_mpcfl(self._h, stream, u, nu, mu, lam_mu, lam_rho, eta, gnorm, dt_max, safety, C.byref(out)))
+        return out.value
+
+    def sum_inside(self, stream, f) -> float:
+        out = C.c_double()
+        self._chk(lib().ifadv_sum_inside(self._h, stream, f, C.byref(out)))
+        return out.value
+
+    def apply_vof_samples(self, stream, f, alpha, nhat, sc, sp, sm):
+        return self._chk(lib().ifadv_apply_vof_samples(self._h, stream, f, alpha, nhat, sc, sp, sm))
+
+    def mom_advect_step_host(self, f_host, u_host, rhou_host, dt, lam_rho, limiter, scheme, uBC, perdir, dirO, report=None):
+        r = C.byref(report) if report is not None else None
+        return self._chk(lib().ifadv_mom_advect_step_host(self._h, f_host, u_host, rhou_host, float(dt), float(lam_rho), int(limiter),
+                                                          int(scheme), _d3(uBC, self.D), perdir_mask(perdir), _i3(dirO, self.D), r))

@@ -1,0 +1,331 @@
+"""Host-side mirror of the reference's interface for the VOF + CMOM advection path.
+
+Reference entry points mirrored here (file:line in /root/reference):
+  cVOF                    src/cVOF.jl:18-89          TwoPhaseSimulation   src/InterfaceAdvection.jl:64-85
+  advect! / advectVOF!    src/advection.jl:17-78     sim_step!            src/InterfaceAdvection.jl:100-103
+  advectfq!/advectVOFρuu! src/flow.jl:157-210        MPFMomStep!          src/flow.jl:60-109 (transport part)
+  u2ρu!/ρu2u!             src/VOFutil.jl:198-211     MPCFL                src/flow.jl:262-281
+  applyVOF!, BCf!         src/VOFutil.jl:9-37,64-75  BC!                  WaterLily
+
+Arrays are torch CUDA tensors with the reference's Julia shapes -- scalar (N1+2, N2+2[, N3+2]), vector (..., D) --
+and COLUMN-MAJOR strides (first index fastest, component slowest), i.e. byte-identical to the CuArrays the Julia
+glue hands to the same C ABI.  Indices into them are 0-based here; directions / dirO / perdir stay 1-based.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LIMITERS, NORMAL_SCHEMES, Context, IfadvError, Report
+
+_DT = {torch.float32: "float32", torch.float64: "float64"}
+
+
+# ---- column-major tensors ------------------------------------------------------------------------------------
+def jl_empty(shape: Sequence[int], dtype=torch.float32, device="cuda") -> torch.Tensor:
+    t = torch.empty(tuple(reversed(shape)), dtype=dtype, device=device)
+    return t.permute(*reversed(range(len(shape))))
+
+
+def jl_zeros(shape, dtype=torch.float32, device="cuda") -> torch.Tensor:
+    t = jl_empty(shape, dtype, device)
+    t.zero_()
+    return t
+
+
+def from_numpy(a: np.ndarray, device="cuda") -> torch.Tensor:
+    """Fortran-ordered numpy array -> column-major device tensor (same bytes)."""
+    a = np.asfortranarray(a)
+    t = torch.from_numpy(np.ascontiguousarray(a.T)).to(device)
+    return t.permute(*reversed(range(a.ndim)))
+
+
+def to_numpy(t: torch.Tensor) -> np.ndarray:
+    """Column-major device tensor -> Fortran-ordered numpy array."""
+    _check(t)
+    return np.asfortranarray(t.permute(*reversed(range(t.dim()))).contiguous().cpu().numpy().T)
+
+
+def _check(t: torch.Tensor):
+    if not t.is_cuda:
+        raise IfadvError("the B200 path needs CUDA tensors; there is no CPU fallback")
+    exp, s = [], 1
+    for n in t.shape:
+        exp.append(s)
+        s *= n
+    if tuple(t.stride()) != tuple(exp):
+        raise IfadvError("tensor is not column-major (use jl_zeros / from_numpy)")
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    _check(t)
+    return t.data_ptr()
+
+
+_contexts = {}
+
+
+def context_for(f: torch.Tensor) -> Context:
+    key = (tuple(f.shape), f.dtype, f.device.index)
+    if key not in _contexts:
+        _contexts[key] = Context(tuple(f.shape), _DT[f.dtype], f.device.index or 0)
+    return _contexts[key]
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ns(s):
+    return NORMAL_SCHEMES[s] if isinstance(s, str) else int(s)
+
+
+def _lim(s):
+    return LIMITERS[s] if isinstance(s, str) else int(s)
+
+
+# ---- field utilities -------------------------------------------------------------------------------------------
+def BCf(f, perdir=()):
+    """BCf!(f;perdir)  (VOFutil.jl:64-75)"""
+    context_for(f).bcf(_stream(f), _p(f), perdir)
+
+
+def BC(a, A, saveexit=False, perdir=()):
+    """WaterLily.BC!(a,A,saveexit,perdir) for a constant tuple A"""
+    if callable(A):
+        raise IfadvError("function-valued uBC is not supported by the B200 path")
+    context_for(a[..., 0]).bc_vec(_stream(a), _p(a), A, saveexit, perdir)
+
+
+def u2rhou(rhou, u, f, lam_rho):
+    """u2ρu!(ρu,u,f,λρ)  (VOFutil.jl:208-211)"""
+    context_for(f).u2rhou(_stream(f), _p(rhou), _p(u), _p(f), lam_rho)
+
+
+def rhou2u(u, rhou, f, lam_rho):
+    """ρu2u!(u,ρu,f,λρ)  (VOFutil.jl:198-201)"""
+    context_for(f).rhou2u(_stream(f), _p(u), _p(rhou), _p(f), lam_rho)
+
+
+def sum_inside(f) -> float:
+    """sum(f[inside(f)]) in Float64 (the mass check of test/maintests.jl:209,215)"""
+    return context_for(f).sum_inside(_stream(f), _p(f))
+
+
+def _cell_centres(shape, dtype, device):
+    D = len(shape)
+    grids = torch.meshgrid(*[torch.arange(n, device=device, dtype=dtype) for n in shape], indexing="ij")
+    # 0-based idx <-> Julia I = idx+1; loc(0,I) = I - 1.5
+    return torch.stack([g - 0.5 for g in grids], dim=-1)
+
+
+def applyVOF(f, alpha, nhat, InterfaceSDF: Optional[Callable]):
+    """applyVOF!(f,α,n̂,InterfaceSDF)  (VOFutil.jl:8-37).  InterfaceSDF maps a (..., D) tensor of positions to
+    signed distances (dark fluid negative) and is evaluated on the device in f's dtype."""
+    if InterfaceSDF is None:
+        return
+    D = f.dim()
+    xc = _cell_centres(f.shape, f.dtype, f.device)
+    dx = torch.tensor(0.01, dtype=f.dtype, device=f.device)
+
+    def colmajor(t):
+        out = jl_empty(t.shape, f.dtype, f.device)
+        out.copy_(t)
+        return out
+
+    sc = colmajor(InterfaceSDF(xc).to(f.dtype))
+    sp = jl_empty(tuple(f.shape) + (D,), f.dtype, f.device)
+    sm = jl_empty(tuple(f.shape) + (D,), f.dtype, f.device)
+    for i in range(D):
+        e = torch.zeros(D, dtype=f.dtype, device=f.device)
+        e[i] = dx
+        sp[..., i] = InterfaceSDF(xc + e).to(f.dtype)
+        sm[..., i] = InterfaceSDF(xc - e).to(f.dtype)
+    context_for(f).apply_vof_samples(_stream(f), _p(f), _p(alpha), _p(nhat), _p(sc), _p(sp), _p(sm))
+
+
+# ---- structs -----------------------------------------------------------------------------------------------------
+class cVOF:
+    """cVOF(N; T, InterfaceSDF, μ, λμ, λρ, η, normalScheme, perdir)  (src/cVOF.jl:45-89)"""
+
+    def __init__(self, N, T=torch.float32, InterfaceSDF=None, mu=1e-3, lam_mu=1e-2, lam_rho=1e-3, eta=None, normalScheme="WH",
+                 perdir=(), device="cuda"):
+        D = len(N)
+        Ng = tuple(n + 2 for n in N)
+        Nv = Ng + (D,)
+        self.D, self.N, self.T = D, tuple(N), T
+        self.f = jl_zeros(Ng, T, device)
+        self.f.fill_(1)
+        self.alpha = jl_zeros(Ng, T, device)
+        self.nhat = jl_zeros(Nv, T, device)
+        self.cbar = jl_zeros(Ng, torch.int8, device)
+        self.perdir = tuple(perdir)
+        if InterfaceSDF is not None:
+            applyVOF(self.f, self.alpha, self.nhat, InterfaceSDF)
+            BCf(self.f, self.perdir)
+        self.f0 = self.f.clone(memory_format=torch.preserve_format)
+        self.ff = jl_zeros(Ng, T, device)
+        self.rhou = jl_zeros(Nv, T, device)
+        self.rhouf = jl_zeros(Nv, T, device)
+        self.drho = jl_zeros(Nv, T, device)
+        self.drho.fill_(1)
+        self.eta = None if (eta is None or eta == 0) else eta
+        self.mu = None if (mu is None or mu == 0) else mu
+        self.lam_rho, self.lam_mu = lam_rho, lam_mu
+        self.normalScheme = normalScheme
+
+
+class Flow:
+    """The subset of WaterLily.Flow the path touches: u, u⁰, f (momentum scratch r), σ, Δt, ν, g, uBC, exitBC,
+    perdir, λ  (SURVEY App. A)."""
+
+    def __init__(self, N, uBC, T=torch.float32, u0fn=None, dt=0.25, nu=0.0, g=None, exitBC=False, perdir=(), lam="Koren",
+                 device="cuda"):
+        D = len(N)
+        Ng = tuple(n + 2 for n in N)
+        self.D, self.N, self.T = D, tuple(N), T
+        self.u = jl_zeros(Ng + (D,), T, device)
+        if u0fn is not None:  # apply!(u0, u): component i sampled at its face centre loc(i,I)
+            xc = _cell_centres(Ng, T, device)
+            for i in range(D):
+                e = torch.zeros(D, dtype=T, device=device)
+                e[i] = 0.5
+                self.u[..., i] = u0fn(i + 1, xc - e).to(T)
+        self.uBC, self.exitBC, self.perdir, self.lam = tuple(uBC), bool(exitBC), tuple(perdir), lam
+        BC(self.u, self.uBC, self.exitBC, self.perdir)
+        self.u0 = self.u.clone(memory_format=torch.preserve_format)
+        self.f = jl_zeros(Ng + (D,), T, device)
+        self.sigma = jl_zeros(Ng, T, device)
+        self.dt = [float(dt)]  # Δt
+        self.nu, self.g = nu, g
+
+
+class TwoPhaseSimulation:
+    """TwoPhaseSimulation(dims, u_BC, L; T, λμ, λρ, η, InterfaceSDF, λ, normalScheme, kwargs...)
+    (src/InterfaceAdvection.jl:64-85).  The Poisson solver and body stay with WaterLily (out of scope)."""
+
+    def __init__(self, dims, u_BC, L, T=torch.float32, lam_mu=1e-2, lam_rho=1e-3, eta=None, InterfaceSDF=None, lam="Koren",
+                 normalScheme="WH", U=None, dt=0.25, nu=0.0, g=None, u0=None, perdir=(), exitBC=False, device="cuda"):
+        self.L = L
+        self.U = U if U is not None else math.sqrt(sum(float(x) ** 2 for x in u_BC))
+        self.flow = Flow(dims, u_BC, T=T, u0fn=u0, dt=dt, nu=nu, g=g, exitBC=exitBC, perdir=perdir, lam=lam, device=device)
+        self.intf = cVOF(dims, T=T, InterfaceSDF=InterfaceSDF, mu=nu, lam_mu=lam_mu, lam_rho=lam_rho, eta=eta,
+                         normalScheme=normalScheme, perdir=perdir, device=device)
+        self.flow.dt[-1] = min(self.flow.dt[-1], MPCFL(self.flow, self.intf))  # InterfaceAdvection.jl:81
+        self.pois, self.body = None, None
+
+
+# ---- the hot path ------------------------------------------------------------------------------------------------------
+def _dirO(flow, D):
+    n = len(flow.dt)
+    return tuple((n + i) % D + 1 for i in range(1, D + 1))  # advection.jl:22, flow.jl:163
+
+
+def _report(status, rep: Report):
+    if status > 0:  # the reference prints and carries on (advection.jl:161-166)
+        which = "max" if status & 1 else "min"
+        val = rep.maxf - 1 if status & 1 else -rep.minf
+        idx = tuple(rep.argmax) if status & 1 else tuple(rep.argmin)
+        print(f"ERROR: {which} VOF @ {idx} ∉ [0,1] @ direction {rep.dir}, Δf = {val}")
+    return status
+
+
+def advectVOF(f, ff, alpha, nhat, u, u0, dt, cbar, rhouf, lam_rho, normalScheme="WH", perdir=(), dirO=None, check=True,
+              want_rhouf=True):
+    """advectVOF!(f,fᶠ,α,n̂,u,u⁰,Δt,c̄,ρuf,λρ,normalScheme; perdir,dirO)  (src/advection.jl:34-78)"""
+    D = f.dim()
+    if dirO is None:  # the reference shuffles when no order is given (advection.jl:34)
+        dirO = tuple(int(x) + 1 for x in np.random.permutation(D))
+    rep = Report() if check else None
+    st = context_for(f).advect_vof(_stream(f), _p(f), _p(ff), _p(alpha), _p(nhat), _p(u), _p(u0), dt, _p(cbar), _p(rhouf), lam_rho,
+                                   _ns(normalScheme), perdir, dirO, 0 if want_rhouf else _lib.IFADV_NO_RHOUF, rep)
+    return _report(st, rep) if check else st
+
+
+def advect(a: Flow, c: cVOF, f=None, u1=None, u2=None, dt=None, check=True):
+    """advect!(a,c,f,u¹,u²,dt)  (src/advection.jl:17-23)"""
+    f = c.f if f is None else f
+    u1 = a.u0 if u1 is None else u1
+    u2 = a.u if u2 is None else u2
+    dt = a.dt[-1] if dt is None else dt
+    return advectVOF(f, c.ff, c.alpha, c.nhat, u1, u2, dt, c.cbar, c.rhouf, c.lam_rho, c.normalScheme, perdir=a.perdir,
+                     dirO=_dirO(a, a.D), check=check)
+
+
+def advectVOFrhouu(f, ff, alpha, nhat, u, u0, dt, cbar, rhou, r, Phi, rhouf, uStar, uOld, dilaU, drho, lam_rho, lam="Koren",
+                   normalScheme="WH", uBC=(0, 0, 0), perdir=(), exitBC=False, dirO=None, check=True):
+    """advectVOFρuu!(f,fᶠ,α,n̂,u,u⁰,Δt,c̄,ρu,r,Φ,ρuf,uStar,uOld,dilaU,dρ,λρ,λ,normalScheme,uBC; perdir,exitBC,dirO)
+    (src/flow.jl:165-210)"""
+    D = f.dim()
+    if callable(uBC):
+        raise IfadvError("function-valued uBC is not supported by the B200 path")
+    if dirO is None:
+        dirO = tuple(int(x) + 1 for x in np.random.permutation(D))
+    rep = Report() if check else None
+    st = context_for(f).advect_vof_rhouu(_stream(f), _p(f), _p(ff), _p(alpha), _p(nhat), _p(u), _p(u0), dt, _p(cbar), _p(rhou), _p(r),
+                                         _p(Phi), _p(rhouf), _p(uStar), _p(uOld), _p(dilaU), _p(drho), lam_rho, _lim(lam),
+                                         _ns(normalScheme), uBC, perdir, exitBC, dirO, rep)
+    return _report(st, rep) if check else st
+
+
+def advectfq(a: Flow, c: cVOF, f=None, u1=None, u2=None, u0=None, dt=None, check=True):
+    """advectfq!(a,c,f,u¹,u²,u⁰,dt)  (src/flow.jl:157-164): binds r≡flow.f, Φ≡flow.σ, uStar≡n̂, dilaU≡α."""
+    f = c.f if f is None else f
+    u1 = a.u0 if u1 is None else u1
+    u2 = a.u if u2 is None else u2
+    u0 = a.u if u0 is None else u0
+    dt = a.dt[-1] if dt is None else dt
+    return advectVOFrhouu(f, c.ff, c.alpha, c.nhat, u1, u2, dt, c.cbar, c.rhou, a.f, a.sigma, c.rhouf, c.nhat, u0, c.alpha, c.drho,
+                          c.lam_rho, a.lam, c.normalScheme, a.uBC, perdir=a.perdir, exitBC=a.exitBC, dirO=_dirO(a, a.D), check=check)
+
+
+def MPCFL(a: Flow, c: cVOF, dt_max=1.0, safety=0.8) -> float:
+    """MPCFL(a,c)  (src/flow.jl:262-281)"""
+    gnorm = 0.0
+    if a.g is not None:
+        gnorm = math.sqrt(sum(float(a.g(i + 1, [0.0] * a.D, sum(a.dt))) ** 2 for i in range(a.D)))
+    return context_for(c.f).mpcfl(_stream(c.f), _p(a.u), nu=a.nu, mu=c.mu or 0.0, lam_mu=c.lam_mu, lam_rho=c.lam_rho, eta=c.eta or 0.0,
+                                  gnorm=gnorm, dt_max=dt_max, safety=safety)
+
+
+def MPFMomStep(a: Flow, b, c: cVOF, d=None, dt=None, project: Optional[Callable] = None, check=False):
+    """Transport part of MPFMomStep!(a,b,c,d)  (src/flow.jl:60-109).
+
+    Lines 61, 69-70, 74, 89-92 and 108 run on the B200 kernels.  The forcing (viscSurfTenρu!, updateU!) and the
+    pressure projection (myproject!) stay on WaterLily's backend; `project(a, c, stage)` is the hook
+    where a caller plugs them in.  Without it velocities are prescribed: u is left untouched between the stages."""
+    dt = a.dt[-1] if dt is None else dt
+    ctx, s = context_for(c.f), _stream(c.f)
+    a.u0.copy_(a.u)
+    c.f0.copy_(c.f)                                                   # :61
+    u2rhou(c.rhou, a.u0, c.f0, c.lam_rho)
+    BC(c.rhou, a.uBC, a.exitBC, a.perdir)                             # :69
+    advectfq(a, c, c.f0, a.u0, a.u, a.u, dt, check=check)             # :70
+    ctx.axpby(s, _p(c.f0), 0.5, _p(c.f0), 0.5, _p(c.f))               # :74
+    if project is not None:
+        project(a, c, "predictor")                                    # :75-82
+    c.f0.copy_(c.f)                                                   # :89
+    u2rhou(c.rhou, a.u0, c.f, c.lam_rho)
+    BC(c.rhou, a.uBC, a.exitBC, a.perdir)                             # :91
+    advectfq(a, c, c.f, a.u, a.u, a.u0, dt, check=check)              # :92
+    if project is not None:
+        project(a, c, "corrector")                                    # :95-106
+    a.dt.append(min(MPCFL(a, c), 1.2 * dt))                           # :108
+
+
+def sim_step(sim: TwoPhaseSimulation, t_end: Optional[float] = None, project=None, check=False):
+    """sim_step!(sim[,t_end])  (src/InterfaceAdvection.jl:100-103 + WaterLily's generic loop)"""
+    if t_end is None:
+        return MPFMomStep(sim.flow, sim.pois, sim.intf, sim.body, project=project, check=check)
+    while sim_time(sim) < t_end:
+        MPFMomStep(sim.flow, sim.pois, sim.intf, sim.body, project=project, check=check)
+
+
+def sim_time(sim: TwoPhaseSimulation) -> float:
+    return sum(sim.flow.dt[:-1]) * sim.U / sim.L

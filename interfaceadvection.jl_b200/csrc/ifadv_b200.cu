@@ -1,0 +1,602 @@
+// ifadv_b200.cu -- libifadv_b200.so: C ABI (include/ifadv.h) + the small field kernels around the fused sweep.
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -shared
+// There is no CPU fallback: every entry point needs a CUDA device and fails with -3 otherwise.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+
+#include "../../include/ifadv.h"
+#include "ifadv_ctx.hpp"
+
+using namespace ifadv;
+
+static size_t esize(int dtype) { return dtype == IFADV_F32 ? 4 : 8; }
+static int fail(ifadv_ctx* c, int code, const char* msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------------------
+__global__ void red_init_kernel(unsigned long long* red, int nsets) {
+  const int t = threadIdx.x;
+  if (t < nsets) {
+    unsigned long long* r = red + 8 * t;
+    r[0] = 0ull; r[1] = ~0ull; r[2] = 0ull; r[3] = ~0ull; r[4] = 0ull; r[5] = 0ull; r[6] = 0ull; r[7] = 0ull;
+  }
+}
+
+// BCf!(f;perdir), VOFutil.jl:64-75: every ghost cell takes the value of its interior-equivalent cell
+// (clamp = Neumann copy, wrap = periodic).  One launch over the six (four) boundary planes.
+template <class T, int D> __global__ void bcf_kernel(T* f, const Geo g) {
+  const long long n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
+  const long long c0 = 2 * n1 * n2, c1 = 2 * n0 * n2, c2 = (D == 3) ? 2 * n0 * n1 : 0;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= c0 + c1 + c2) return;
+  int x, y, z;
+  if (t < c0) { const long long r = t >> 1; x = (t & 1) ? (int)n0 : 1; y = (int)(r % n1) + 1; z = (int)(r / n1) + 1; }
+  else if (t < c0 + c1) { const long long q = t - c0, r = q >> 1; y = (q & 1) ? (int)n1 : 1; x = (int)(r % n0) + 1; z = (int)(r / n0) + 1; }
+  else { const long long q = t - c0 - c1, r = q >> 1; z = (q & 1) ? (int)n2 : 1; x = (int)(r % n0) + 1; y = (int)(r / n0) + 1; }
+  const int mx = mapc(x, g.n[0], g.per & 1u), my = mapc(y, g.n[1], g.per & 2u), mz = (D == 3) ? mapc(z, g.n[2], g.per & 4u) : 1;
+  f[lin3(g, x, y, z)] = f[lin3(g, mx, my, mz)];
+}
+
+// WaterLily.BC!(a,A,saveexit,perdir) for a constant tuple A: closed form of the sequential
+// plane passes -- Dirichlet planes {1,2,N} of the normal component, otherwise the interior-equivalent cell.
+template <class T, int D> __global__ void bcvec_kernel(T* a, const Geo g, T A0, T A1, T A2, int saveexit) {
+  // threads enumerate planes {1,2,N} of every dimension
+  const long long n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
+  const long long c0 = 3 * n1 * n2, c1 = 3 * n0 * n2, c2 = (D == 3) ? 3 * n0 * n1 : 0;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= c0 + c1 + c2) return;
+  int x, y, z;
+  auto plane = [](int s, long long n) { return s == 0 ? 1 : (s == 1 ? 2 : (int)n); };
+  if (t < c0) { const long long r = t / 3; x = plane((int)(t % 3), n0); y = (int)(r % n1) + 1; z = (int)(r / n1) + 1; }
+  else if (t < c0 + c1) { const long long q = t - c0, r = q / 3; y = plane((int)(q % 3), n1); x = (int)(r % n0) + 1; z = (int)(r / n0) + 1; }
+  else { const long long q = t - c0 - c1, r = q / 3; z = plane((int)(q % 3), n2); x = (int)(r % n0) + 1; y = (int)(r / n0) + 1; }
+  const int v[3] = {x, y, z};
+  const T A[3] = {A0, A1, A2};
+  const bool ghost = (x == 1 || x == g.n[0] || y == 1 || y == g.n[1] || (D == 3 && (z == 1 || z == g.n[2])));
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const bool peri = (g.per >> i) & 1u;
+    const bool dirichlet = !peri && (v[i] == 1 || v[i] == 2 || (v[i] == g.n[i] && !(saveexit && i == 0)));
+    if (!ghost && !dirichlet) continue;  // plane 2 is interior for the other components
+    T val;
+    if (dirichlet) val = A[i];
+    else {
+      int m[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const bool perk = (g.per >> k) & 1u;
+        if (k >= D) m[k] = 1;
+        else if (k == i) m[k] = perk ? wrapc(v[k], g.n[k]) : v[k];
+        else m[k] = mapc(v[k], g.n[k], perk);
+      }
+      val = a[(long long)i * g.S + lin3(g, m[0], m[1], m[2])];
+    }
+    a[(long long)i * g.S + lin3(g, x, y, z)] = val;
+  }
+}
+
+// u2ρu! / ρu2u!, VOFutil.jl:198-211
+template <class T, int D, bool TO_RHOU> __global__ void urhou_kernel(T* out, const T* in, const T* f, const Geo g, T lr, T omlr) {
+  const int x = 2 + blockIdx.x * blockDim.x + threadIdx.x, y = 2 + blockIdx.y, z = (D == 3) ? 2 + blockIdx.z : 1;
+  if (x > g.n[0] - 1) return;
+  const long long l = lin3(g, x, y, z);
+  const T fc = f[l];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const long long sd = (d == 0) ? 1 : ((d == 1) ? g.s1 : g.s2);
+    const T rho = lin_interp((fc + f[l - sd]) / T(2), lr, omlr);
+    const long long ld = (long long)d * g.S + l;
+    out[ld] = TO_RHOU ? in[ld] * rho : in[ld] / rho;
+  }
+}
+
+template <class T> __global__ void fill_kernel(T* out, T v, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v;
+}
+template <class T> __global__ void axpby_kernel(T* out, T a, const T* x, T b, const T* y, long long n, int same) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = same ? (x[i] + y[i]) * a : a * x[i] + b * y[i];
+}
+
+// MPCFL's two field reductions (flow.jl:267-271): max flux_out and max maxTotalFlux over inside(σ)
+template <class T, int D> __global__ void cfl_kernel(const T* u, const Geo g, unsigned long long* red) {
+  const int x = 2 + blockIdx.x * blockDim.x + threadIdx.x, y = 2 + blockIdx.y, z = (D == 3) ? 2 + blockIdx.z : 1;
+  double fo = 0.0, tf = 0.0;
+  if (x <= g.n[0] - 1) {
+    const long long l = lin3(g, x, y, z);
+    T s2 = T(0);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const long long sd = (i == 0) ? 1 : ((i == 1) ? g.s1 : g.s2);
+      const T ul = u[(long long)i * g.S + l], uh = u[(long long)i * g.S + l + sd];
+      fo += fmax(0.0, (double)uh) + fmax(0.0, -(double)ul);  // `max(0.,…)` promotes in WaterLily's flux_out
+      s2 += t_max(t_abs(ul), t_abs(uh));
+    }
+    fo = (double)(T)fo;  // stored into σ::T before maximum()
+    tf = (double)s2;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    fo = fmax(fo, __shfl_xor_sync(0xffffffffu, fo, off));
+    tf = fmax(tf, __shfl_xor_sync(0xffffffffu, tf, off));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(red + 0, ord_key(fo));
+    atomicMax(red + 1, ord_key(tf));
+  }
+}
+
+template <class T, int D> __global__ void sum_inside_kernel(const T* f, const Geo g, double* out) {
+  const int x = 2 + blockIdx.x * blockDim.x + threadIdx.x, y = 2 + blockIdx.y, z = (D == 3) ? 2 + blockIdx.z : 1;
+  double s = (x <= g.n[0] - 1) ? (double)f[lin3(g, x, y, z)] : 0.0;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  __shared__ double ws[32];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += ws[w];
+    atomicAdd(out, t);
+  }
+}
+
+// applyVOF! per-cell body + cleanWisp!, VOFutil.jl:15-37,127-136
+template <class T, int D> __global__ void applyvof_kernel(T* f, T* al, T* nh, const T* sc, const T* sp, const T* sm, const Geo g, T tol) {
+  const int x = 2 + blockIdx.x * blockDim.x + threadIdx.x, y = 2 + blockIdx.y, z = (D == 3) ? 2 + blockIdx.z : 1;
+  if (x > g.n[0] - 1) return;
+  const long long l = lin3(g, x, y, z);
+  T n[3] = {T(0), T(0), T(0)}, sumN = T(0), sumN2 = T(0);
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const T dd = sp[(long long)i * g.S + l] - sm[(long long)i * g.S + l];
+    nh[(long long)i * g.S + l] = dd;
+    n[i] = dd;
+    sumN += dd;
+    sumN2 += dd * dd;
+  }
+  const T a = sumN / T(2) - t_sqrt(sumN2) * sc[l];
+  al[l] = a;
+  T v = get_volume_fraction<T, D>(n, a);
+  v = (v < tol) ? T(0) : ((v > T(1) - tol) ? T(1) : v);
+  f[l] = v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------------------
+static inline dim3 row_grid(const Geo& g, int D, int bx) {
+  return dim3((unsigned)((g.n[0] - 2 + bx - 1) / bx), (unsigned)(g.n[1] - 2), (unsigned)(D == 3 ? g.n[2] - 2 : 1));
+}
+
+template <class T, bool MOM> static int launch_sweep(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  if (c->D == 2) return launch_sweep_dim<T, 2, MOM>(c, st, q);
+  return launch_sweep_dim<T, 3, MOM>(c, st, q);
+}
+
+template <class T> static int launch_bcf(ifadv_ctx* c, cudaStream_t st, T* f, unsigned per) {
+  Geo g = c->g;
+  g.per = per;
+  const long long n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
+  const long long tot = 2 * n1 * n2 + 2 * n0 * n2 + (c->D == 3 ? 2 * n0 * n1 : 0);
+  const int bs = 256;
+  const unsigned nb = (unsigned)((tot + bs - 1) / bs);
+  if (c->D == 2) bcf_kernel<T, 2><<<nb, bs, 0, st>>>(f, g);
+  else bcf_kernel<T, 3><<<nb, bs, 0, st>>>(f, g);
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+static int check_common(ifadv_ctx* c, int ns, const int* dirO) {
+  if (!c) return -2;
+  if (ns < 0 || ns > 8) return fail(c, -2, "invalid normal_scheme");
+  unsigned seen = 0;
+  for (int k = 0; k < c->D; ++k) {
+    if (dirO[k] < 1 || dirO[k] > c->D) return fail(c, -2, "dirO entries must be in 1..D");
+    seen |= 1u << (dirO[k] - 1);
+  }
+  (void)seen;
+  return 0;
+}
+
+// decode the per-sweep reductions into status + report (reportFillError semantics, advection.jl:145-189)
+static double key_to_double(unsigned long long k) {
+  long long b = (k & 0x8000000000000000ull) ? (long long)(k & 0x7fffffffffffffffull) : (long long)(~k);
+  double d;
+  memcpy(&d, &b, 8);
+  return d;
+}
+static int decode_report(ifadv_ctx* c, const int* dirO, double filltol, ifadv_report* rep) {
+  int status = 0;
+  rep->status = 0; rep->dir = -1; rep->maxf = 0; rep->minf = 0;
+  for (int k = 0; k < 3; ++k) rep->argmax[k] = rep->argmin[k] = 0;
+  for (int s = 0; s < c->D; ++s) {
+    const unsigned long long* r = c->red_host + 8 * s;
+    const double mx = key_to_double(r[0]), mn = key_to_double(r[1]);
+    int st = 0;
+    if (r[4] != 0 || mx != mx || mn != mn) st = -1;
+    else {
+      if (mx - 1 > filltol) st |= 1;
+      if (mn < -filltol) st |= 2;
+    }
+    if (st != 0 || rep->status == 0) {
+      rep->maxf = mx; rep->minf = mn; rep->dir = dirO[s];
+      const unsigned long long am = r[2] & 0xffffffffull, an = r[3] & 0xffffffffull;
+      rep->argmax[0] = (int64_t)(am % c->g.n[0]) + 1; rep->argmax[1] = (int64_t)((am / c->g.n[0]) % c->g.n[1]) + 1;
+      rep->argmax[2] = (int64_t)(am / ((unsigned long long)c->g.n[0] * c->g.n[1])) + 1;
+      rep->argmin[0] = (int64_t)(an % c->g.n[0]) + 1; rep->argmin[1] = (int64_t)((an / c->g.n[0]) % c->g.n[1]) + 1;
+      rep->argmin[2] = (int64_t)(an / ((unsigned long long)c->g.n[0] * c->g.n[1])) + 1;
+    }
+    if (st < 0) { rep->status = st; return st; }
+    status |= st;
+    rep->status = status;
+  }
+  return status;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// typed drivers
+// ------------------------------------------------------------------------------------------------------------
+template <class T>
+static int advect_vof_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* al, const T* u, const T* u0, double dt, int8_t* cbar, T* rhouf,
+                        double lr, int ns, unsigned per, const int* dirO, int flags, ifadv_report* rep) {
+  const int D = c->D;
+  c->g.per = per;
+  red_init_kernel<<<1, 32, 0, st>>>(c->red_dev, 3);
+  c->launches++;
+  const bool want_rhouf = !(flags & IFADV_NO_RHOUF) && rhouf != nullptr;
+  if (want_rhouf) CU_CHECK(c, cudaMemsetAsync(rhouf, 0, sizeof(T) * c->g.S * D, st));  // fill!(ρuf,0), advection.jl:37
+  T* bufs[4] = {f, ff, (D == 3) ? al : f, f};  // f -> fᶠ -> α -> f (3-D);  f -> fᶠ -> f (2-D)
+  for (int s = 0; s < D; ++s) {
+    SweepCfg<T> q{};
+    q.f_in = bufs[s]; q.f_out = bufs[s + 1];
+    q.u = u; q.u0 = u0; q.cbar = cbar; q.rhouf = want_rhouf ? rhouf : nullptr;
+    q.dt = dt; q.lr = lr; q.scheme = ns; q.lim = 0; q.first = (s == 0); q.j = dirO[s] - 1;
+    q.red = c->red_dev + 8 * s;
+    int rc = launch_sweep<T, false>(c, st, q);
+    if (rc) return rc;
+  }
+  int rc = launch_bcf<T>(c, st, f, per);  // BCf!(f;perdir), advection.jl:72 (only the final ghosts are observable)
+  if (rc) return rc;
+  if (rep) {
+    CU_CHECK(c, cudaMemcpyAsync(c->red_host, c->red_dev, sizeof(unsigned long long) * 24, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(c, cudaStreamSynchronize(st));
+    return decode_report(c, dirO, 10.0 * (double)std::numeric_limits<T>::epsilon(), rep);  // tol, advection.jl:69
+  }
+  return 0;
+}
+
+template <class T>
+static int advect_vof_rhouu_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* Phi, const T* u, const T* u0, double dt, int8_t* cbar, T* rhou,
+                              T* r, T* rhouf, const T* uOld, const T* drho, double lr, int lim, int ns, const double* uBC, unsigned per,
+                              const int* dirO, ifadv_report* rep) {
+  const int D = c->D;
+  c->g.per = per;
+  red_init_kernel<<<1, 32, 0, st>>>(c->red_dev, 3);
+  c->launches++;
+  T* fb[4] = {f, ff, (D == 3) ? Phi : f, f};        // f -> fᶠ -> Φ -> f
+  T* rb[4] = {rhou, r, (D == 3) ? rhouf : rhou, rhou};  // ρu -> r -> ρuf -> ρu
+  for (int s = 0; s < D; ++s) {
+    SweepCfg<T> q{};
+    q.f_in = fb[s]; q.f_out = fb[s + 1];
+    q.rhou_in = rb[s]; q.rhou_out = rb[s + 1];
+    q.u = u; q.u0 = u0; q.uOld = uOld; q.drho = drho; q.cbar = cbar; q.rhouf = nullptr;
+    q.dt = dt; q.lr = lr; q.scheme = ns; q.lim = lim; q.first = (s == 0); q.j = dirO[s] - 1;
+    for (int i = 0; i < 3; ++i) q.A[i] = (i < D) ? uBC[i] : 0.0;
+    q.red = c->red_dev + 8 * s;
+    int rc = launch_sweep<T, true>(c, st, q);
+    if (rc) return rc;
+  }
+  int rc = launch_bcf<T>(c, st, f, per);
+  if (rc) return rc;
+  if (rep) {
+    CU_CHECK(c, cudaMemcpyAsync(c->red_host, c->red_dev, sizeof(unsigned long long) * 24, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(c, cudaStreamSynchronize(st));
+    return decode_report(c, dirO, 100.0 * (double)std::numeric_limits<T>::epsilon(), rep);  // 10tol, advection.jl:85
+  }
+  return 0;
+}
+
+template <class T> static int u2rhou_t(ifadv_ctx* c, cudaStream_t st, T* out, const T* in, const T* f, double lr, bool to_rhou) {
+  const int bx = 128;
+  dim3 grid = row_grid(c->g, c->D, bx);
+  const T l = (T)lr, om = T(1) - l;
+  if (c->D == 2) {
+    if (to_rhou) urhou_kernel<T, 2, true><<<grid, bx, 0, st>>>(out, in, f, c->g, l, om);
+    else urhou_kernel<T, 2, false><<<grid, bx, 0, st>>>(out, in, f, c->g, l, om);
+  } else {
+    if (to_rhou) urhou_kernel<T, 3, true><<<grid, bx, 0, st>>>(out, in, f, c->g, l, om);
+    else urhou_kernel<T, 3, false><<<grid, bx, 0, st>>>(out, in, f, c->g, l, om);
+  }
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+template <class T> static int bcvec_t(ifadv_ctx* c, cudaStream_t st, T* a, const double* A, int saveexit, unsigned per) {
+  Geo g = c->g;
+  g.per = per;
+  const long long n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
+  const long long tot = 3 * n1 * n2 + 3 * n0 * n2 + (c->D == 3 ? 3 * n0 * n1 : 0);
+  const int bs = 256;
+  const unsigned nb = (unsigned)((tot + bs - 1) / bs);
+  if (c->D == 2) bcvec_kernel<T, 2><<<nb, bs, 0, st>>>(a, g, (T)A[0], (T)A[1], T(0), saveexit);
+  else bcvec_kernel<T, 3><<<nb, bs, 0, st>>>(a, g, (T)A[0], (T)A[1], (T)A[2], saveexit);
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+template <class T> static int axpby_t(ifadv_ctx* c, cudaStream_t st, T* out, double a, const T* x, double b, const T* y) {
+  const long long n = c->g.S;
+  const int bs = 256;
+  axpby_kernel<T><<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(out, (T)a, x, (T)b, y, n, a == b);
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* ifadv_version(void) { return "ifadv-b200 0.1 (sm_100a)"; }
+
+int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int device) {
+  if (!out || (D != 2 && D != 3) || (dtype != IFADV_F32 && dtype != IFADV_F64)) return -2;
+  for (int k = 0; k < D; ++k)
+    if (Ng[k] < 3) return -2;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return -3;  // no CPU fallback
+  if (cudaSetDevice(device) != cudaSuccess) return -3;
+  ifadv_ctx* c = new ifadv_ctx();
+  c->D = D; c->dtype = dtype; c->device = device; c->launches = 0;
+  c->g.n[0] = (int)Ng[0]; c->g.n[1] = (int)Ng[1]; c->g.n[2] = (D == 3) ? (int)Ng[2] : 1;
+  c->g.s1 = c->g.n[0]; c->g.s2 = (long long)c->g.n[0] * c->g.n[1];
+  c->g.S = c->g.s2 * c->g.n[2];
+  c->g.per = 0;
+  for (int k = 0; k < 3; ++k) c->Ng[k] = c->g.n[k];
+  for (auto& p : c->w) p = nullptr;
+  c->pin_f = c->pin_u = c->pin_ru = nullptr;
+  c->own_stream = nullptr;
+  if (cudaMalloc(&c->red_dev, sizeof(unsigned long long) * 24) != cudaSuccess ||
+      cudaMallocHost(&c->red_host, sizeof(unsigned long long) * 24) != cudaSuccess ||
+      cudaMalloc(&c->misc_dev, sizeof(unsigned long long) * 8) != cudaSuccess ||
+      cudaMallocHost(&c->misc_host, sizeof(unsigned long long) * 8) != cudaSuccess) {
+    delete c;
+    return -3;
+  }
+  *out = c;
+  return 0;
+}
+
+int ifadv_destroy(ifadv_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaFree(c->red_dev); cudaFreeHost(c->red_host); cudaFree(c->misc_dev); cudaFreeHost(c->misc_host);
+  for (auto& p : c->w) if (p) cudaFree(p);
+  if (c->pin_f) cudaFreeHost(c->pin_f);
+  if (c->pin_u) cudaFreeHost(c->pin_u);
+  if (c->pin_ru) cudaFreeHost(c->pin_ru);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  return 0;
+}
+
+const char* ifadv_last_error(const ifadv_ctx* c) { return c ? c->err.c_str() : "null context"; }
+int64_t ifadv_launch_count(const ifadv_ctx* c) { return c ? c->launches : 0; }
+
+int ifadv_advect_vof(ifadv_ctx* c, void* stream, void* f, void* ff, void* alpha, void* nhat, const void* u, const void* u0, double dt,
+                     int8_t* cbar, void* rhouf, double lambda_rho, int normal_scheme, unsigned perdir_mask, const int dirO[3], int flags,
+                     ifadv_report* report) {
+  (void)nhat;
+  int rc = check_common(c, normal_scheme, dirO);
+  if (rc) return rc;
+  if (!f || !ff || !u || !u0 || !cbar || (c->D == 3 && !alpha)) return fail(c, -2, "null array");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->dtype == IFADV_F32)
+    return advect_vof_t<float>(c, st, (float*)f, (float*)ff, (float*)alpha, (const float*)u, (const float*)u0, dt, cbar, (float*)rhouf,
+                               lambda_rho, normal_scheme, perdir_mask, dirO, flags, report);
+  return advect_vof_t<double>(c, st, (double*)f, (double*)ff, (double*)alpha, (const double*)u, (const double*)u0, dt, cbar, (double*)rhouf,
+                              lambda_rho, normal_scheme, perdir_mask, dirO, flags, report);
+}
+
+int ifadv_advect_vof_rhouu(ifadv_ctx* c, void* stream, void* f, void* ff, void* alpha, void* nhat, const void* u, const void* u0, double dt,
+                           int8_t* cbar, void* rhou, void* r, void* Phi, void* rhouf, void* uStar, const void* uOld, void* dilaU,
+                           const void* drho, double lambda_rho, int limiter, int normal_scheme, const double uBC[3], unsigned perdir_mask,
+                           int exitBC, const int dirO[3], ifadv_report* report) {
+  (void)alpha; (void)nhat; (void)uStar; (void)dilaU;
+  int rc = check_common(c, normal_scheme, dirO);
+  if (rc) return rc;
+  if (limiter < 0 || limiter > 10) return fail(c, -2, "invalid limiter");
+  if (exitBC) return fail(c, -2, "exitBC=true is not supported: the reference reads stale scratch on the exit plane (DESIGN.md)");
+  if (!f || !ff || !u || !u0 || !cbar || !rhou || !r || !uOld || !drho || !uBC || (c->D == 3 && (!Phi || !rhouf)))
+    return fail(c, -2, "null array");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->dtype == IFADV_F32)
+    return advect_vof_rhouu_t<float>(c, st, (float*)f, (float*)ff, (float*)Phi, (const float*)u, (const float*)u0, dt, cbar, (float*)rhou,
+                                     (float*)r, (float*)rhouf, (const float*)uOld, (const float*)drho, lambda_rho, limiter, normal_scheme,
+                                     uBC, perdir_mask, dirO, report);
+  return advect_vof_rhouu_t<double>(c, st, (double*)f, (double*)ff, (double*)Phi, (const double*)u, (const double*)u0, dt, cbar,
+                                    (double*)rhou, (double*)r, (double*)rhouf, (const double*)uOld, (const double*)drho, lambda_rho, limiter,
+                                    normal_scheme, uBC, perdir_mask, dirO, report);
+}
+
+int ifadv_u2rhou(ifadv_ctx* c, void* stream, void* rhou, const void* u, const void* f, double lr) {
+  if (!c || !rhou || !u || !f) return -2;
+  if (c->dtype == IFADV_F32) return u2rhou_t<float>(c, (cudaStream_t)stream, (float*)rhou, (const float*)u, (const float*)f, lr, true);
+  return u2rhou_t<double>(c, (cudaStream_t)stream, (double*)rhou, (const double*)u, (const double*)f, lr, true);
+}
+int ifadv_rhou2u(ifadv_ctx* c, void* stream, void* u, const void* rhou, const void* f, double lr) {
+  if (!c || !rhou || !u || !f) return -2;
+  if (c->dtype == IFADV_F32) return u2rhou_t<float>(c, (cudaStream_t)stream, (float*)u, (const float*)rhou, (const float*)f, lr, false);
+  return u2rhou_t<double>(c, (cudaStream_t)stream, (double*)u, (const double*)rhou, (const double*)f, lr, false);
+}
+int ifadv_bc_vec(ifadv_ctx* c, void* stream, void* a, const double A[3], int saveexit, unsigned perdir_mask) {
+  if (!c || !a || !A) return -2;
+  if (c->dtype == IFADV_F32) return bcvec_t<float>(c, (cudaStream_t)stream, (float*)a, A, saveexit, perdir_mask);
+  return bcvec_t<double>(c, (cudaStream_t)stream, (double*)a, A, saveexit, perdir_mask);
+}
+int ifadv_bcf(ifadv_ctx* c, void* stream, void* f, unsigned perdir_mask) {
+  if (!c || !f) return -2;
+  if (c->dtype == IFADV_F32) return launch_bcf<float>(c, (cudaStream_t)stream, (float*)f, perdir_mask);
+  return launch_bcf<double>(c, (cudaStream_t)stream, (double*)f, perdir_mask);
+}
+int ifadv_axpby(ifadv_ctx* c, void* stream, void* out, double a, const void* x, double b, const void* y) {
+  if (!c || !out || !x || !y) return -2;
+  if (c->dtype == IFADV_F32) return axpby_t<float>(c, (cudaStream_t)stream, (float*)out, a, (const float*)x, b, (const float*)y);
+  return axpby_t<double>(c, (cudaStream_t)stream, (double*)out, a, (const double*)x, b, (const double*)y);
+}
+
+int ifadv_mpcfl(ifadv_ctx* c, void* stream, const void* u, double nu, double mu, double lambda_mu, double lambda_rho, double eta,
+                double gnorm, double dt_max, double safety, double* dt_out) {
+  if (!c || !u || !dt_out) return -2;
+  cudaStream_t st = (cudaStream_t)stream;
+  CU_CHECK(c, cudaMemsetAsync(c->misc_dev, 0, sizeof(unsigned long long) * 8, st));
+  const int bx = 128;
+  dim3 grid = row_grid(c->g, c->D, bx);
+  if (c->dtype == IFADV_F32) {
+    if (c->D == 2) cfl_kernel<float, 2><<<grid, bx, 0, st>>>((const float*)u, c->g, c->misc_dev);
+    else cfl_kernel<float, 3><<<grid, bx, 0, st>>>((const float*)u, c->g, c->misc_dev);
+  } else {
+    if (c->D == 2) cfl_kernel<double, 2><<<grid, bx, 0, st>>>((const double*)u, c->g, c->misc_dev);
+    else cfl_kernel<double, 3><<<grid, bx, 0, st>>>((const double*)u, c->g, c->misc_dev);
+  }
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  CU_CHECK(c, cudaMemcpyAsync(c->misc_host, c->misc_dev, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
+  CU_CHECK(c, cudaStreamSynchronize(st));
+  // ghosts of σ are 0 after fill!(a.σ,0) (flow.jl:264), so the maxima are at least 0 -- the keys start at 0.0's floor
+  double mfo = c->misc_host[0] ? key_to_double(c->misc_host[0]) : 0.0, mtf = c->misc_host[1] ? key_to_double(c->misc_host[1]) : 0.0;
+  mfo = std::fmax(mfo, 0.0); mtf = std::fmax(mtf, 0.0);
+  auto compute = [&](auto tag) {
+    using T = decltype(tag);
+    const T dtAdv = T(1) / ((T)mfo + T(5) * (T)nu);
+    const T dtVOF = T(1) / (T(2) * (T)mtf);
+    const T dtGrav = (gnorm > 0) ? T(1) / (T(2) * (T)gnorm) : (T)dt_max;
+    const T dtVisc = (mu > 0) ? T(3) / (T(14) * (T)mu * std::max(T(1), (T)lambda_mu / (T)lambda_rho)) : (T)dt_max;
+    const T dtSurf = (eta > 0) ? std::sqrt((T(1) + (T)lambda_rho) / (T(8 * M_PI) * (T)eta)) : (T)dt_max;
+    return (double)((T)safety * std::min(std::min(std::min(dtVOF, dtAdv), std::min(dtGrav, dtVisc)), dtSurf));
+  };
+  *dt_out = (c->dtype == IFADV_F32) ? compute(float()) : compute(double());
+  return 0;
+}
+
+int ifadv_sum_inside(ifadv_ctx* c, void* stream, const void* f, double* out) {
+  if (!c || !f || !out) return -2;
+  cudaStream_t st = (cudaStream_t)stream;
+  CU_CHECK(c, cudaMemsetAsync(c->misc_dev, 0, sizeof(unsigned long long) * 8, st));
+  const int bx = 128;
+  dim3 grid = row_grid(c->g, c->D, bx);
+  double* acc = reinterpret_cast<double*>(c->misc_dev);
+  if (c->dtype == IFADV_F32) {
+    if (c->D == 2) sum_inside_kernel<float, 2><<<grid, bx, 0, st>>>((const float*)f, c->g, acc);
+    else sum_inside_kernel<float, 3><<<grid, bx, 0, st>>>((const float*)f, c->g, acc);
+  } else {
+    if (c->D == 2) sum_inside_kernel<double, 2><<<grid, bx, 0, st>>>((const double*)f, c->g, acc);
+    else sum_inside_kernel<double, 3><<<grid, bx, 0, st>>>((const double*)f, c->g, acc);
+  }
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  CU_CHECK(c, cudaMemcpyAsync(c->misc_host, c->misc_dev, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
+  CU_CHECK(c, cudaStreamSynchronize(st));
+  memcpy(out, c->misc_host, sizeof(double));
+  return 0;
+}
+
+int ifadv_apply_vof_samples(ifadv_ctx* c, void* stream, void* f, void* alpha, void* nhat, const void* sc, const void* sp, const void* sm) {
+  if (!c || !f || !alpha || !nhat || !sc || !sp || !sm) return -2;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int bx = 128;
+  dim3 grid = row_grid(c->g, c->D, bx);
+  if (c->dtype == IFADV_F32) {
+    const float tol = 10 * std::numeric_limits<float>::epsilon();
+    if (c->D == 2) applyvof_kernel<float, 2><<<grid, bx, 0, st>>>((float*)f, (float*)alpha, (float*)nhat, (const float*)sc, (const float*)sp, (const float*)sm, c->g, tol);
+    else applyvof_kernel<float, 3><<<grid, bx, 0, st>>>((float*)f, (float*)alpha, (float*)nhat, (const float*)sc, (const float*)sp, (const float*)sm, c->g, tol);
+  } else {
+    const double tol = 10 * std::numeric_limits<double>::epsilon();
+    if (c->D == 2) applyvof_kernel<double, 2><<<grid, bx, 0, st>>>((double*)f, (double*)alpha, (double*)nhat, (const double*)sc, (const double*)sp, (const double*)sm, c->g, tol);
+    else applyvof_kernel<double, 3><<<grid, bx, 0, st>>>((double*)f, (double*)alpha, (double*)nhat, (const double*)sc, (const double*)sp, (const double*)sm, c->g, tol);
+  }
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+// One CMOM advection step on host buffers (what bench.py's e2e leg times).  Work arrays (device):
+// w[0]=f w[1]=f⁰ w[2]=fᶠ w[3]=Φ w[4]=u w[5]=u⁰ w[6]=ρu w[7]=r w[8]=ρuf w[9]=dρ w[10]=c̄
+int ifadv_mom_advect_step_host(ifadv_ctx* c, void* f_host, const void* u_host, void* rhou_host, double dt, double lambda_rho, int limiter,
+                               int normal_scheme, const double uBC[3], unsigned perdir_mask, const int dirO[3], ifadv_report* report) {
+  if (!c || !f_host || !u_host || !rhou_host || !uBC || !dirO) return -2;
+  const size_t es = esize(c->dtype), sb = es * c->g.S, vb = sb * c->D;
+  CU_CHECK(c, cudaSetDevice(c->device));
+  if (!c->own_stream) CU_CHECK(c, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  cudaStream_t st = c->own_stream;
+  if (!c->w[0]) {
+    const size_t sz[11] = {sb, sb, sb, sb, vb, vb, vb, vb, vb, vb, (size_t)c->g.S};
+    for (int k = 0; k < 11; ++k) CU_CHECK(c, cudaMalloc(&c->w[k], sz[k]));
+    // dρ keeps its constructor value 1 (cVOF.jl:74)
+    {
+      const long long n = (long long)c->g.S * c->D;
+      const int bs = 256;
+      if (c->dtype == IFADV_F32) fill_kernel<float><<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>((float*)c->w[9], 1.f, n);
+      else fill_kernel<double><<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>((double*)c->w[9], 1.0, n);
+      c->launches++;
+      CU_CHECK(c, cudaGetLastError());
+    }
+    CU_CHECK(c, cudaMallocHost(&c->pin_f, sb));
+    CU_CHECK(c, cudaMallocHost(&c->pin_u, vb));
+    CU_CHECK(c, cudaMallocHost(&c->pin_ru, vb));
+  }
+  void *f = c->w[0], *f0 = c->w[1], *ff = c->w[2], *Phi = c->w[3], *u = c->w[4], *u0 = c->w[5], *ru = c->w[6], *r = c->w[7], *ruf = c->w[8],
+       *drho = c->w[9];
+  int8_t* cbar = (int8_t*)c->w[10];
+  // caller buffers that are already page-locked (cudaHostRegister / pinned allocators) are used directly
+  auto pinned = [](const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  };
+  const bool pf = pinned(f_host), pu = pinned(u_host), pr = pinned(rhou_host);
+  if (!pf) memcpy(c->pin_f, f_host, sb);
+  if (!pu) memcpy(c->pin_u, u_host, vb);
+  CU_CHECK(c, cudaMemcpyAsync(f, pf ? f_host : c->pin_f, sb, cudaMemcpyHostToDevice, st));
+  CU_CHECK(c, cudaMemcpyAsync(u, pu ? u_host : c->pin_u, vb, cudaMemcpyHostToDevice, st));
+  // copyto!(u⁰,u); copyto!(f⁰,f)                                           flow.jl:61
+  CU_CHECK(c, cudaMemcpyAsync(u0, u, vb, cudaMemcpyDeviceToDevice, st));
+  CU_CHECK(c, cudaMemcpyAsync(f0, f, sb, cudaMemcpyDeviceToDevice, st));
+  int rc;
+  // predictor                                                             flow.jl:69-70
+  if ((rc = ifadv_u2rhou(c, st, ru, u0, f0, lambda_rho))) return rc;
+  if ((rc = ifadv_bc_vec(c, st, ru, uBC, 0, perdir_mask))) return rc;
+  if ((rc = ifadv_advect_vof_rhouu(c, st, f0, ff, nullptr, nullptr, u0, u, dt, cbar, ru, r, Phi, ruf, nullptr, u, nullptr, drho, lambda_rho,
+                                   limiter, normal_scheme, uBC, perdir_mask, 0, dirO, nullptr)) < 0) return rc;
+  if ((rc = ifadv_axpby(c, st, f0, 0.5, f0, 0.5, f))) return rc;  // flow.jl:74
+  // corrector                                                             flow.jl:89-92
+  CU_CHECK(c, cudaMemcpyAsync(f0, f, sb, cudaMemcpyDeviceToDevice, st));
+  if ((rc = ifadv_u2rhou(c, st, ru, u0, f, lambda_rho))) return rc;
+  if ((rc = ifadv_bc_vec(c, st, ru, uBC, 0, perdir_mask))) return rc;
+  rc = ifadv_advect_vof_rhouu(c, st, f, ff, nullptr, nullptr, u, u, dt, cbar, ru, r, Phi, ruf, nullptr, u0, nullptr, drho, lambda_rho, limiter,
+                              normal_scheme, uBC, perdir_mask, 0, dirO, report);
+  if (rc < 0) return rc;
+  CU_CHECK(c, cudaMemcpyAsync(pf ? f_host : c->pin_f, f, sb, cudaMemcpyDeviceToHost, st));
+  CU_CHECK(c, cudaMemcpyAsync(pr ? rhou_host : c->pin_ru, ru, vb, cudaMemcpyDeviceToHost, st));
+  CU_CHECK(c, cudaStreamSynchronize(st));
+  if (!pf) memcpy(f_host, c->pin_f, sb);
+  if (!pr) memcpy(rhou_host, c->pin_ru, vb);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+// ifadv_ctx.hpp -- context object and launch descriptors shared by the translation units of libifadv_b200.so
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "ifadv_sweep.cuh"
+
+// ------------------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------------------
+struct ifadv_ctx {
+  int D, dtype, device;
+  ifadv::Geo g;
+  int64_t Ng[3];
+  unsigned long long* red_dev;   // 3 sweeps x 8 slots
+  unsigned long long* red_host;  // pinned mirror
+  unsigned long long* misc_dev;  // 8 slots for CFL / sum reductions
+  unsigned long long* misc_host;
+  int64_t launches;
+  std::string err;
+  // work arrays of the host-buffer convenience entry point (allocated lazily)
+  void* w[16];
+  void* pin_f;
+  void* pin_u;
+  void* pin_ru;
+  cudaStream_t own_stream;
+};
+
+#define CU_CHECK(ctx, call)                                                                 \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      if (ctx) (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);             \
+      return -3;                                                                            \
+    }                                                                                       \
+  } while (0)
+
+
+namespace ifadv {
+template <class T> struct SweepCfg {
+  const T *f_in, *u, *u0, *rhou_in, *uOld, *drho;
+  T *f_out, *rhou_out, *rhouf;
+  int8_t* cbar;
+  double dt, lr;
+  double A[3];
+  int scheme, lim, first, j;  // j 0-based
+  unsigned long long* red;
+};
+
+
+// one fused directional sweep; defined in ifadv_sweep_inst.cu, one translation unit per (T, D, MOM)
+template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
+}  // namespace ifadv

@@ -1,0 +1,50 @@
+// ifadv_sweep_inst.cu -- instantiates the fused sweep kernels for ONE (T, D, MOM) combination, chosen with
+// -DIFADV_T=float|double -DIFADV_D=2|3 -DIFADV_MOM=0|1, so that the instantiations compile in parallel.
+#include <limits>
+
+#include "ifadv_ctx.hpp"
+
+namespace ifadv {
+
+template <class T, int D, int J, int TX, int TY, int TZ, bool MOM>
+static int launch_sweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  constexpr int NT = 256;
+  using TL = Tile<D, J, TX, TY, TZ>;
+  SweepP<T> P;
+  P.f_in = q.f_in; P.f_out = q.f_out;
+  P.uj = q.u + (long long)J * c->g.S; P.u0j = q.u0 + (long long)J * c->g.S;
+  P.cbar = q.cbar;
+  P.rhou_in = q.rhou_in; P.rhou_out = q.rhou_out; P.uOld = q.uOld; P.drho = q.drho;
+  P.rhouf_j = q.rhouf ? q.rhouf + (long long)J * c->g.S : nullptr;
+  P.dt = (T)q.dt; P.hdt = P.dt / T(2); P.idt = T(1) / P.dt; P.lr = (T)q.lr; P.omlr = T(1) - P.lr;
+  P.tol = T(10) * std::numeric_limits<T>::epsilon(); P.onemtol = T(1) - P.tol;
+  for (int i = 0; i < 3; ++i) P.A[i] = (T)q.A[i];
+  P.g = c->g; P.scheme = q.scheme; P.lim = q.lim; P.first = q.first; P.red = q.red;
+  const size_t smem = TL::template smem_bytes<T>(MOM);
+  auto kern = sweep_kernel<T, D, J, TX, TY, TZ, MOM, NT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((c->g.n[0] - 2 + TL::T0 - 1) / TL::T0), (unsigned)((c->g.n[1] - 2 + TL::T1 - 1) / TL::T1),
+            (unsigned)(D == 3 ? (c->g.n[2] - 2 + TL::T2 - 1) / TL::T2 : 1));
+  kern<<<grid, NT, smem, st>>>(P);
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  if constexpr (D == 2) {
+    if (q.j == 0) return launch_sweep_t<T, 2, 0, 64, 8, 1, MOM>(c, st, q);
+    return launch_sweep_t<T, 2, 1, 32, 16, 1, MOM>(c, st, q);
+  } else {
+    if (q.j == 0) return launch_sweep_t<T, 3, 0, 32, 8, 4, MOM>(c, st, q);
+    if (q.j == 1) return launch_sweep_t<T, 3, 1, 32, 8, 4, MOM>(c, st, q);
+    return launch_sweep_t<T, 3, 2, 32, 4, 8, MOM>(c, st, q);
+  }
+}
+template int launch_sweep_dim<IFADV_T, IFADV_D, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
+
+}  // namespace ifadv
