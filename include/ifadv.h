@@ -71,6 +71,11 @@ const char* ifadv_last_error(const ifadv_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t ifadv_launch_count(const ifadv_ctx* ctx);
 const char* ifadv_version(void);
+/* Measurement aid for bench.py: while enabled, every fused sweep launch is bracketed by CUDA events recorded on
+ * the launching stream (up to 4096 launches).  ifadv_profile_read synchronises those events, returns the summed
+ * kernel time in ms and the number of launches, and resets the pool. */
+int ifadv_profile(ifadv_ctx* ctx, int enable);
+int ifadv_profile_read(ifadv_ctx* ctx, double* total_ms, int64_t* launches);
 
 /* ---- the hot path --------------------------------------------------------------------------------------- */
 /* advectVOF!(f,fᶠ,α,n̂,u,u⁰,Δt,c̄,ρuf,λρ,normalScheme; perdir,dirO)            src/advection.jl:34-78

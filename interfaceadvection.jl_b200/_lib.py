@@ -40,6 +40,8 @@ def lib():
         L.ifadv_last_error.argtypes = [vp]
         L.ifadv_launch_count.restype = C.c_int64
         L.ifadv_launch_count.argtypes = [vp]
+        L.ifadv_profile.argtypes = [vp, i32]
+        L.ifadv_profile_read.argtypes = [vp, dblp, i64p]
         L.ifadv_create.argtypes = [C.POINTER(vp), i32, i64p, i32, i32]
         L.ifadv_destroy.argtypes = [vp]
         L.ifadv_advect_vof.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, dbl, vp, vp, dbl, i32, u32, i32p, i32, rep]
@@ -110,6 +112,14 @@ class Context:
     @property
     def launches(self) -> int:
         return int(lib().ifadv_launch_count(self._h))
+
+    def profile(self, enable: bool):
+        return self._chk(lib().ifadv_profile(self._h, int(bool(enable))))
+
+    def profile_read(self):
+        ms, n = C.c_double(), C.c_int64()
+        self._chk(lib().ifadv_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, int(n.value)
 
     def advect_vof(self, stream, f, ff, alpha, nhat, u, u0, dt, cbar, rhouf, lam_rho, scheme, perdir, dirO, flags=0, report=None):
         r = C.byref(report) if report is not None else None

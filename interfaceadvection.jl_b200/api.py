@@ -72,6 +72,8 @@ _contexts = {}
 
 
 def context_for(f: torch.Tensor) -> Context:
+    if not f.is_cuda:
+        raise IfadvError("the B200 path needs CUDA tensors; there is no CPU fallback")
     key = (tuple(f.shape), f.dtype, f.device.index)
     if key not in _contexts:
         _contexts[key] = Context(tuple(f.shape), _DT[f.dtype], f.device.index or 0)
@@ -79,6 +81,8 @@ def context_for(f: torch.Tensor) -> Context:
 
 
 def _stream(t: torch.Tensor) -> int:
+    if not t.is_cuda:
+        raise IfadvError("the B200 path needs CUDA tensors; there is no CPU fallback")
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
@@ -294,12 +298,9 @@ def MPCFL(a: Flow, c: cVOF, dt_max=1.0, safety=0.8) -> float:
                                   gnorm=gnorm, dt_max=dt_max, safety=safety)
 
 
-def MPFMomStep(a: Flow, b, c: cVOF, d=None, dt=None, project: Optional[Callable] = None, check=False):
-    """Transport part of MPFMomStep!(a,b,c,d)  (src/flow.jl:60-109).
-
-    Lines 61, 69-70, 74, 89-92 and 108 run on the B200 kernels.  The forcing (viscSurfTenρu!, updateU!) and the
-    pressure projection (myproject!) stay on WaterLily's backend (SURVEY §8f); `project(a, c, stage)` is the hook
-    where a caller plugs them in.  Without it velocities are prescribed: u is left untouched between the stages."""
+def mom_advect_step(a: Flow, c: cVOF, dt=None, project: Optional[Callable] = None, check=False):
+    """The transport half of MPFMomStep! (src/flow.jl:61,69-70,74,89-92): two u2ρu!+BC!+advectfq! groups and the
+    midpoint f⁰.  This is one "advection step" of the benchmark metric; MPCFL is separate."""
     dt = a.dt[-1] if dt is None else dt
     ctx, s = context_for(c.f), _stream(c.f)
     a.u0.copy_(a.u)
@@ -309,13 +310,23 @@ def MPFMomStep(a: Flow, b, c: cVOF, d=None, dt=None, project: Optional[Callable]
     advectfq(a, c, c.f0, a.u0, a.u, a.u, dt, check=check)             # :70
     ctx.axpby(s, _p(c.f0), 0.5, _p(c.f0), 0.5, _p(c.f))               # :74
     if project is not None:
-        project(a, c, "predictor")                                    # :75-82
+        project(a, c, "predictor")                                    # :75-82 (WaterLily side)
     c.f0.copy_(c.f)                                                   # :89
     u2rhou(c.rhou, a.u0, c.f, c.lam_rho)
     BC(c.rhou, a.uBC, a.exitBC, a.perdir)                             # :91
     advectfq(a, c, c.f, a.u, a.u, a.u0, dt, check=check)              # :92
     if project is not None:
-        project(a, c, "corrector")                                    # :95-106
+        project(a, c, "corrector")                                    # :95-106 (WaterLily side)
+
+
+def MPFMomStep(a: Flow, b, c: cVOF, d=None, dt=None, project: Optional[Callable] = None, check=False):
+    """Transport part of MPFMomStep!(a,b,c,d)  (src/flow.jl:60-109).
+
+    Lines 61, 69-70, 74, 89-92 and 108 run on the B200 kernels.  The forcing (viscSurfTenρu!, updateU!) and the
+    pressure projection (myproject!) stay on WaterLily's backend (SURVEY §8f); `project(a, c, stage)` is the hook
+    where a caller plugs them in.  Without it velocities are prescribed: u is left untouched between the stages."""
+    dt = a.dt[-1] if dt is None else dt
+    mom_advect_step(a, c, dt, project=project, check=check)
     a.dt.append(min(MPCFL(a, c), 1.2 * dt))                           # :108
 
 

@@ -371,6 +371,7 @@ int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int dev
   for (auto& p : c->w) p = nullptr;
   c->pin_f = c->pin_u = c->pin_ru = nullptr;
   c->own_stream = nullptr;
+  c->prof_on = 0; c->prof_n = 0; c->prof_ev = nullptr;
   if (cudaMalloc(&c->red_dev, sizeof(unsigned long long) * 24) != cudaSuccess ||
       cudaMallocHost(&c->red_host, sizeof(unsigned long long) * 24) != cudaSuccess ||
       cudaMalloc(&c->misc_dev, sizeof(unsigned long long) * 8) != cudaSuccess ||
@@ -391,7 +392,33 @@ int ifadv_destroy(ifadv_ctx* c) {
   if (c->pin_u) cudaFreeHost(c->pin_u);
   if (c->pin_ru) cudaFreeHost(c->pin_ru);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->prof_ev) { for (int k = 0; k < 2 * IFADV_PROF_MAX; ++k) cudaEventDestroy(c->prof_ev[k]); delete[] c->prof_ev; }
   delete c;
+  return 0;
+}
+
+int ifadv_profile(ifadv_ctx* c, int enable) {
+  if (!c) return -2;
+  if (enable && !c->prof_ev) {
+    c->prof_ev = new cudaEvent_t[2 * IFADV_PROF_MAX];
+    for (int k = 0; k < 2 * IFADV_PROF_MAX; ++k) CU_CHECK(c, cudaEventCreate(&c->prof_ev[k]));
+  }
+  c->prof_on = enable ? 1 : 0;
+  if (enable) c->prof_n = 0;
+  return 0;
+}
+int ifadv_profile_read(ifadv_ctx* c, double* total_ms, int64_t* launches) {
+  if (!c || !total_ms || !launches) return -2;
+  double tot = 0.0;
+  for (int k = 0; k < c->prof_n; ++k) {
+    float ms = 0.f;
+    CU_CHECK(c, cudaEventSynchronize(c->prof_ev[2 * k + 1]));
+    CU_CHECK(c, cudaEventElapsedTime(&ms, c->prof_ev[2 * k], c->prof_ev[2 * k + 1]));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *launches = c->prof_n;
+  c->prof_n = 0;
   return 0;
 }
 

@@ -26,7 +26,11 @@ struct ifadv_ctx {
   void* pin_u;
   void* pin_ru;
   cudaStream_t own_stream;
+  // optional per-launch CUDA-event timing of the fused sweep (ifadv_profile)
+  int prof_on, prof_n;
+  cudaEvent_t* prof_ev;  // 2 * IFADV_PROF_MAX events
 };
+#define IFADV_PROF_MAX 4096
 
 #define CU_CHECK(ctx, call)                                                                 \
   do {                                                                                      \

@@ -29,7 +29,10 @@ static int launch_sweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   }
   dim3 grid((unsigned)((c->g.n[0] - 2 + TL::T0 - 1) / TL::T0), (unsigned)((c->g.n[1] - 2 + TL::T1 - 1) / TL::T1),
             (unsigned)(D == 3 ? (c->g.n[2] - 2 + TL::T2 - 1) / TL::T2 : 1));
+  const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
+  if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
   kern<<<grid, NT, smem, st>>>(P);
+  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_n++; }
   c->launches++;
   CU_CHECK(c, cudaGetLastError());
   return 0;
