@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -372,6 +373,10 @@ int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int dev
   c->pin_f = c->pin_u = c->pin_ru = nullptr;
   c->own_stream = nullptr;
   c->prof_on = 0; c->prof_n = 0; c->prof_ev = nullptr;
+  {
+    const char* e = getenv("IFADV_KERNEL");
+    c->use_march = !(e && std::string(e) == "tile");
+  }
   if (cudaMalloc(&c->red_dev, sizeof(unsigned long long) * 24) != cudaSuccess ||
       cudaMallocHost(&c->red_host, sizeof(unsigned long long) * 24) != cudaSuccess ||
       cudaMalloc(&c->misc_dev, sizeof(unsigned long long) * 8) != cudaSuccess ||

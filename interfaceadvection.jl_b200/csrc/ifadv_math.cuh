@@ -141,6 +141,7 @@ template <class T> IFADV_DI T sweby(T u, T c, T d, T gam) {
   return c + (s * t_max(T(0), t_max(m1, m2))) / T(2);
 }
 template <class T> IFADV_DI T limiter(int lam, T u, T c, T d) {
+  if (lam == 2) return median3((T(7) * c + d - T(2) * u) / T(6), c, median3(T(2) * c - u, c, d));  // Koren, the default: no jump table
   switch (lam) {
     case 0: return c;
     case 1: return median3((T(3) * c - u) / T(2), c, (c + d) / T(2));

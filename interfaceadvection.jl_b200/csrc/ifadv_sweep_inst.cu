@@ -3,6 +3,7 @@
 #include <limits>
 
 #include "ifadv_ctx.hpp"
+#include "ifadv_march.cuh"
 
 namespace ifadv {
 
@@ -38,7 +39,62 @@ static int launch_sweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   return 0;
 }
 
+template <class T> static void fill_params(ifadv_ctx* c, const SweepCfg<T>& q, int J, SweepP<T>& P) {
+  P.f_in = q.f_in; P.f_out = q.f_out;
+  P.uj = q.u + (long long)J * c->g.S; P.u0j = q.u0 + (long long)J * c->g.S;
+  P.cbar = q.cbar;
+  P.rhou_in = q.rhou_in; P.rhou_out = q.rhou_out; P.uOld = q.uOld; P.drho = q.drho;
+  P.rhouf_j = q.rhouf ? q.rhouf + (long long)J * c->g.S : nullptr;
+  P.dt = (T)q.dt; P.hdt = P.dt / T(2); P.idt = T(1) / P.dt; P.lr = (T)q.lr; P.omlr = T(1) - P.lr;
+  P.tol = T(10) * std::numeric_limits<T>::epsilon(); P.onemtol = T(1) - P.tol;
+  for (int i = 0; i < 3; ++i) P.A[i] = (T)q.A[i];
+  P.g = c->g; P.scheme = q.scheme; P.lim = q.lim; P.first = q.first; P.red = q.red;
+}
+
+// v2: plane-marching kernel (3-D only)
+template <class T, int J, int TA, int TB, bool MOM, int MINB>
+static int launch_march_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  constexpr int NT = 256;
+  using TL = MTile<J, TA, TB, NT>;
+  SweepP<T> P;
+  fill_params<T>(c, q, J, P);
+  const size_t smem = TL::template smem_bytes<T>(MOM);
+  auto kern = march_kernel<T, J, TA, TB, MOM, NT, MINB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  constexpr int DB = (J == 0) ? 1 : 0, DC = (J == 2) ? 1 : 2;
+  const int nx = c->g.n[0] - 2, no = c->g.n[(J == 2) ? 2 : 1] - 2, nc = c->g.n[DC] - 2;
+  (void)DB;
+  const int tx = TL::AX ? TA : TB, to = TL::AX ? TB : TA;
+  // chunk the march direction so that the grid holds several waves of CTAs
+  const long long tiles = (long long)((nx + tx - 1) / tx) * ((no + to - 1) / to);
+  int chunk = 32;
+  while (chunk > 8 && tiles * ((nc + chunk - 1) / chunk) < 148 * 8) chunk >>= 1;
+  dim3 grid((unsigned)((nx + tx - 1) / tx), (unsigned)((no + to - 1) / to), (unsigned)((nc + chunk - 1) / chunk));
+  const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
+  if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
+  kern<<<grid, NT, smem, st>>>(P, chunk);
+  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_n++; }
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
 template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  if constexpr (D == 3) {
+    if (c->use_march) {
+      // tile shapes sized so that 25 shared planes leave 3 (f32) / 2-3 (f64) CTAs per SM
+      constexpr int TO = (sizeof(T) == 4) ? 16 : 8;
+      constexpr int TAX = (sizeof(T) == 4) ? 64 : 32;
+      constexpr int MB = (sizeof(T) == 4) ? 3 : 2;
+      if (q.j == 0) return launch_march_t<T, 0, TAX, 8, MOM, MB>(c, st, q);
+      if (q.j == 1) return launch_march_t<T, 1, TO, 32, MOM, MB>(c, st, q);
+      return launch_march_t<T, 2, TO, 32, MOM, MB>(c, st, q);
+    }
+  }
   if constexpr (D == 2) {
     if (q.j == 0) return launch_sweep_t<T, 2, 0, 64, 8, 1, MOM>(c, st, q);
     return launch_sweep_t<T, 2, 1, 32, 16, 1, MOM>(c, st, q);
