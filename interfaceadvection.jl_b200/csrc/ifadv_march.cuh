@@ -10,11 +10,13 @@
 // entries t, t+NT, t+2NT.. of it.  Everything that depends only on the entry -- the global offsets with the ghost
 // rules of BCf!/BC! folded in (clamp = Neumann, wrap = periodic), and a bit mask of which stage regions and which
 // one-sided / Dirichlet rules apply -- is computed ONCE before the march, so the per-plane work is pure data flow:
-//   wait   cp.async copies of plane k (issued one plane earlier) have landed in shared memory
-//   issue  cp.async copies of plane k+1: f, u_a, u⁰_a, ρu (3 components) -> the other ring slots (HBM latency hidden
+//   wait   cp.async copies of plane k (issued one plane earlier; f two planes earlier) have landed in shared memory
+//   issue  cp.async copies of f(k+2) and u_a, u⁰_a, ρu (3 components) of plane k+1 -> other ring slots (HBM latency hidden
 //          behind the arithmetic of plane k; the row pitch 4(N+2) B is not a multiple of 16 B, so TMA tiled copies
 //          cannot be used on the reference's array layout -- LDGSTS 4/8-byte copies can)
-//   P2     VOF face flux fᶠ + mass flux (advection.jl:108-137), dilation ρ̄∂ⱼuⱼ (flow.jl:216), u★ = ρu/ρ (flow.jl:197)
+//   P2     VOF face flux fᶠ + mass flux (advection.jl:108-137), dilation ρ̄∂ⱼuⱼ (flow.jl:216), u★ = ρu/ρ (flow.jl:197);
+//          faces whose upwind cell holds an interface are only MARKED here and then reconstructed lane-dense from the
+//          shared f planes (3^3 box: planes k-1,k,k+1) -- a divergent in-line PLIC would cost a full warp per interface cell
 //   P3     SynDRoM momentum flux through every a-face of the tile, once per face (flow.jl:20-57,223)
 //   P4     cell update: f (advection.jl:83, cleanWisp!), ρu (flow.jl:224-231), fill-error extrema
 // Quantities of the previous plane that the stencil reaches along c (f, mass flux, dilation) stay in shared-memory
@@ -26,14 +28,15 @@ namespace ifadv {
 
 template <int J, int TA, int TB, int NT> struct MTile {
   static constexpr bool AX = (J == 0);  // is the sweep direction the contiguous one?
-  static constexpr int HAm = 3, HAp = 2, HBm = 1;
-  static constexpr int WA = TA + HAm + HAp, WB = TB + HBm;
+  // halo: -3..+2 along a (u★ line + upwind cell), -2..+1 along b (3^3 PLIC box of a cell at b = -1 / TB-1)
+  static constexpr int HAm = 3, HAp = 2, HBm = 2, HBp = 1;
+  static constexpr int WA = TA + HAm + HAp, WB = TB + HBm + HBp;
   static constexpr int PL = WA * WB;                      // entries of one shared plane
   static constexpr int SA = AX ? 1 : WB, SB = AX ? WA : 1;  // x fastest; entry index == shared index
   static constexpr int TRIPS = (PL + NT - 1) / NT;
-  // CMOM planes: F x3, U x2, U0 x2, RU x6, Us x3, M x2, FF, Div, Dil x2, Fl x3 = 25 ; pure VOF: F x3, U x2, U0 x2, M, FF = 9
-  static constexpr int NPLANES_MOM = 25, NPLANES_VOF = 9;
-  template <class T> static constexpr size_t smem_bytes(bool mom) { return sizeof(T) * (size_t)PL * (mom ? NPLANES_MOM : NPLANES_VOF); }
+  // CMOM planes: F x4, U x2, U0 x2, M x2, FF, RU x6, Us x3, Dil x2, Fl x3 = 25 ; pure VOF: F x4, U x2, U0 x2, M, FF, list = 11
+  static constexpr int NPLANES_MOM = 25, NPLANES_VOF = 11;
+  template <class T> static constexpr size_t smem_bytes(bool mom) { return sizeof(T) * (size_t)PL * (mom ? NPLANES_MOM : NPLANES_VOF) + 16; }
 };
 
 enum : unsigned {
@@ -62,6 +65,19 @@ template <class T> IFADV_DI void cp_async(T* smem_dst, const T* gsrc) {
 IFADV_DI void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 IFADV_DI void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// 3^3 box accessor of the normal schemes reading the shared f planes: (dx,dy,dz) in global axes -> (a,b,c) offsets
+template <class T, int J, int PL, int SA, int SB> struct SBox {
+  const T* sF;  // 4-slot ring of f planes
+  int e;        // entry of the box centre
+  int vc;       // plane of the box centre
+  IFADV_DI T operator()(int dx, int dy, int dz) const {
+    const int da = (J == 0) ? dx : ((J == 1) ? dy : dz);
+    const int db = (J == 0) ? dy : dx;
+    const int dc = (J == 2) ? dy : dz;
+    return sF[((vc + dc) & 3) * PL + e + da * SA + db * SB];
+  }
+};
+
 template <class T, int J, int TA, int TB, bool MOM, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, const int chunk) {
   using TL = MTile<J, TA, TB, NT>;
@@ -87,16 +103,20 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
   const int k0 = 2 + blockIdx.z * chunk, k1 = min(k0 + chunk, nC);
 
   // shared planes
-  T* sF = sm;                                   // 3 slots: plane k%3
-  T* sU = sm + 3 * PL;                          // 2 slots: plane k&1
-  T* sU0 = sm + 5 * PL;                         // 2 slots
-  T* sM = sm + 7 * PL;                          // CMOM: 2 slots; pure VOF: 1
-  T* sFF = MOM ? sm + 9 * PL : sm + 8 * PL;
-  T* sRU = sm + 10 * PL;                        // [slot][role] : (k&1)*3 + r
-  T* sUs = sm + 16 * PL;                        // [role]
-  T* sDiv = sm + 19 * PL;
+  T* sF = sm;                                   // 4 slots: plane k&3 (loaded two planes ahead: the PLIC box reaches k+1)
+  T* sU = sm + 4 * PL;                          // 2 slots: plane k&1
+  T* sU0 = sm + 6 * PL;                         // 2 slots
+  T* sM = sm + 8 * PL;                          // CMOM: 2 slots; pure VOF: 1
+  T* sFF = MOM ? sm + 10 * PL : sm + 9 * PL;
+  T* sRU = sm + 11 * PL;                        // [slot][role] : (k&1)*3 + r
+  T* sUs = sm + 17 * PL;                        // [role]
   T* sDil = sm + 20 * PL;                       // 2 slots
   T* sFl = sm + 22 * PL;                        // [role]
+  // interface faces of the current plane, compacted so that the expensive reconstruction runs lane-dense;
+  // the list shares storage with the momentum-flux planes (CMOM) that are written only after it is consumed
+  int* sList = reinterpret_cast<int*>(MOM ? sFl : sm + 10 * PL);
+  int* sCnt = reinterpret_cast<int*>(sm + (size_t)PL * (MOM ? TL::NPLANES_MOM : TL::NPLANES_VOF));
+  if (tid == 0) *sCnt = 0;
 
   // ---- per-entry constants (hoisted out of the march) ----------------------------------------------------------------------
   unsigned flg[TR];
@@ -111,13 +131,14 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
     const int va = oa + la, vb = ob + lb;
     unsigned f = 0;
     if (e < PL) {
-      const bool inU = la >= -1 && la <= TA;
+      const bool inB = lb >= -1 && lb <= TB - 1;  // b-range of every computed region (lb = -2 and lb = TB only feed the PLIC box)
+      const bool inU = inB && la >= -1 && la <= TA;
       if (inU) f |= MF_U;
       if (inU && !(la < 0 && lb < 0) && va <= nA && (perA || va >= 2)) f |= MF_NEEDM;
-      if (la >= -1 && la <= TA - 1) f |= MF_DIL;
-      if (la >= -2 && la <= TA + 1 && lb >= 0) f |= MF_US;
-      if (la >= 0 && la <= TA && lb >= 0 && va <= nA) f |= MF_FL;
-      if (la >= 0 && la <= TA - 1 && lb >= 0 && va <= nA - 1 && vb <= nB - 1) f |= MF_CELL;
+      if (inB && la >= -1 && la <= TA - 1) f |= MF_DIL;
+      if (inB && la >= -2 && la <= TA + 1 && lb >= 0) f |= MF_US;
+      if (inB && la >= 0 && la <= TA && lb >= 0 && va <= nA) f |= MF_FL;
+      if (inB && la >= 0 && la <= TA - 1 && lb >= 0 && va <= nA - 1 && vb <= nB - 1) f |= MF_CELL;
       if (!perA) {
         if (va == 1 || va == 2 || va == nA) f |= MF_DIRA;
         if (va - 1 == 1 || va - 1 == 2 || va - 1 == nA) f |= MF_DIRAM;
@@ -138,39 +159,41 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
     gmo[t] = (int)((ma - 1) * sA + (wb - 1) * sB);
   }
 
-  const FMap<T, 3> F{P.f_in, g};
   const T lr = P.lr, omlr = P.omlr, dt = P.dt;
   const T AA = P.A[J], AB = P.A[DB], AC = P.A[DC];
 
   // ---- asynchronous plane loads ---------------------------------------------------------------------------------------------------
-  auto issue_loads = [&](int vc, bool full) {
+  auto issue_f = [&](int vc) {
+    const T* fp = P.f_in + (long long)(mapc(vc, nC, perC) - 1) * sC;
+    T* dF = sF + (vc & 3) * PL;
+#pragma unroll
+    for (int t = 0; t < TR; ++t) {
+      const int e = tid + t * NT;
+      if (e < PL) cp_async(dF + e, fp + gmm[t]);
+    }
+  };
+  auto issue_rest = [&](int vc, bool full) {
     const long long pm = (long long)(mapc(vc, nC, perC) - 1) * sC;
     const long long po = (long long)((perC ? wrapc(vc, nC) : min(max(vc, 1), nC)) - 1) * sC;
-    const int f3 = ((vc % 3) + 3) % 3, s2 = vc & 1;
-    const T* fp = P.f_in + pm;
+    const int s2 = vc & 1;
     const T* up = P.uj + pm;
     const T* u0p = P.u0j + pm;
-    T* dF = sF + f3 * PL;
     T* dU = sU + s2 * PL;
     T* dU0 = sU0 + s2 * PL;
 #pragma unroll
     for (int t = 0; t < TR; ++t) {
       const int e = tid + t * NT;
-      if (e < PL) {
-        cp_async(dF + e, fp + gmm[t]);
-        if (flg[t] & MF_U) {
-          cp_async(dU + e, up + gom[t]);
-          cp_async(dU0 + e, u0p + gom[t]);
-        }
-        if (MOM && full && (flg[t] & MF_US)) {
-          T* dR = sRU + (s2 * 3) * PL + e;
-          cp_async(dR, P.rhou_in + cA + pm + gom[t]);
-          cp_async(dR + PL, P.rhou_in + cB + pm + gmo[t]);
-          cp_async(dR + 2 * PL, P.rhou_in + cC + po + gmm[t]);
-        }
+      if (flg[t] & MF_U) {
+        cp_async(dU + e, up + gom[t]);
+        cp_async(dU0 + e, u0p + gom[t]);
+      }
+      if (MOM && full && (flg[t] & MF_US)) {
+        T* dR = sRU + (s2 * 3) * PL + e;
+        cp_async(dR, P.rhou_in + cA + pm + gom[t]);
+        cp_async(dR + PL, P.rhou_in + cB + pm + gmo[t]);
+        cp_async(dR + 2 * PL, P.rhou_in + cC + po + gmm[t]);
       }
     }
-    cp_async_commit();
   };
 
   // c̄ of the entries of plane vc (non-first sweeps: read one plane ahead into registers)
@@ -186,8 +209,8 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
   // ---- P2a: VOF face flux + mass flux (+ dilation) of plane vc ---------------------------------------------------------------------
   int cbk[TR];
   auto flux_stage = [&](int vc) {
-    const int f3 = ((vc % 3) + 3) % 3, s2 = vc & 1;
-    const T* cF = sF + f3 * PL;
+    const int s2 = vc & 1;
+    const T* cF = sF + (vc & 3) * PL;
     const T* cU = sU + s2 * PL;
     const T* cU0 = sU0 + s2 * PL;
     T* cM = sM + (MOM ? s2 * PL : 0);
@@ -203,18 +226,11 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
             const bool up = dl > T(0);            // upwind cell la-1, advection.jl:120
             const T fc = cF[up ? e - SA : e];
             const bool ghost = (fl & (up ? MF_GHLO : MF_GHHI)) != 0;
-            if (ghost || fullorempty(fc)) ff = fc * dl;  // advection.jl:125-126
-            else {
-              // rare path: full 3^3 reconstruction straight from global memory
-              const int ia = AX ? e % TL::WA : e / TL::WB, ib = AX ? e / TL::WA : e % TL::WB;
-              const int ua = mapc(oa + ia - TL::HAm - (up ? 1 : 0), nA, perA), ub = mapc(ob + ib - TL::HBm, nB, perB);
-              const int uc = mapc(vc, nC, perC);
-              const int cx = (J == 0) ? ua : ub, cy = (J == 0) ? ub : ((J == 1) ? ua : uc), cz = (J == 2) ? ua : uc;
-              FBox<T, 3> B{F, cx, cy, cz};
-              ff = plic_face_flux<T, 3>(P.scheme, B, fc, J, dl);  // advection.jl:131-134
-            }
-            m = dl * lr + omlr * ff;  // fᶠ2ρuf, VOFutil.jl:218
-            if (MOM) m = m * P.idt;   // rmul!(ρuf, inv(δt)), flow.jl:207
+            if (ghost || fullorempty(fc)) {       // advection.jl:125-126
+              ff = fc * dl;
+              m = dl * lr + omlr * ff;            // fᶠ2ρuf, VOFutil.jl:218
+              if (MOM) m = m * P.idt;             // rmul!(ρuf, inv(δt)), flow.jl:207
+            } else sList[atomicAdd(sCnt, 1)] = e;  // interface face: reconstructed lane-dense in plic_stage
           }
         }
         sFF[e] = ff;
@@ -225,17 +241,35 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
         const T div = (cU[e2 + SA] - cU[e2]) + (cU0[e2 + SA] - cU0[e2]);  // ∂(d,I,u)+∂(d,I,u⁰)
         const int cb = P.first ? ((cF[e] < T(0.5)) ? 0 : 1) : cbn[t];  // flow.jl:172 (c̄ from the incoming f)
         cbk[t] = cb;
-        sDiv[e] = div;
         sDil[s2 * PL + e] = (lin_interp(T(cb), lr, omlr) * div) / T(2);  // flow.jl:216
       }
+    }
+  };
+  // PLIC reconstruction + flux of the compacted interface faces (general branch of getVOFFlux!, advection.jl:131-134)
+  auto plic_stage = [&](int vc, int cnt) {
+    const int s2 = vc & 1;
+    const T* cF = sF + (vc & 3) * PL;
+    const T* cU = sU + s2 * PL;
+    const T* cU0 = sU0 + s2 * PL;
+    T* cM = sM + (MOM ? s2 * PL : 0);
+    for (int i = tid; i < cnt; i += NT) {
+      const int e = sList[i];
+      const T dl = P.hdt * (cU[e] + cU0[e]);
+      const int eu = (dl > T(0)) ? e - SA : e;
+      SBox<T, J, PL, SA, SB> B{sF, eu, vc};
+      const T ff = plic_face_flux<T, 3>(P.scheme, B, cF[eu], J, dl);
+      T m = dl * lr + omlr * ff;
+      if (MOM) m = m * P.idt;
+      sFF[e] = ff;
+      cM[e] = m;
     }
   };
 
   // ---- P2b: u★ = BC!(ρu/ρ(f̄)) of plane vc (flow.jl:197, VOFutil.jl:198-201) -----------------------------------------------------------
   auto ustar_stage = [&](int vc) {
-    const int f3 = ((vc % 3) + 3) % 3, p3 = (((vc - 1) % 3) + 3) % 3, s2 = vc & 1;
-    const T* cF = sF + f3 * PL;
-    const T* pF = sF + p3 * PL;
+    const int s2 = vc & 1;
+    const T* cF = sF + (vc & 3) * PL;
+    const T* pF = sF + ((vc - 1) & 3) * PL;
     const T* cR = sRU + (s2 * 3) * PL;
     const bool dirC = !perC && (vc == 2 || vc == nC);
 #pragma unroll
@@ -244,9 +278,9 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
       const unsigned fl = flg[t];
       if (fl & MF_US) {
         const T fc = cF[e];
-        const T ra = cR[e] / lin_interp((fc + cF[e - SA]) / T(2), lr, omlr);
-        const T rb = cR[PL + e] / lin_interp((fc + cF[e - SB]) / T(2), lr, omlr);
-        const T rc = cR[2 * PL + e] / lin_interp((fc + pF[e]) / T(2), lr, omlr);
+        const T ra = t_div(cR[e], lin_interp((fc + cF[e - SA]) / T(2), lr, omlr));
+        const T rb = t_div(cR[PL + e], lin_interp((fc + cF[e - SB]) / T(2), lr, omlr));
+        const T rc = t_div(cR[2 * PL + e], lin_interp((fc + pF[e]) / T(2), lr, omlr));
         sUs[e] = (fl & MF_DIRA) ? AA : ra;  // Dirichlet planes of BC!
         sUs[PL + e] = (fl & MF_DIRB) ? AB : rb;
         sUs[2 * PL + e] = dirC ? AC : rc;
@@ -256,9 +290,9 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
 
   // ---- P3: SynDRoM momentum flux through the lower a-face of every momentum cell of the tile -----------------------------------------------
   auto mom_flux_stage = [&](int vc) {
-    const int f3 = ((vc % 3) + 3) % 3, p3 = (((vc - 1) % 3) + 3) % 3, s2 = vc & 1;
-    const T* cF = sF + f3 * PL;
-    const T* pF = sF + p3 * PL;
+    const int s2 = vc & 1;
+    const T* cF = sF + (vc & 3) * PL;
+    const T* pF = sF + ((vc - 1) & 3) * PL;
     const T* cM = sM + s2 * PL;
     const T* pM = sM + (s2 ^ 1) * PL;
 #pragma unroll
@@ -316,8 +350,8 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
   unsigned int amax = 0, amin = 0;
   int rnan = 0;
   auto update_stage = [&](int vc) {
-    const int f3 = ((vc % 3) + 3) % 3, s2 = vc & 1;
-    const T* cF = sF + f3 * PL;
+    const int s2 = vc & 1;
+    const T* cF = sF + (vc & 3) * PL;
     const T* cU = sU + s2 * PL;
     const T* cU0 = sU0 + s2 * PL;
     const T* cM = sM + (MOM ? s2 * PL : 0);
@@ -330,12 +364,9 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
         const long long lk = pc + gmm[t];  // owned cells are interior: the mapped offset is the cell itself
         const T fK = cF[e];
         int cb;
-        T div;
-        if (MOM) { cb = cbk[t]; div = sDiv[e]; }
-        else {
-          cb = P.first ? ((fK < T(0.5)) ? 0 : 1) : (int)P.cbar[lk];
-          div = (cU[e + SA] - cU[e]) + (cU0[e + SA] - cU0[e]);
-        }
+        if (MOM) cb = cbk[t];
+        else cb = P.first ? ((fK < T(0.5)) ? 0 : 1) : (int)P.cbar[lk];
+        const T div = (cU[e + SA] - cU[e]) + (cU0[e + SA] - cU0[e]);
         if (P.first) P.cbar[lk] = (int8_t)cb;
         // f[I] += fᶠ[I]-fᶠ[I+δ] + c̄[I]*(∂u+∂u⁰)*δt/2          advection.jl:83
         T fn = fK + ((sFF[e] - sFF[e + SA]) + ((T(cb) * div) * dt) / T(2));
@@ -371,31 +402,62 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
   };
 
   // ---- march -----------------------------------------------------------------------------------------------------------------------------------
+  // one directional VOF flux pass over plane vc: mark + (if any interface face) lane-dense reconstruction
+  auto vof_flux = [&](int vc) {
+    flux_stage(vc);
+  };
   if (MOM) {
-    // prologue: plane k0-1 supplies f, mass flux and dilation of the previous plane
-    issue_loads(k0 - 1, false);
+    // prologue: plane k0-1 supplies f, mass flux and dilation of the previous plane (its PLIC box reaches k0-2 .. k0)
+    issue_f(k0 - 2); issue_f(k0 - 1); issue_f(k0);
+    issue_rest(k0 - 1, false);
+    cp_async_commit();
     load_cbar(k0 - 1);
     cp_async_wait_all();
     __syncthreads();
-    issue_loads(k0, true);
-    flux_stage(k0 - 1);
+    issue_f(k0 + 1);
+    issue_rest(k0, true);
+    cp_async_commit();
+    vof_flux(k0 - 1);
+    __syncthreads();
+    {
+      const int cnt = *sCnt;
+      if (cnt > 0) plic_stage(k0 - 1, cnt);
+    }
     load_cbar(k0);
+    __syncthreads();
+    if (tid == 0) *sCnt = 0;
   } else {
-    issue_loads(k0, true);
+    issue_f(k0 - 1); issue_f(k0); issue_f(k0 + 1);
+    issue_rest(k0, true);
+    cp_async_commit();
   }
   for (int k = k0; k < k1; ++k) {
     cp_async_wait_all();
-    __syncthreads();
-    if (k + 1 < k1) issue_loads(k + 1, true);
-    flux_stage(k);
+    __syncthreads();  // S1: plane k (and f of plane k+1) landed for every thread
+    if (k + 1 < k1) {
+      issue_f(k + 2);
+      issue_rest(k + 1, true);
+      cp_async_commit();
+    }
+    vof_flux(k);
     if (MOM) {
       if (k + 1 < k1) load_cbar(k + 1);
       ustar_stage(k);
-      __syncthreads();
-      mom_flux_stage(k);
     }
-    __syncthreads();
+    __syncthreads();  // S2
+    {
+      const int cnt = *sCnt;  // block-uniform
+      if (cnt > 0) {
+        plic_stage(k, cnt);
+        __syncthreads();
+      }
+    }
+    if (MOM) {
+      mom_flux_stage(k);
+      __syncthreads();  // S3
+    }
     update_stage(k);
+    if (tid == 0) *sCnt = 0;
   }
 
   // ---- fill-error reduction: warp shuffles, then one atomic per warp (replaces findmax/findmin + host sync) -----------------------------------

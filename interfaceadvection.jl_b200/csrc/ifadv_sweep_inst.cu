@@ -88,9 +88,9 @@ template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStrea
     if (c->use_march) {
       // tile shapes sized so that 25 shared planes leave 3 (f32) / 2-3 (f64) CTAs per SM
       constexpr int TO = (sizeof(T) == 4) ? 16 : 8;
-      constexpr int TAX = (sizeof(T) == 4) ? 64 : 32;
+      constexpr int TBX = (sizeof(T) == 4) ? 16 : 8;
       constexpr int MB = (sizeof(T) == 4) ? 3 : 2;
-      if (q.j == 0) return launch_march_t<T, 0, TAX, 8, MOM, MB>(c, st, q);
+      if (q.j == 0) return launch_march_t<T, 0, 32, TBX, MOM, MB>(c, st, q);
       if (q.j == 1) return launch_march_t<T, 1, TO, 32, MOM, MB>(c, st, q);
       return launch_march_t<T, 2, TO, 32, MOM, MB>(c, st, q);
     }
