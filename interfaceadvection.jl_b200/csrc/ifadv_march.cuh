@@ -33,7 +33,19 @@ template <int J, int TA, int TB, int NT> struct MTile {
   static constexpr int WA = TA + HAm + HAp, WB = TB + HBm + HBp;
   static constexpr int PL = WA * WB;                      // entries of one shared plane
   static constexpr int SA = AX ? 1 : WB, SB = AX ? WA : 1;  // x fastest; entry index == shared index
-  static constexpr int TRIPS = (PL + NT - 1) / NT;
+  // Entry enumeration: in the main trips a warp owns whole rows of the 32 tile columns along x (all lanes active in
+  // every stage); the few halo columns are enumerated separately in one extra trip, so no stage pays for idle lanes.
+  static constexpr int NW = NT / 32;
+  static constexpr int ROWS = AX ? WB : WA;                 // rows = the non-contiguous in-plane direction
+  static constexpr int WX = AX ? WA : WB;                   // row length (x)
+  static constexpr int HXm = AX ? HAm : HBm;                // halo columns left of the tile
+  static constexpr int NHC = WX - 32;                       // halo columns per row
+  static constexpr int TM = (ROWS + NW - 1) / NW;           // main trips
+  static constexpr int NH = ROWS * NHC;                     // halo entries
+  static constexpr int TH = (NH + NT - 1) / NT;             // halo trips
+  static constexpr int TRIPS = TM + TH;
+  static constexpr int ESTR = NW * WX;                      // entry stride between main trips
+  static_assert((AX ? TA : TB) == 32, "the tile must be 32 cells wide along x");
   // CMOM planes: F x4, U x2, U0 x2, M x2, FF, RU x6, Us x3, Dil x2, Fl x3 = 25 ; pure VOF: F x4, U x2, U0 x2, M, FF, list = 11
   static constexpr int NPLANES_MOM = 25, NPLANES_VOF = 11;
   template <class T> static constexpr size_t smem_bytes(bool mom) { return sizeof(T) * (size_t)PL * (mom ? NPLANES_MOM : NPLANES_VOF) + 16; }
@@ -54,7 +66,8 @@ enum : unsigned {
   MF_RVAR = 1u << 11,   // ϕuR face (va == nA, a not periodic)
   MF_GHLO = 1u << 12,   // cell la-1 is a ghost cell on a non-periodic side (no PLIC reconstruction)
   MF_GHHI = 1u << 13,   // cell la itself is one
-  MF_TOPA = 1u << 14,   // owned cell with va == nA-1 (writes the boundary face of ρuf in the pure-VOF path)
+  MF_TOPA = 1u << 14,
+  MF_VALID = 1u << 15,  // entry exists (trip slot in use)   // owned cell with va == nA-1 (writes the boundary face of ρuf in the pure-VOF path)
 };
 
 template <class T> IFADV_DI void cp_async(T* smem_dst, const T* gsrc) {
@@ -122,15 +135,25 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
   unsigned flg[TR];
   int gmm[TR];  // offset within a c-plane, both in-plane indices mapped to the interior (f, c̄, tangential components)
   int gom[TR];  // a as stored (component a / u_a faces), b mapped
-  int gmo[TR];  // a mapped, b as stored (component b)
+  const int lane = tid & 31, warp = tid >> 5;
+  const int e0 = warp * TL::WX + TL::HXm + lane;  // main-trip entry of trip 0; trip t adds t*ESTR
+  int eh[TL::TH > 0 ? TL::TH : 1];
+#pragma unroll
+  for (int h = 0; h < TL::TH; ++h) {
+    const int q = tid + h * NT, row = q / TL::NHC, c = q % TL::NHC;
+    eh[h] = row * TL::WX + (c < TL::HXm ? c : c + 32);
+  }
+  auto ent = [&](int t) -> int { return (t < TL::TM) ? e0 + t * TL::ESTR : eh[(t < TL::TM) ? 0 : t - TL::TM]; };
 #pragma unroll
   for (int t = 0; t < TR; ++t) {
-    const int e = tid + t * NT;
+    const int e = ent(t);
+    const bool valid = (t < TL::TM) ? (warp + t * TL::NW < TL::ROWS) : (tid + (t - TL::TM) * NT < TL::NH);
     const int ia = AX ? e % TL::WA : e / TL::WB, ib = AX ? e / TL::WA : e % TL::WB;
     const int la = ia - TL::HAm, lb = ib - TL::HBm;
     const int va = oa + la, vb = ob + lb;
     unsigned f = 0;
-    if (e < PL) {
+    if (valid) {
+      f |= MF_VALID;
       const bool inB = lb >= -1 && lb <= TB - 1;  // b-range of every computed region (lb = -2 and lb = TB only feed the PLIC box)
       const bool inU = inB && la >= -1 && la <= TA;
       if (inU) f |= MF_U;
@@ -153,10 +176,9 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
     }
     flg[t] = f;
     const int ma = mapc(va, nA, perA), mb = mapc(vb, nB, perB);
-    const int wa = perA ? wrapc(va, nA) : min(max(va, 1), nA), wb = perB ? wrapc(vb, nB) : min(max(vb, 1), nB);
+    const int wa = perA ? wrapc(va, nA) : min(max(va, 1), nA);
     gmm[t] = (int)((ma - 1) * sA + (mb - 1) * sB);
-    gom[t] = (int)((wa - 1) * sA + (mb - 1) * sB);
-    gmo[t] = (int)((ma - 1) * sA + (wb - 1) * sB);
+    gom[t] = (int)((wa - 1) * sA + (mb - 1) * sB);  // (component b "as stored" == mapped: its entries all have vb interior)
   }
 
   const T lr = P.lr, omlr = P.omlr, dt = P.dt;
@@ -168,8 +190,8 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
     T* dF = sF + (vc & 3) * PL;
 #pragma unroll
     for (int t = 0; t < TR; ++t) {
-      const int e = tid + t * NT;
-      if (e < PL) cp_async(dF + e, fp + gmm[t]);
+      const int e = ent(t);
+      if (flg[t] & MF_VALID) cp_async(dF + e, fp + gmm[t]);
     }
   };
   auto issue_rest = [&](int vc, bool full) {
@@ -182,15 +204,21 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
     T* dU0 = sU0 + s2 * PL;
 #pragma unroll
     for (int t = 0; t < TR; ++t) {
-      const int e = tid + t * NT;
+      const int e = ent(t);
       if (flg[t] & MF_U) {
         cp_async(dU + e, up + gom[t]);
         cp_async(dU0 + e, u0p + gom[t]);
       }
+      if (MOM && full && (flg[t] & MF_CELL)) {  // uOld of the next plane: pull the lines into L2/L1 ahead of the update stage
+        const T* uo = P.uOld + (long long)(vc - 1) * sC + gmm[t];
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(uo + cA));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(uo + cB));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(uo + cC));
+      }
       if (MOM && full && (flg[t] & MF_US)) {
         T* dR = sRU + (s2 * 3) * PL + e;
         cp_async(dR, P.rhou_in + cA + pm + gom[t]);
-        cp_async(dR + PL, P.rhou_in + cB + pm + gmo[t]);
+        cp_async(dR + PL, P.rhou_in + cB + pm + gmm[t]);
         cp_async(dR + 2 * PL, P.rhou_in + cC + po + gmm[t]);
       }
     }
@@ -216,7 +244,7 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
     T* cM = sM + (MOM ? s2 * PL : 0);
 #pragma unroll
     for (int t = 0; t < TR; ++t) {
-      const int e = tid + t * NT;
+      const int e = ent(t);
       const unsigned fl = flg[t];
       if (fl & MF_U) {
         T ff = T(0), m = T(0);
@@ -274,7 +302,7 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
     const bool dirC = !perC && (vc == 2 || vc == nC);
 #pragma unroll
     for (int t = 0; t < TR; ++t) {
-      const int e = tid + t * NT;
+      const int e = ent(t);
       const unsigned fl = flg[t];
       if (fl & MF_US) {
         const T fc = cF[e];
@@ -297,7 +325,7 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
     const T* pM = sM + (s2 ^ 1) * PL;
 #pragma unroll
     for (int t = 0; t < TR; ++t) {
-      const int e = tid + t * NT;
+      const int e = ent(t);
       const unsigned fl = flg[t];
       if (fl & MF_FL) {
         // BC-aware mass flux (velocity BC! on ρuf: Dirichlet planes of component a), flow.jl:207
@@ -358,7 +386,7 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
     const long long pc = (long long)(vc - 1) * sC;
 #pragma unroll
     for (int t = 0; t < TR; ++t) {
-      const int e = tid + t * NT;
+      const int e = ent(t);
       const unsigned fl = flg[t];
       if (fl & MF_CELL) {
         const long long lk = pc + gmm[t];  // owned cells are interior: the mapped offset is the cell itself

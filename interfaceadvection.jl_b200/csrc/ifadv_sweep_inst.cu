@@ -71,8 +71,8 @@ static int launch_march_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   const int tx = TL::AX ? TA : TB, to = TL::AX ? TB : TA;
   // chunk the march direction so that the grid holds several waves of CTAs
   const long long tiles = (long long)((nx + tx - 1) / tx) * ((no + to - 1) / to);
-  int chunk = 32;
-  while (chunk > 8 && tiles * ((nc + chunk - 1) / chunk) < 148 * 8) chunk >>= 1;
+  int chunk = 64;
+  while (chunk > 8 && tiles * ((nc + chunk - 1) / chunk) < 148 * 6) chunk >>= 1;
   dim3 grid((unsigned)((nx + tx - 1) / tx), (unsigned)((no + to - 1) / to), (unsigned)((nc + chunk - 1) / chunk));
   const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
   if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
@@ -89,7 +89,7 @@ template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStrea
       // tile shapes sized so that 25 shared planes leave 3 (f32) / 2-3 (f64) CTAs per SM
       constexpr int TO = (sizeof(T) == 4) ? 16 : 8;
       constexpr int TBX = (sizeof(T) == 4) ? 16 : 8;
-      constexpr int MB = (sizeof(T) == 4) ? 3 : 2;
+      constexpr int MB = 2;
       if (q.j == 0) return launch_march_t<T, 0, 32, TBX, MOM, MB>(c, st, q);
       if (q.j == 1) return launch_march_t<T, 1, TO, 32, MOM, MB>(c, st, q);
       return launch_march_t<T, 2, TO, 32, MOM, MB>(c, st, q);
