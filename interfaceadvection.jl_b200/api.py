@@ -122,20 +122,21 @@ def sum_inside(f) -> float:
     return context_for(f).sum_inside(_stream(f), _p(f))
 
 
-def _cell_centres(shape, dtype, device):
+def _cell_centres(shape, dtype, device, origin=None):
     D = len(shape)
+    o = origin or (0,) * D
     grids = torch.meshgrid(*[torch.arange(n, device=device, dtype=dtype) for n in shape], indexing="ij")
-    # 0-based idx <-> Julia I = idx+1; loc(0,I) = I - 1.5
-    return torch.stack([g - 0.5 for g in grids], dim=-1)
+    # 0-based idx <-> Julia I = idx+1; loc(0,I) = I - 1.5 (+ the global offset of a slab)
+    return torch.stack([g - 0.5 + o[k] for k, g in enumerate(grids)], dim=-1)
 
 
-def applyVOF(f, alpha, nhat, InterfaceSDF: Optional[Callable]):
+def applyVOF(f, alpha, nhat, InterfaceSDF: Optional[Callable], origin=None):
     """applyVOF!(f,α,n̂,InterfaceSDF)  (VOFutil.jl:8-37).  InterfaceSDF maps a (..., D) tensor of positions to
     signed distances (dark fluid negative) and is evaluated on the device in f's dtype."""
     if InterfaceSDF is None:
         return
     D = f.dim()
-    xc = _cell_centres(f.shape, f.dtype, f.device)
+    xc = _cell_centres(f.shape, f.dtype, f.device, origin)
     dx = torch.tensor(0.01, dtype=f.dtype, device=f.device)
 
     def colmajor(t):
@@ -159,7 +160,7 @@ class cVOF:
     """cVOF(N; T, InterfaceSDF, μ, λμ, λρ, η, normalScheme, perdir)  (src/cVOF.jl:45-89)"""
 
     def __init__(self, N, T=torch.float32, InterfaceSDF=None, mu=1e-3, lam_mu=1e-2, lam_rho=1e-3, eta=None, normalScheme="WH",
-                 perdir=(), device="cuda"):
+                 perdir=(), device="cuda", origin=None):
         D = len(N)
         Ng = tuple(n + 2 for n in N)
         Nv = Ng + (D,)
@@ -171,7 +172,7 @@ class cVOF:
         self.cbar = jl_zeros(Ng, torch.int8, device)
         self.perdir = tuple(perdir)
         if InterfaceSDF is not None:
-            applyVOF(self.f, self.alpha, self.nhat, InterfaceSDF)
+            applyVOF(self.f, self.alpha, self.nhat, InterfaceSDF, origin)
             BCf(self.f, self.perdir)
         self.f0 = self.f.clone(memory_format=torch.preserve_format)
         self.ff = jl_zeros(Ng, T, device)

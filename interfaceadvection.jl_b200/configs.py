@@ -16,8 +16,9 @@ class _NP:
     pi = math.pi
 
     @staticmethod
-    def coords(Ng, dtype):
-        return [g.astype(dtype) - dtype(0.5) for g in np.meshgrid(*[np.arange(n) for n in Ng], indexing="ij")]
+    def coords(Ng, dtype, origin=None):
+        o = origin or (0,) * len(Ng)
+        return [g.astype(dtype) - dtype(0.5) + dtype(o[k]) for k, g in enumerate(np.meshgrid(*[np.arange(n) for n in Ng], indexing="ij"))]
 
     sin, cos, sqrt, minimum, maximum, abs = np.sin, np.cos, np.sqrt, np.minimum, np.maximum, np.abs
 
@@ -37,8 +38,10 @@ def _torch_shim(device):
         pi = math.pi
 
         @staticmethod
-        def coords(Ng, dtype):
-            return [g - 0.5 for g in torch.meshgrid(*[torch.arange(n, device=device, dtype=dtype) for n in Ng], indexing="ij")]
+        def coords(Ng, dtype, origin=None):
+            o = origin or (0,) * len(Ng)
+            gs = torch.meshgrid(*[torch.arange(n, device=device, dtype=dtype) for n in Ng], indexing="ij")
+            return [g - 0.5 + o[k] for k, g in enumerate(gs)]
 
         sin, cos, sqrt, minimum, maximum, abs = torch.sin, torch.cos, torch.sqrt, torch.minimum, torch.maximum, torch.abs
 
@@ -63,10 +66,10 @@ def backend(device=None):
 
 
 # ---- velocity fields (sampled at face centres; all discretely solenoidal to round-off) --------------
-def rigid_rotation(N, dtype, omega=None, xp=_NP):
+def rigid_rotation(N, dtype, omega=None, xp=_NP, Nl=None, origin=None):
     """C1: u = -Ω(y-c), v = Ω(x-c) about the domain centre; Ω = 2π/(16 N) so that |u|Δt <= 0.2 with Δt = 1."""
-    Ng = tuple(n + 2 for n in N)
-    X = xp.coords(Ng, dtype)
+    Ng = tuple(n + 2 for n in (Nl or N))
+    X = xp.coords(Ng, dtype, origin)
     om = (2 * math.pi / (16 * N[0])) if omega is None else omega
     cx, cy = N[0] / 2, N[1] / 2
     u = -om * (X[1] - cy)      # x-face: y is the cell-centre coordinate
@@ -74,12 +77,12 @@ def rigid_rotation(N, dtype, omega=None, xp=_NP):
     return xp.stack([u, v])
 
 
-def tgv(N, dtype, U=0.25, xp=_NP):
+def tgv(N, dtype, U=0.25, xp=_NP, Nl=None, origin=None):
     """Taylor-Green field of test/alloctest.jl:16-21 / test/helper.jl:7-9 scaled to the box: zero normal velocity on
     every wall and periodic with the box length, so it serves walls and periodic configs alike."""
     D = len(N)
-    Ng = tuple(n + 2 for n in N)
-    X = xp.coords(Ng, dtype)
+    Ng = tuple(n + 2 for n in (Nl or N))
+    X = xp.coords(Ng, dtype, origin)
 
     def sc(k, face):  # scaled coordinate (2x - N)π/N of dimension k, on the lower face if `face`
         x = X[k] - (0.5 if face else 0.0)
@@ -96,11 +99,11 @@ def tgv(N, dtype, U=0.25, xp=_NP):
     return xp.stack([u, v, xp.zeros_like(u)])
 
 
-def enright(N, dtype, amp=0.2, xp=_NP):
+def enright(N, dtype, amp=0.2, xp=_NP, Nl=None, origin=None):
     """C2: LeVeque/Enright deformation field as the DISCRETE CURL of a vector potential sampled on cell edges
     (exactly discretely solenoidal).  A = (0, -sin²(πx̂)sin(2πŷ)sin²(πẑ)/π, sin²(πx̂)sin²(πŷ)sin(2πẑ)/π)·N·amp/2."""
-    Ng = tuple(n + 2 for n in N)
-    X = xp.coords(Ng, dtype)
+    Ng = tuple(n + 2 for n in (Nl or N))
+    X = xp.coords(Ng, dtype, origin)
     n = float(N[0])
 
     def h(k, lower):  # normalised coordinate of dimension k at the cell centre or the lower face/edge
@@ -197,8 +200,10 @@ CONFIGS = {
 }
 
 
-def make_case(name_or_N, dtype=None, device=None, kind=None):
-    """Return dict(N, sdf, u, perdir, lam_rho, cmom) for a named config, or for an explicit (N, kind) at reduced size."""
+def make_case(name_or_N, dtype=None, device=None, kind=None, Nl=None, origin=None):
+    """Return dict(N, sdf, u, perdir, lam_rho, cmom) for a named config, or for an explicit (N, kind) at reduced size.
+    Nl / origin: sample the velocity on a sub-box of Nl cells whose first interior cell has global index origin+1
+    (slab decomposition); N always describes the GLOBAL box the analytic fields are scaled to."""
     if isinstance(name_or_N, str):
         cfg = dict(CONFIGS[name_or_N])
         kind = name_or_N.split("_")[0]
@@ -218,16 +223,17 @@ def make_case(name_or_N, dtype=None, device=None, kind=None):
         import torch
 
         T = getattr(torch, dtype)
+    kw = dict(xp=xp, Nl=Nl, origin=origin)
     if kind == "C1":
-        sdf, u = sdf_zalesak(N[0]), rigid_rotation(N, T, xp=xp)
+        sdf, u = sdf_zalesak(N[0]), rigid_rotation(N, T, **kw)
     elif kind == "C2":
-        sdf, u = sdf_sphere([0.35 * n for n in N], 0.15 * N[0]), enright(N, T, xp=xp)
+        sdf, u = sdf_sphere([0.35 * n for n in N], 0.15 * N[0]), enright(N, T, **kw)
     elif kind == "C3":
-        sdf, u = sdf_dambreak(N), tgv(N, T, xp=xp)
+        sdf, u = sdf_dambreak(N), tgv(N, T, **kw)
     elif kind == "C4":
-        sdf, u = sdf_sphere([N[0] / 2, N[1] / 2, N[2] / 4], N[0] / 8, inside_dark=False), tgv(N, T, xp=xp)
+        sdf, u = sdf_sphere([N[0] / 2, N[1] / 2, N[2] / 4], N[0] / 8, inside_dark=False), tgv(N, T, **kw)
     elif kind == "C5":
-        sdf, u = sdf_sloshing(N), tgv(N, T, xp=xp)
+        sdf, u = sdf_sloshing(N), tgv(N, T, **kw)
     else:
         raise KeyError(kind)
     cfg.update(sdf=sdf, u=u, dtype=dtype, kind=kind)
