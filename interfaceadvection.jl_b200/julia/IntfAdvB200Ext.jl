@@ -1,0 +1,142 @@
+# IntfAdvB200Ext.jl -- package extension that routes InterfaceAdvection.jl's VOF + CMOM advection path to
+# libifadv_b200.so (hand-written sm_100a CUDA, C ABI in include/ifadv.h) for CuArray arguments.
+#
+# It replaces ext/IntfAdvCUDAExt.jl ON THIS PATH: instead of only allowing scalar indexing (the 8 lines the stock
+# extension consists of, ext/IntfAdvCUDAExt.jl:19-23) it overrides the two sweep drivers
+#     advectVOF!     (src/advection.jl:34)      and      advectVOFρuu!  (src/flow.jl:165)
+# plus the secondary seams u2ρu!/ρu2u! (src/VOFutil.jl:198-211) and MPCFL (src/flow.jl:262) for CuArray{Float32|Float64}.
+# No KernelAbstractions, no multi-backend dispatch, no CPU fallback: unsupported argument combinations raise.
+#
+# NOTE: no Julia toolchain exists in the environment this library was built in, so this file has been written
+# against the C header but never executed (INTEGRATION.md).  Install: copy to ext/, add to Project.toml
+#     [extensions]  IntfAdvB200Ext = "CUDA"      (instead of IntfAdvCUDAExt)
+# and point ENV["IFADV_B200_LIB"] at libifadv_b200.so.
+module IntfAdvB200Ext
+
+using CUDA
+using InterfaceAdvection
+import InterfaceAdvection: advectVOF!, advectVOFρuu!, u2ρu!, ρu2u!, MPCFL, _scalar_op, cVOF
+import InterfaceAdvection: getInterfaceNormal_WH!, getInterfaceNormal_WY!, getInterfaceNormal_Column!, getInterfaceNormal_PCD!,
+                           getInterfaceNormal_SLIC!, getInterfaceNormal_MYC!, getInterfaceNormal_Y!, getInterfaceNormal_CD!,
+                           getInterfaceNormal_XYLIC!
+import InterfaceAdvection: upwind, minmod, Koren, vanAlbada1, Sweby, superbee, TVDcen, TVDdown
+import WaterLily
+import WaterLily: Flow, quick, vanLeer, cds
+
+const LIB = get(ENV, "IFADV_B200_LIB", "libifadv_b200.so")
+
+__init__() = @assert CUDA.functional()
+
+# the stock extension's only job stays available for the diagnostics that still index scalars
+_scalar_op(op::F, ::CUDA.CuArray) where {F<:Function} = CUDA.@allowscalar op()
+
+# ---- function identity -> enum (include/ifadv.h) -------------------------------------------------------------------
+const NORMAL_ENUM = IdDict{Any,Cint}(
+    getInterfaceNormal_WH! => 0, getInterfaceNormal_WY! => 1, getInterfaceNormal_Column! => 2, getInterfaceNormal_PCD! => 3,
+    getInterfaceNormal_SLIC! => 4, getInterfaceNormal_MYC! => 5, getInterfaceNormal_Y! => 6, getInterfaceNormal_CD! => 7,
+    getInterfaceNormal_XYLIC! => 8)
+const LIMITER_ENUM = IdDict{Any,Cint}(
+    upwind => 0, minmod => 1, Koren => 2, vanAlbada1 => 3, Sweby => 4, superbee => 5, TVDcen => 6, TVDdown => 7,
+    quick => 8, vanLeer => 9, cds => 10)
+normal_enum(f) = get(NORMAL_ENUM, f) do; error("IntfAdvB200Ext: normalScheme $f has no sm_100a kernel (no fallback)"); end
+limiter_enum(f) = get(LIMITER_ENUM, f) do; error("IntfAdvB200Ext: limiter $f has no sm_100a kernel (no fallback)"); end
+perdir_mask(perdir) = reduce(|, (UInt32(1) << (j - 1) for j in perdir); init=UInt32(0))
+dtype_enum(::Type{Float32}) = Cint(0)
+dtype_enum(::Type{Float64}) = Cint(1)
+
+struct IfadvReport
+    maxf::Cdouble; minf::Cdouble
+    argmax::NTuple{3,Int64}; argmin::NTuple{3,Int64}
+    dir::Cint; status::Cint
+end
+
+# ---- one context per (device, size, eltype) ----------------------------------------------------------------------------
+const CONTEXTS = Dict{Tuple{Int,NTuple{3,Int64},DataType},Ptr{Cvoid}}()
+function context(f::CuArray{T,D}) where {T,D}
+    Ng = ntuple(i -> i <= D ? Int64(size(f, i)) : Int64(1), 3)
+    key = (CUDA.deviceid(CUDA.device()), Ng, T)
+    get!(CONTEXTS, key) do
+        ctx = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:ifadv_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Ref{NTuple{3,Int64}}, Cint, Cint),
+                   ctx, D, Ref(Ng), dtype_enum(T), key[1])
+        rc == 0 || error("ifadv_create failed ($rc)")
+        ctx[]
+    end
+end
+stream_ptr() = Base.unsafe_convert(Ptr{Cvoid}, CUDA.stream().handle)
+dptr(a::CuArray) = reinterpret(Ptr{Cvoid}, UInt(pointer(a)))
+function check(ctx, rc)
+    rc == -1 && error("NaN!")                                   # error("NaN!"), src/advection.jl:148
+    rc < 0 && error("ifadv error $rc: " * unsafe_string(ccall((:ifadv_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx)))
+    rc
+end
+function report(rc, rep::IfadvReport)
+    rc > 0 || return
+    which, Δ, idx = (rc & 1) != 0 ? ("max", rep.maxf - 1, rep.argmax) : ("min", -rep.minf, rep.argmin)
+    Base.printstyled("ERROR: "; color=:red, bold=true)   # printed, not thrown -- like reportFillError (advection.jl:161-166)
+    println("$which VOF @ $idx ∉ [0,1] @ direction $(rep.dir), Δf = $Δ")
+end
+const CHECK_EVERY = Ref(1)   # set to k > 1 to fetch the fill-error report (a stream sync) only every k-th call
+const CALLS = Ref(0)
+
+# ---- advectVOF!  (src/advection.jl:34-78) ----------------------------------------------------------------------------------
+function advectVOF!(f::CuArray{T,D}, fᶠ, α, n̂, u, u⁰, Δt, c̄, ρuf, λρ, normalScheme; perdir=(), dirO=nothing) where {T<:Union{Float32,Float64},D}
+    ctx = context(f)
+    dO = isnothing(dirO) ? Random.shuffle(1:D) : dirO
+    dirv = Cint[dO...; zeros(Cint, 3 - D)]
+    rep = Ref(IfadvReport(0, 0, (0, 0, 0), (0, 0, 0), 0, 0))
+    want = (CALLS[] += 1) % CHECK_EVERY[] == 0
+    rc = ccall((:ifadv_advect_vof, LIB), Cint,
+               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Ptr{Cvoid},
+                Cdouble, Cint, Cuint, Ptr{Cint}, Cint, Ptr{IfadvReport}),
+               ctx, stream_ptr(), dptr(f), dptr(fᶠ), dptr(α), dptr(n̂), dptr(u), dptr(u⁰), Δt, dptr(c̄), dptr(ρuf),
+               λρ, normal_enum(normalScheme), perdir_mask(perdir), dirv, 0, want ? rep : C_NULL)
+    report(check(ctx, rc), rep[])
+    nothing
+end
+
+# ---- advectVOFρuu!  (src/flow.jl:165-210) ------------------------------------------------------------------------------------
+function advectVOFρuu!(f::CuArray{T,D}, fᶠ, α, n̂, u, u⁰, Δt, c̄, ρu, r, Φ, ρuf, uStar, uOld, dilaU, dρ, λρ, λ, normalScheme, uBC;
+                       perdir=(), exitBC=false, dirO=nothing) where {T<:Union{Float32,Float64},D}
+    uBC isa Function && error("IntfAdvB200Ext: function-valued uBC is not supported (no fallback)")
+    ctx = context(f)
+    dO = isnothing(dirO) ? Random.shuffle(1:D) : dirO
+    dirv = Cint[dO...; zeros(Cint, 3 - D)]
+    A = Cdouble[uBC...; zeros(3 - D)]
+    rep = Ref(IfadvReport(0, 0, (0, 0, 0), (0, 0, 0), 0, 0))
+    want = (CALLS[] += 1) % CHECK_EVERY[] == 0
+    rc = ccall((:ifadv_advect_vof_rhouu, LIB), Cint,
+               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid},
+                Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Cint,
+                Ptr{Cdouble}, Cuint, Cint, Ptr{Cint}, Ptr{IfadvReport}),
+               ctx, stream_ptr(), dptr(f), dptr(fᶠ), dptr(α), dptr(n̂), dptr(u), dptr(u⁰), Δt, dptr(c̄),
+               dptr(ρu), dptr(r), dptr(Φ), dptr(ρuf), dptr(uStar), dptr(uOld), dptr(dilaU), dptr(dρ), λρ, limiter_enum(λ),
+               normal_enum(normalScheme), A, perdir_mask(perdir), exitBC ? 1 : 0, dirv, want ? rep : C_NULL)
+    report(check(ctx, rc), rep[])
+    nothing
+end
+
+# ---- secondary seams -------------------------------------------------------------------------------------------------------------
+function u2ρu!(ρu::CuArray{T}, u, f::CuArray{T}, λρ) where {T<:Union{Float32,Float64}}   # src/VOFutil.jl:208
+    ctx = context(f)
+    check(ctx, ccall((:ifadv_u2rhou, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble),
+                     ctx, stream_ptr(), dptr(ρu), dptr(u), dptr(f), λρ)); nothing
+end
+function ρu2u!(u::CuArray{T}, ρu, f::CuArray{T}, λρ) where {T<:Union{Float32,Float64}}   # src/VOFutil.jl:198
+    ctx = context(f)
+    check(ctx, ccall((:ifadv_rhou2u, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble),
+                     ctx, stream_ptr(), dptr(u), dptr(ρu), dptr(f), λρ)); nothing
+end
+function MPCFL(a::Flow{D,T}, c::cVOF; Δt_max=one(T), safetyMargin=T(0.8)) where {D,T<:Union{Float32,Float64}}   # src/flow.jl:262
+    a.u isa CuArray || return invoke(MPCFL, Tuple{Flow,cVOF}, a, c; Δt_max, safetyMargin)
+    ctx = context(c.f)
+    g2 = isnothing(a.g) ? 0.0 : sqrt(sum(abs2, (a.g(i, zeros(T, D), sum(a.Δt)) for i in 1:D)))
+    out = Ref{Cdouble}(0)
+    check(ctx, ccall((:ifadv_mpcfl, LIB), Cint,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Ref{Cdouble}),
+                     ctx, stream_ptr(), dptr(a.u), a.ν, isnothing(c.μ) ? 0.0 : c.μ, c.λμ, c.λρ, isnothing(c.η) ? 0.0 : c.η, g2,
+                     Δt_max, safetyMargin, out))
+    T(out[])
+end
+
+end # module
