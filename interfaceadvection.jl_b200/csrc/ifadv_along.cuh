@@ -1,0 +1,385 @@
+// ifadv_along.cuh -- fused directional sweep along y or z (J = 1, 2) for 3-D grids: REGISTER MARCHING.
+//
+// A CTA owns a tile of 32 (x) x TC (cross direction c) columns and marches along the sweep direction a = J through a
+// chunk of planes; thread (tx, tc) owns ONE column.  Everything the stencil reaches ALONG the sweep -- the 4-point u★
+// line of each component, the VOF / mass / momentum flux through the lower face, the previous dilation, the face
+// velocities -- rolls through REGISTERS, so each flux is evaluated exactly once and never leaves the thread.  Shared
+// memory only carries what a thread needs from its x-1 / c-1 neighbours (mass flux, dilation, f) and the
+// cp.async-staged input planes:
+//     f        8-slot ring, halo -2..+1 in x and c (the 3^3 PLIC box of a halo column), loaded 3 planes ahead
+//     u_a,u⁰_a 4-slot rings (faces), ρu 4-slot ring x 3 components, uOld 2-slot ring x 3 components (no halo)
+// Per plane: ONE wait + barrier (S1), issue the next plane's copies, u★(k+2), VOF flux / mass flux at face k+1,
+// dilation(k), barrier (S2), [lane-dense PLIC of marked interface faces], SynDRoM fluxes at face k+1, update of cell k.
+// A chunk starts 4 planes early (warm-up) to fill the register pipeline.
+// Reference lines as in ifadv_march.cuh / ifadv_sweep.cuh (same boundary rules, same expression order).
+#pragma once
+#include "ifadv_march.cuh"
+
+namespace ifadv {
+
+template <int TC> struct ATile {
+  static constexpr int WX = 35, WC = TC + 3, PLH = WX * WC, NC = 32 * TC, NH = PLH - NC;
+  static constexpr int RF = 8, RU = 4, RR = 4, RO = 2;
+  // halo planes: F, U, U0, M x2, FX (+ Dil x2) ; core planes (CMOM): ρu, uOld ; + interface list + counter
+  template <class T> static constexpr size_t smem_bytes(bool mom) {
+    return sizeof(T) * ((size_t)PLH * (RF + 2 * RU + 3 + (mom ? 2 : 0)) + (mom ? (size_t)NC * 3 * (RR + RO) : 0)) + sizeof(int) * (PLH + 4);
+  }
+};
+
+// 3^3 box accessor on the 8-slot f ring of the along kernel
+template <class T, int J, int PLH, int WX> struct ABox {
+  const T* sF;
+  int e, pl;
+  IFADV_DI T operator()(int dx, int dy, int dz) const {
+    const int da = (J == 1) ? dy : dz, dc = (J == 1) ? dz : dy;
+    return sF[((pl + da) & 7) * PLH + e + dx + dc * WX];
+  }
+};
+
+template <class T> IFADV_DI void cp_async_s(unsigned saddr, const T* gsrc) {
+  if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(saddr), "l"(gsrc));
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(gsrc));
+}
+// branch-free index maps for plane indices that stay within one period of the box (chunks do)
+IFADV_DI int wrap1(int v, int n) { const int m = n - 2; v += (v < 2) ? m : 0; v -= (v > n - 1) ? m : 0; return v; }
+IFADV_DI int map1(int v, int n, bool per) { return per ? wrap1(v, n) : min(max(v, 2), n - 1); }
+IFADV_DI int own1(int v, int n, bool per) { return per ? wrap1(v, n) : min(max(v, 1), n); }
+
+template <class T, int J, int TC, bool MOM, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, const int chunk) {
+  using TL = ATile<TC>;
+  static_assert(NT == TL::NC, "one thread per column");
+  static_assert(J == 1 || J == 2, "sweeps along x use the in-plane kernel");
+  constexpr int DCC = (J == 1) ? 2 : 1;  // global dimension of the cross direction c
+  constexpr int WX = TL::WX, PLH = TL::PLH, NC = TL::NC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sm = reinterpret_cast<T*>(smem_raw);
+  T* sF = sm;
+  T* sU = sF + TL::RF * PLH;
+  T* sU0 = sU + TL::RU * PLH;
+  T* sM = sU0 + TL::RU * PLH;                 // 2 slots (face & 1): mass flux
+  T* sFX = sM + 2 * PLH;                      // fᶠ of reconstructed interface faces (handed back to the owning thread)
+  T* sDil = sFX + PLH;                        // 2 slots (plane & 1)           [CMOM]
+  T* sR = sDil + (MOM ? 2 * PLH : 0);         // [(plane&3)*3 + role][NC]     [CMOM]
+  T* sO = sR + (MOM ? TL::RR * 3 * NC : 0);   // [(plane&1)*3 + role][NC]     [CMOM]
+  int* sList = reinterpret_cast<int*>(sO + (MOM ? TL::RO * 3 * NC : 0));
+  int* sCnt = sList + PLH;
+
+  const Geo& g = P.g;
+  const int tid = threadIdx.x, tx = tid & 31, tc = tid >> 5;
+  const int nA = g.n[J], nX = g.n[0], nCc = g.n[DCC];
+  const long long st3[3] = {1, g.s1, g.s2};
+  const long long sA = st3[J], sCc = st3[DCC];
+  const bool perA = (g.per >> J) & 1u, perX = g.per & 1u, perC = (g.per >> DCC) & 1u;
+  const long long S = g.S;
+  const long long cA = (long long)J * S, cC = (long long)DCC * S;  // component x has offset 0
+  const int ox = 2 + blockIdx.x * 32, oc = 2 + blockIdx.y * TC;
+  const int k0 = 2 + blockIdx.z * chunk, k1 = min(k0 + chunk, nA);
+  const T lr = P.lr, omlr = P.omlr, dt = P.dt;
+  const T AA = P.A[J], AXv = P.A[0], ACv = P.A[DCC];
+  if (tid == 0) *sCnt = 0;
+
+  // ---- per-thread constants: own column and (for the first NH threads) one halo entry ----------------------------------------
+  const int vx = ox + tx, vcc = oc + tc;
+  const int eo = (tx + 2) + WX * (tc + 2);
+  const int go = (mapc(vx, nX, perX) - 1) + (int)((mapc(vcc, nCc, perC) - 1) * sCc);
+  const bool valid = vx <= nX - 1 && vcc <= nCc - 1;
+  const bool dirX = !perX && (vx == 2 || vx == nX), dirC = !perC && (vcc == 2 || vcc == nCc);
+  int eh = 0, gh = 0;
+  const bool hasH = tid < TL::NH;
+  bool hU = false;
+  if (hasH) {
+    int lx, lc;
+    const int h = tid;
+    if (h < 2 * WX) { lc = -2 + h / WX; lx = -2 + h % WX; }
+    else if (h < 3 * WX) { lc = TC; lx = -2 + (h - 2 * WX); }
+    else { const int r = h - 3 * WX; lc = r / 3; lx = (r % 3 < 2) ? (r % 3) - 2 : 32; }
+    eh = (lx + 2) + WX * (lc + 2);
+    gh = (mapc(ox + lx, nX, perX) - 1) + (int)((mapc(oc + lc, nCc, perC) - 1) * sCc);
+    hU = lx >= -1 && lx <= 31 && lc >= -1 && lc <= TC - 1 && !(lx < 0 && lc < 0);  // faces feeding Ψ / dilation neighbours
+  }
+
+  // plane offsets along a: mapped (f, tangential components, c̄, uOld) and as stored (component a, face velocities).
+  // They are block-uniform and roll with the march, so only pm(k+4), po(k+4) are evaluated per plane.
+  auto pm = [&](int v) -> long long { return (long long)(map1(v, nA, perA) - 1) * sA; };
+  auto po = [&](int v) -> long long { return (long long)(own1(v, nA, perA) - 1) * sA; };
+  auto dirAf = [&](int v) -> bool { return !perA && (v == 1 || v == 2 || v == nA); };
+  constexpr unsigned SZ = sizeof(T);
+  const unsigned sb = (unsigned)__cvta_generic_to_shared(sm);
+  const unsigned aF = sb + eo * SZ, aFh = sb + eh * SZ;                                  // f ring: + (v&7)*PLH*SZ
+  const unsigned aU = sb + (TL::RF * PLH + eo) * SZ, aUh = sb + (TL::RF * PLH + eh) * SZ;  // u ring: + (v&3)*PLH*SZ ; u⁰: + RU*PLH*SZ
+  const unsigned aR = sb + (unsigned)((sR - sm) + tid) * SZ;                                // ρu ring: + ((v&3)*3 + r)*NC*SZ
+  const unsigned aO = sb + (unsigned)((sO - sm) + tid) * SZ;                                // uOld ring: + ((v&1)*3 + r)*NC*SZ
+  const T* gf = P.f_in + go;
+  const T* gfh = P.f_in + gh;
+
+  auto issue_f = [&](int v, long long pmv) {
+    const unsigned so = (unsigned)(v & 7) * (PLH * SZ);
+    cp_async_s(aF + so, gf + pmv);
+    if (hasH) cp_async_s(aFh + so, gfh + pmv);
+  };
+  auto issue_u = [&](int v, long long pov) {
+    const unsigned so = (unsigned)(v & 3) * (PLH * SZ);
+    const long long o = pov + go;
+    cp_async_s(aU + so, P.uj + o);
+    cp_async_s(aU + so + TL::RU * PLH * SZ, P.u0j + o);
+    if (MOM && hU) {
+      const long long oh = pov + gh;
+      cp_async_s(aUh + so, P.uj + oh);
+      cp_async_s(aUh + so + TL::RU * PLH * SZ, P.u0j + oh);
+    }
+  };
+  auto issue_ru = [&](int v, long long pmv, long long pov) {
+    const unsigned d = aR + (unsigned)((v & 3) * 3) * (NC * SZ);
+    const T* r0 = P.rhou_in + go;
+    cp_async_s(d, r0 + cA + pov);
+    cp_async_s(d + NC * SZ, r0 + pmv);
+    cp_async_s(d + 2 * NC * SZ, r0 + cC + pmv);
+  };
+  auto issue_uold = [&](int v, long long pmv) {
+    const unsigned d = aO + (unsigned)((v & 1) * 3) * (NC * SZ);
+    const T* o0 = P.uOld + go + pmv;
+    cp_async_s(d, o0 + cA);
+    cp_async_s(d + NC * SZ, o0);
+    cp_async_s(d + 2 * NC * SZ, o0 + cC);
+  };
+  int cbo_n = 0, cbh_n = 0;  // c̄ of the next plane (own column, halo entry), read one plane ahead
+  auto load_cbar = [&](long long pmv) {
+    if (!P.first) {
+      cbo_n = (int)P.cbar[pmv + go];
+      if (MOM && hU) cbh_n = (int)P.cbar[pmv + gh];
+    }
+  };
+
+  // ---- rolling register state -------------------------------------------------------------------------------------------------------
+  T usA[4], usX[4], usC[4];  // u★ at planes k-1, k, k+1, k+2
+#pragma unroll
+  for (int i = 0; i < 4; ++i) usA[i] = usX[i] = usC[i] = T(0);
+  T FloA = T(0), FloX = T(0), FloC = T(0), FFlo = T(0), Mlo = T(0), dilm1 = T(0);
+  T rmax = -INFINITY, rmin = INFINITY;
+  unsigned int amax = 0, amin = 0;
+  int rnan = 0;
+
+  // ---- prologue: planes needed by the first warm-up step ks = k0-4 ----------------------------------------------------------------------
+  const int ks = k0 - 4;
+  issue_f(ks - 1, pm(ks - 1)); issue_f(ks, pm(ks)); issue_f(ks + 1, pm(ks + 1)); issue_f(ks + 2, pm(ks + 2));
+  issue_u(ks, po(ks)); issue_u(ks + 1, po(ks + 1));
+  if (MOM) {
+    issue_ru(ks, pm(ks), po(ks)); issue_ru(ks + 1, pm(ks + 1), po(ks + 1)); issue_ru(ks + 2, pm(ks + 2), po(ks + 2));
+    issue_uold(ks, pm(ks));
+  }
+  cp_async_commit();
+  load_cbar(pm(ks));
+  cp_async_wait_all();
+  __syncthreads();
+  long long pmA = pm(ks + 1), pmB = pm(ks + 2), pmC = pm(ks + 3), poB = po(ks + 2), poC = po(ks + 3);  // pm(k+1..k+3), po(k+2..k+3)
+  T uk = sU[(ks & 3) * PLH + eo], u0k = sU0[(ks & 3) * PLH + eo];  // face velocities at face k (own column)
+
+#pragma unroll 1
+  for (int k = ks; k < k1; ++k) {
+    const int p = k + 1, q = k + 2;
+    if (k > ks) {
+      cp_async_wait_all();
+      __syncthreads();  // S1: everything issued during step k-1 has landed; all reads of step k-1 are done
+    }
+    const int cbo = cbo_n, cbh = cbh_n;
+    // A. next plane's copies (HBM latency hides behind this plane's arithmetic)
+    issue_f(k + 3, pmC);
+    issue_u(k + 2, poB);
+    if (MOM) { issue_ru(k + 3, pmC, poC); issue_uold(k + 1, pmA); }
+    cp_async_commit();
+    load_cbar(pmA);
+    pmA = pmB; pmB = pmC; pmC = pm(k + 4); poB = poC; poC = po(k + 4);
+
+    const T* Fk = sF + (k & 7) * PLH;
+    const T* Fp = sF + (p & 7) * PLH;
+    // B. u★ of plane q = k+2 (flow.jl:197): BC!(ρu/ρ(f̄))
+    if (MOM) {
+      const T* Fq = sF + (q & 7) * PLH;
+      const T* R = sR + ((q & 3) * 3) * NC + tid;
+      const T fq = Fq[eo];
+      const T ra = t_div(R[0], lin_interp((fq + Fp[eo]) / T(2), lr, omlr));
+      const T rx = t_div(R[NC], lin_interp((fq + Fq[eo - 1]) / T(2), lr, omlr));
+      const T rc = t_div(R[2 * NC], lin_interp((fq + Fq[eo - WX]) / T(2), lr, omlr));
+      usA[3] = dirAf(q) ? AA : ra;  // Dirichlet planes of BC!
+      usX[3] = dirX ? AXv : rx;
+      usC[3] = dirC ? ACv : rc;
+    }
+    // C. VOF flux + mass flux through face p = k+1 (advection.jl:108-137): own column, then the halo entry
+    const bool needp = p <= nA && (perA || p >= 2);
+    const T* Up = sU + (p & 3) * PLH;
+    const T* U0p = sU0 + (p & 3) * PLH;
+    T* Mp = sM + (p & 1) * PLH;
+    const T up1 = Up[eo], u0p1 = U0p[eo];
+    T FFhi = T(0), Mhi = T(0);
+    bool marked = false;
+    if (needp) {
+      const T dl = P.hdt * (up1 + u0p1);  // δt/2*(u+u⁰)
+      if (dl != T(0)) {
+        const bool up = dl > T(0);
+        const T fc = up ? Fk[eo] : Fp[eo];  // upwind cell
+        const int cu = up ? k : p;
+        const bool ghost = !perA && (cu < 2 || cu > nA - 1);
+        if (ghost || fullorempty(fc)) {
+          FFhi = fc * dl;
+          Mhi = dl * lr + omlr * FFhi;
+          if (MOM) Mhi = Mhi * P.idt;
+        } else { sList[atomicAdd(sCnt, 1)] = eo; marked = true; }
+      }
+    }
+    Mp[eo] = Mhi;
+    if (MOM && hU) {
+      T m = T(0);
+      if (needp) {
+        const T dl = P.hdt * (Up[eh] + U0p[eh]);
+        if (dl != T(0)) {
+          const bool up = dl > T(0);
+          const T fc = up ? Fk[eh] : Fp[eh];
+          const int cu = up ? k : p;
+          const bool ghost = !perA && (cu < 2 || cu > nA - 1);
+          if (ghost || fullorempty(fc)) {
+            m = dl * lr + omlr * (fc * dl);
+            m = m * P.idt;
+          } else sList[atomicAdd(sCnt, 1)] = eh;
+        }
+      }
+      Mp[eh] = m;
+    }
+    // D. dilation of plane k (flow.jl:216): own column, then the halo entry
+    const T div = (up1 - uk) + (u0p1 - u0k);  // ∂(d,I,u)+∂(d,I,u⁰)
+    const T fK = Fk[eo];
+    const int cb = P.first ? ((fK < T(0.5)) ? 0 : 1) : cbo;  // flow.jl:172 (c̄ from the incoming f)
+    T dilk = T(0);
+    if (MOM) {
+      dilk = (lin_interp(T(cb), lr, omlr) * div) / T(2);
+      sDil[(k & 1) * PLH + eo] = dilk;
+      if (hU) {
+        const T* Uk = sU + (k & 3) * PLH;
+        const T* U0k = sU0 + (k & 3) * PLH;
+        const T dh = (Up[eh] - Uk[eh]) + (U0p[eh] - U0k[eh]);
+        const int ch = P.first ? ((Fk[eh] < T(0.5)) ? 0 : 1) : cbh;
+        sDil[(k & 1) * PLH + eh] = (lin_interp(T(ch), lr, omlr) * dh) / T(2);
+      }
+    }
+    __syncthreads();  // S2: mass flux of face p, dilation of plane k and the interface list are complete
+    {
+      const int cnt = *sCnt;  // block-uniform
+      if (cnt > 0) {
+        // lane-dense PLIC reconstruction of the marked faces (general branch of getVOFFlux!, advection.jl:131-134)
+        for (int i = tid; i < cnt; i += NT) {
+          const int e = sList[i];
+          const T dl = P.hdt * (Up[e] + U0p[e]);
+          const int pl = (dl > T(0)) ? k : p;
+          ABox<T, J, PLH, WX> B{sF, e, pl};
+          const T ff = plic_face_flux<T, 3>(P.scheme, B, sF[(pl & 7) * PLH + e], J, dl);
+          T m = dl * lr + omlr * ff;
+          if (MOM) m = m * P.idt;
+          sFX[e] = ff;
+          Mp[e] = m;
+        }
+        __syncthreads();
+        if (marked) { FFhi = sFX[eo]; Mhi = Mp[eo]; }
+      }
+    }
+    // G. SynDRoM momentum flux through face p of the three momentum cells of this column (flow.jl:20-57,223)
+    T FhiA = T(0), FhiX = T(0), FhiC = T(0);
+    if (MOM) {
+      const bool dp = dirAf(p), dpm = dirAf(p - 1);
+      const T Mc = dp ? AA : Mhi;  // velocity BC! on ρuf (flow.jl:207)
+      const bool Lvar = !perA && p == 2, Rvar = !perA && p == nA;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        T Mo;
+        if (r == 0) Mo = dpm ? AA : Mlo;
+        else if (r == 1) Mo = dp ? AA : Mp[eo - 1];
+        else Mo = dp ? AA : Mp[eo - WX];
+        const T Psi = (Mc + Mo) / T(2);
+        const T* us = (r == 0) ? usA : ((r == 1) ? usX : usC);
+        const bool pos = Psi > T(0);
+        T uu, cc, dd;
+        if (Lvar) {  // ϕuL
+          if (pos) { uu = T(2) * us[1] - us[2]; cc = us[1]; dd = us[2]; }
+          else { uu = us[3]; cc = us[2]; dd = us[1]; }
+        } else if (Rvar) {  // ϕuR
+          if (Psi < T(0)) { uu = T(2) * us[2] - us[1]; cc = us[2]; dd = us[1]; }
+          else { uu = us[0]; cc = us[1]; dd = us[2]; }
+        } else {  // ϕu
+          uu = pos ? us[0] : us[3];
+          cc = pos ? us[1] : us[2];
+          dd = pos ? us[2] : us[1];
+        }
+        // donor momentum cell: plane k (Ψ>0) or p; its face-centred old f (dρ after f2face!+BCv!, flow.jl:205)
+        const T* Fd = pos ? Fk : Fp;
+        T fo;
+        if (r == 0) {
+          const T* Fdm = pos ? sF + ((k - 1) & 7) * PLH : Fk;
+          fo = (Fd[eo] + Fdm[eo]) / T(2);
+          if (Lvar && pos) fo = (sF[(q & 7) * PLH + eo] + Fp[eo]) / T(2);  // donor index 1: BCv! copies plane 3 = (f(3)+f(2))/2
+          if (Rvar && !pos) fo = __ldg(P.drho + cA + (long long)(nA - 1) * sA + go);  // donor index nA: never written by f2face!
+        } else if (r == 1) fo = (Fd[eo] + Fd[eo - 1]) / T(2);
+        else fo = (Fd[eo] + Fd[eo - WX]) / T(2);
+        const T fl = syndrom_flux(P.lim, Psi, uu, cc, dd, lin_interp(fo, lr, omlr), dt);
+        if (r == 0) FhiA = fl; else if (r == 1) FhiX = fl; else FhiC = fl;
+      }
+    }
+    // H. update of cell k
+    if (k >= k0 && valid) {
+      const long long lk = (long long)(k - 1) * sA + go;
+      if (P.first) P.cbar[lk] = (int8_t)cb;
+      T fn = fK + ((FFlo - FFhi) + ((T(cb) * div) * dt) / T(2));  // advection.jl:83
+      if (fn != fn) rnan = 1;
+      if (fn > rmax) { rmax = fn; amax = (unsigned int)lk; }
+      if (fn < rmin) { rmin = fn; amin = (unsigned int)lk; }
+      fn = (fn < P.tol) ? T(0) : ((fn > P.onemtol) ? T(1) : fn);  // cleanWisp!
+      P.f_out[lk] = fn;
+      if (!MOM && P.rhouf_j != nullptr) {
+        P.rhouf_j[lk] = Mlo;
+        if (k == nA - 1) P.rhouf_j[lk + sA] = Mhi;  // inside_uWB includes the upper boundary face
+      }
+      if (MOM) {
+        const T* R = sR + ((k & 3) * 3) * NC + tid;
+        const T* O = sO + ((k & 1) * 3) * NC + tid;
+        const T* Dk = sDil + (k & 1) * PLH;
+        const T dNa = (!perA && k == 2) ? dilk : dilm1;  // BCf! (Neumann) on ρ̄∂ⱼuⱼ along the sweep direction
+        // r = Φ[I] - Φ[I+δj] + uOld*ϕ(i,I,ρ̄∂ⱼuⱼ);  ρu += δt*r          flow.jl:223-231
+        const T rA = (FloA - FhiA) + O[0] * ((dilk + dNa) / T(2));
+        const T rX = (FloX - FhiX) + O[NC] * ((dilk + Dk[eo - 1]) / T(2));
+        const T rC = (FloC - FhiC) + O[2 * NC] * ((dilk + Dk[eo - WX]) / T(2));
+        P.rhou_out[cA + lk] = R[0] + dt * rA;
+        P.rhou_out[lk] = R[NC] + dt * rX;
+        P.rhou_out[cC + lk] = R[2 * NC] + dt * rC;
+      }
+    }
+    // I. roll the register pipeline
+    FloA = FhiA; FloX = FhiX; FloC = FhiC; FFlo = FFhi; Mlo = Mhi; dilm1 = dilk; uk = up1; u0k = u0p1;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { usA[i] = usA[i + 1]; usX[i] = usX[i + 1]; usC[i] = usC[i + 1]; }
+    if (tid == 0) *sCnt = 0;
+  }
+
+  // ---- fill-error reduction ------------------------------------------------------------------------------------------------------------
+  if (P.red != nullptr) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const T omax = __shfl_xor_sync(0xffffffffu, rmax, off), omin = __shfl_xor_sync(0xffffffffu, rmin, off);
+      const unsigned int oamax = __shfl_xor_sync(0xffffffffu, amax, off), oamin = __shfl_xor_sync(0xffffffffu, amin, off);
+      const int onan = __shfl_xor_sync(0xffffffffu, rnan, off);
+      if (omax > rmax) { rmax = omax; amax = oamax; }
+      if (omin < rmin) { rmin = omin; amin = oamin; }
+      rnan |= onan;
+    }
+    if ((tid & 31) == 0) {
+      if (rmax > -INFINITY) {
+        atomicMax(P.red + 0, ord_key((double)rmax));
+        atomicMax(P.red + 2, ((unsigned long long)ord_key32((float)rmax) << 32) | amax);
+      }
+      if (rmin < INFINITY) {
+        atomicMin(P.red + 1, ord_key((double)rmin));
+        atomicMin(P.red + 3, ((unsigned long long)ord_key32((float)rmin) << 32) | amin);
+      }
+      if (rnan) atomicAdd(P.red + 4, 1ull);
+    }
+  }
+}
+
+}  // namespace ifadv

@@ -375,7 +375,8 @@ int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int dev
   c->prof_on = 0; c->prof_n = 0; c->prof_ev = nullptr;
   {
     const char* e = getenv("IFADV_KERNEL");
-    c->use_march = !(e && std::string(e) == "tile");
+    // default: register-marching (y,z sweeps) + plane-marching (x sweep); "march": plane-marching for all; "tile": v1
+    c->use_march = (e && std::string(e) == "tile") ? 0 : ((e && std::string(e) == "march") ? 2 : 1);
   }
   if (cudaMalloc(&c->red_dev, sizeof(unsigned long long) * 24) != cudaSuccess ||
       cudaMallocHost(&c->red_host, sizeof(unsigned long long) * 24) != cudaSuccess ||

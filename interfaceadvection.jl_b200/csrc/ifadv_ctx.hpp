@@ -27,7 +27,7 @@ struct ifadv_ctx {
   void* pin_ru;
   cudaStream_t own_stream;
   // optional per-launch CUDA-event timing of the fused sweep (ifadv_profile)
-  int use_march;  // 1: v2 plane-marching kernel for 3-D grids (default); 0: v1 tile kernel (IFADV_KERNEL=tile)
+  int use_march;  // 1: register-marching (y,z) + plane-marching (x) kernels (default); 2: plane-marching only; 0: v1 tile kernel
   int prof_on, prof_n;
   cudaEvent_t* prof_ev;  // 2 * IFADV_PROF_MAX events
 };

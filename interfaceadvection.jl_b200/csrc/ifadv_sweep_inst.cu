@@ -4,6 +4,7 @@
 
 #include "ifadv_ctx.hpp"
 #include "ifadv_march.cuh"
+#include "ifadv_along.cuh"
 
 namespace ifadv {
 
@@ -83,8 +84,42 @@ static int launch_march_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   return 0;
 }
 
+// v3: register-marching kernel for sweeps along y / z (3-D only)
+template <class T, int J, int TC, bool MOM, int MINB>
+static int launch_along_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  constexpr int NT = 32 * TC;
+  using TL = ATile<TC>;
+  SweepP<T> P;
+  fill_params<T>(c, q, J, P);
+  const size_t smem = TL::template smem_bytes<T>(MOM);
+  auto kern = along_kernel<T, J, TC, MOM, NT, MINB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  constexpr int DCC = (J == 1) ? 2 : 1;
+  const int nx = c->g.n[0] - 2, ncc = c->g.n[DCC] - 2, na = c->g.n[J] - 2;
+  const long long tiles = (long long)((nx + 31) / 32) * ((ncc + TC - 1) / TC);
+  int chunk = 128;  // 4 warm-up planes per chunk
+  while (chunk > 16 && tiles * ((na + chunk - 1) / chunk) < 148 * 8) chunk >>= 1;
+  dim3 grid((unsigned)((nx + 31) / 32), (unsigned)((ncc + TC - 1) / TC), (unsigned)((na + chunk - 1) / chunk));
+  const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
+  if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
+  kern<<<grid, NT, smem, st>>>(P, chunk);
+  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_n++; }
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
 template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   if constexpr (D == 3) {
+    if (c->use_march == 1 && q.j != 0) {
+      constexpr int MB = (sizeof(T) == 4) ? 3 : 2;
+      if (q.j == 1) return launch_along_t<T, 1, 8, MOM, MB>(c, st, q);
+      return launch_along_t<T, 2, 8, MOM, MB>(c, st, q);
+    }
     if (c->use_march) {
       // tile shapes sized so that 25 shared planes leave 3 (f32) / 2-3 (f64) CTAs per SM
       constexpr int TO = (sizeof(T) == 4) ? 16 : 8;
