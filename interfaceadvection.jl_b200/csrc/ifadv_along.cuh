@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
   const long long sA = st3[J], sCc = st3[DCC];
   const bool perA = (g.per >> J) & 1u, perX = g.per & 1u, perC = (g.per >> DCC) & 1u;
   const long long S = g.S;
-  const long long cA = (long long)J * S, cC = (long long)DCC * S;  // component x has offset 0
+  const long long cA = P.coff[J], cC = P.coff[DCC];  // component offsets (host-computed; component x has offset 0)
   const int ox = 2 + blockIdx.x * 32, oc = 2 + blockIdx.y * TC;
   const int k0 = 2 + blockIdx.z * chunk, k1 = min(k0 + chunk, nA);
   const T lr = P.lr, omlr = P.omlr, dt = P.dt;
@@ -89,14 +89,20 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
   const bool hasH = tid < TL::NH;
   bool hU = false;
   if (hasH) {
+    // the 8*TC/8+32 entries that also carry face velocities / mass flux / dilation come first (warp 0 + 8 lanes), so only
+    // two warps execute the halo flux / dilation code; the remaining entries only feed the 3^3 PLIC box
     int lx, lc;
     const int h = tid;
-    if (h < 2 * WX) { lc = -2 + h / WX; lx = -2 + h % WX; }
-    else if (h < 3 * WX) { lc = TC; lx = -2 + (h - 2 * WX); }
-    else { const int r = h - 3 * WX; lc = r / 3; lx = (r % 3 < 2) ? (r % 3) - 2 : 32; }
+    if (h < 32) { lx = h; lc = -1; }
+    else if (h < 32 + TC) { lx = -1; lc = h - 32; }
+    else if (h < 32 + TC + WX) { lc = -2; lx = h - (32 + TC) - 2; }
+    else if (h < 35 + TC + WX) { lc = -1; const int r = h - (32 + TC + WX); lx = (r < 2) ? r - 2 : 32; }
+    else if (h < 35 + TC + 2 * WX) { lc = TC; lx = h - (35 + TC + WX) - 2; }
+    else if (h < 35 + 2 * TC + 2 * WX) { lx = -2; lc = h - (35 + TC + 2 * WX); }
+    else { lx = 32; lc = h - (35 + 2 * TC + 2 * WX); }
     eh = (lx + 2) + WX * (lc + 2);
     gh = (mapc(ox + lx, nX, perX) - 1) + (int)((mapc(oc + lc, nCc, perC) - 1) * sCc);
-    hU = lx >= -1 && lx <= 31 && lc >= -1 && lc <= TC - 1 && !(lx < 0 && lc < 0);  // faces feeding Ψ / dilation neighbours
+    hU = h < 32 + TC;
   }
 
   // plane offsets along a: mapped (f, tangential components, c̄, uOld) and as stored (component a, face velocities).
@@ -183,13 +189,19 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
       __syncthreads();  // S1: everything issued during step k-1 has landed; all reads of step k-1 are done
     }
     const int cbo = cbo_n, cbh = cbh_n;
+    const bool dq = dirAf(q), dp = dirAf(p), dpm = dirAf(k);
     // A. next plane's copies (HBM latency hides behind this plane's arithmetic)
     issue_f(k + 3, pmC);
     issue_u(k + 2, poB);
     if (MOM) { issue_ru(k + 3, pmC, poC); issue_uold(k + 1, pmA); }
     cp_async_commit();
     load_cbar(pmA);
-    pmA = pmB; pmB = pmC; pmC = pm(k + 4); poB = poC; poC = po(k + 4);
+    pmA = pmB; pmB = pmC; poB = poC;
+    {  // pm(k+4), po(k+4): one stride further unless the plane is within the boundary band (block-uniform)
+      const int v = k + 4;
+      if (v >= 4 && v <= nA - 2) { pmC += sA; poC += sA; }
+      else { pmC = pm(v); poC = po(v); }
+    }
 
     const T* Fk = sF + (k & 7) * PLH;
     const T* Fp = sF + (p & 7) * PLH;
@@ -201,7 +213,7 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
       const T ra = t_div(R[0], lin_interp((fq + Fp[eo]) / T(2), lr, omlr));
       const T rx = t_div(R[NC], lin_interp((fq + Fq[eo - 1]) / T(2), lr, omlr));
       const T rc = t_div(R[2 * NC], lin_interp((fq + Fq[eo - WX]) / T(2), lr, omlr));
-      usA[3] = dirAf(q) ? AA : ra;  // Dirichlet planes of BC!
+      usA[3] = dq ? AA : ra;  // Dirichlet planes of BC!
       usX[3] = dirX ? AXv : rx;
       usC[3] = dirC ? ACv : rc;
     }
@@ -284,7 +296,6 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
     // G. SynDRoM momentum flux through face p of the three momentum cells of this column (flow.jl:20-57,223)
     T FhiA = T(0), FhiX = T(0), FhiC = T(0);
     if (MOM) {
-      const bool dp = dirAf(p), dpm = dirAf(p - 1);
       const T Mc = dp ? AA : Mhi;  // velocity BC! on ρuf (flow.jl:207)
       const bool Lvar = !perA && p == 2, Rvar = !perA && p == nA;
 #pragma unroll

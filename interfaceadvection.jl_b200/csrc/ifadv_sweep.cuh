@@ -47,6 +47,7 @@ template <class T> struct SweepP {
   T* rhouf_j;  // optional (pure VOF): ρuf[:, j]
   T dt, hdt, idt, lr, omlr, tol, onemtol;
   T A[3];
+  long long coff[3];  // component offsets d*S
   Geo g;
   int scheme, lim, first;
   unsigned long long* red;  // [0] max key, [1] min key, [2] argmax pack, [3] argmin pack, [4] nan count

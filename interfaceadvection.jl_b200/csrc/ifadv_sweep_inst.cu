@@ -50,6 +50,7 @@ template <class T> static void fill_params(ifadv_ctx* c, const SweepCfg<T>& q, i
   P.tol = T(10) * std::numeric_limits<T>::epsilon(); P.onemtol = T(1) - P.tol;
   for (int i = 0; i < 3; ++i) P.A[i] = (T)q.A[i];
   P.g = c->g; P.scheme = q.scheme; P.lim = q.lim; P.first = q.first; P.red = q.red;
+  for (int i = 0; i < 3; ++i) P.coff[i] = (long long)i * c->g.S;
 }
 
 // v2: plane-marching kernel (3-D only)
