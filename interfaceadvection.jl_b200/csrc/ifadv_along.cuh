@@ -17,8 +17,8 @@
 
 namespace ifadv {
 
-template <int TC> struct ATile {
-  static constexpr int WX = 35, WC = TC + 3, PLH = WX * WC, NC = 32 * TC, NH = PLH - NC;
+template <int TCT> struct ATile {  // TCT = tile extent along c (rows) = 8 * columns-per-thread
+  static constexpr int WX = 35, WC = TCT + 3, PLH = WX * WC, NC = 32 * TCT, NH = PLH - NC, NHU = 32 + TCT;
   static constexpr int RF = 8, RU = 4, RR = 4, RO = 2;
   // halo planes: F, U, U0, M x2, FX (+ Dil x2) ; core planes (CMOM): ρu, uOld ; + interface list + counter
   template <class T> static constexpr size_t smem_bytes(bool mom) {
@@ -45,11 +45,13 @@ IFADV_DI int wrap1(int v, int n) { const int m = n - 2; v += (v < 2) ? m : 0; v 
 IFADV_DI int map1(int v, int n, bool per) { return per ? wrap1(v, n) : min(max(v, 2), n - 1); }
 IFADV_DI int own1(int v, int n, bool per) { return per ? wrap1(v, n) : min(max(v, 1), n); }
 
-template <class T, int J, int TC, bool MOM, int NT, int MINB>
+template <class T, int J, int CPT, bool MOM, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, const int chunk) {
-  using TL = ATile<TC>;
-  static_assert(NT == TL::NC, "one thread per column");
+  constexpr int TR = NT / 32;      // rows of threads
+  constexpr int TCT = TR * CPT;    // tile rows: a thread owns CPT columns, rows tc, tc+TR, ...
+  using TL = ATile<TCT>;
   static_assert(J == 1 || J == 2, "sweeps along x use the in-plane kernel");
+  static_assert(TL::NH <= NT, "one halo entry per thread");
   constexpr int DCC = (J == 1) ? 2 : 1;  // global dimension of the cross direction c
   constexpr int WX = TL::WX, PLH = TL::PLH, NC = TL::NC;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -71,38 +73,43 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
   const long long st3[3] = {1, g.s1, g.s2};
   const long long sA = st3[J], sCc = st3[DCC];
   const bool perA = (g.per >> J) & 1u, perX = g.per & 1u, perC = (g.per >> DCC) & 1u;
-  const long long S = g.S;
   const long long cA = P.coff[J], cC = P.coff[DCC];  // component offsets (host-computed; component x has offset 0)
-  const int ox = 2 + blockIdx.x * 32, oc = 2 + blockIdx.y * TC;
+  const int ox = 2 + blockIdx.x * 32, oc = 2 + blockIdx.y * TCT;
   const int k0 = 2 + blockIdx.z * chunk, k1 = min(k0 + chunk, nA);
   const T lr = P.lr, omlr = P.omlr, dt = P.dt;
   const T AA = P.A[J], AXv = P.A[0], ACv = P.A[DCC];
   if (tid == 0) *sCnt = 0;
 
-  // ---- per-thread constants: own column and (for the first NH threads) one halo entry ----------------------------------------
-  const int vx = ox + tx, vcc = oc + tc;
-  const int eo = (tx + 2) + WX * (tc + 2);
-  const int go = (mapc(vx, nX, perX) - 1) + (int)((mapc(vcc, nCc, perC) - 1) * sCc);
-  const bool valid = vx <= nX - 1 && vcc <= nCc - 1;
-  const bool dirX = !perX && (vx == 2 || vx == nX), dirC = !perC && (vcc == 2 || vcc == nCc);
+  // ---- per-thread constants: own columns and (for the first NH threads) one halo entry ---------------------------------------
+  const int vx = ox + tx;
+  const bool dirX = !perX && (vx == 2 || vx == nX);
+  int eo[CPT], go[CPT];
+  bool valid[CPT], dirC[CPT];
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) {
+    const int lc = tc + j * TR, vcc = oc + lc;
+    eo[j] = (tx + 2) + WX * (lc + 2);
+    go[j] = (mapc(vx, nX, perX) - 1) + (int)((mapc(vcc, nCc, perC) - 1) * sCc);
+    valid[j] = vx <= nX - 1 && vcc <= nCc - 1;
+    dirC[j] = !perC && (vcc == 2 || vcc == nCc);
+  }
   int eh = 0, gh = 0;
   const bool hasH = tid < TL::NH;
-  bool hU = false;
+  const bool hU = tid < TL::NHU;
   if (hasH) {
-    // the 8*TC/8+32 entries that also carry face velocities / mass flux / dilation come first (warp 0 + 8 lanes), so only
-    // two warps execute the halo flux / dilation code; the remaining entries only feed the 3^3 PLIC box
+    // the 32+TCT entries that also carry face velocities / mass flux / dilation come first, so only the first warps
+    // execute the halo flux / dilation code; the remaining entries only feed the 3^3 PLIC box
     int lx, lc;
     const int h = tid;
     if (h < 32) { lx = h; lc = -1; }
-    else if (h < 32 + TC) { lx = -1; lc = h - 32; }
-    else if (h < 32 + TC + WX) { lc = -2; lx = h - (32 + TC) - 2; }
-    else if (h < 35 + TC + WX) { lc = -1; const int r = h - (32 + TC + WX); lx = (r < 2) ? r - 2 : 32; }
-    else if (h < 35 + TC + 2 * WX) { lc = TC; lx = h - (35 + TC + WX) - 2; }
-    else if (h < 35 + 2 * TC + 2 * WX) { lx = -2; lc = h - (35 + TC + 2 * WX); }
-    else { lx = 32; lc = h - (35 + 2 * TC + 2 * WX); }
+    else if (h < 32 + TCT) { lx = -1; lc = h - 32; }
+    else if (h < 32 + TCT + WX) { lc = -2; lx = h - (32 + TCT) - 2; }
+    else if (h < 35 + TCT + WX) { lc = -1; const int r = h - (32 + TCT + WX); lx = (r < 2) ? r - 2 : 32; }
+    else if (h < 35 + TCT + 2 * WX) { lc = TCT; lx = h - (35 + TCT + WX) - 2; }
+    else if (h < 35 + 2 * TCT + 2 * WX) { lx = -2; lc = h - (35 + TCT + 2 * WX); }
+    else { lx = 32; lc = h - (35 + 2 * TCT + 2 * WX); }
     eh = (lx + 2) + WX * (lc + 2);
     gh = (mapc(ox + lx, nX, perX) - 1) + (int)((mapc(oc + lc, nCc, perC) - 1) * sCc);
-    hU = h < 32 + TC;
   }
 
   // plane offsets along a: mapped (f, tangential components, c̄, uOld) and as stored (component a, face velocities).
@@ -112,56 +119,73 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
   auto dirAf = [&](int v) -> bool { return !perA && (v == 1 || v == 2 || v == nA); };
   constexpr unsigned SZ = sizeof(T);
   const unsigned sb = (unsigned)__cvta_generic_to_shared(sm);
-  const unsigned aF = sb + eo * SZ, aFh = sb + eh * SZ;                                  // f ring: + (v&7)*PLH*SZ
-  const unsigned aU = sb + (TL::RF * PLH + eo) * SZ, aUh = sb + (TL::RF * PLH + eh) * SZ;  // u ring: + (v&3)*PLH*SZ ; u⁰: + RU*PLH*SZ
-  const unsigned aR = sb + (unsigned)((sR - sm) + tid) * SZ;                                // ρu ring: + ((v&3)*3 + r)*NC*SZ
-  const unsigned aO = sb + (unsigned)((sO - sm) + tid) * SZ;                                // uOld ring: + ((v&1)*3 + r)*NC*SZ
-  const T* gf = P.f_in + go;
-  const T* gfh = P.f_in + gh;
+  const unsigned aFh = sb + eh * SZ, aUh = sb + (TL::RF * PLH + eh) * SZ;
+  const unsigned aR = sb + (unsigned)((sR - sm) + tid) * SZ;  // ρu ring: + ((v&3)*3 + r)*NC*SZ + j*NT*SZ
+  const unsigned aO = sb + (unsigned)((sO - sm) + tid) * SZ;  // uOld ring: + ((v&1)*3 + r)*NC*SZ + j*NT*SZ
 
   auto issue_f = [&](int v, long long pmv) {
-    const unsigned so = (unsigned)(v & 7) * (PLH * SZ);
-    cp_async_s(aF + so, gf + pmv);
-    if (hasH) cp_async_s(aFh + so, gfh + pmv);
+    const unsigned so = sb + (unsigned)(v & 7) * (PLH * SZ);
+    const T* fp = P.f_in + pmv;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) cp_async_s(so + eo[j] * SZ, fp + go[j]);
+    if (hasH) cp_async_s(aFh + (unsigned)(v & 7) * (PLH * SZ), fp + gh);
   };
   auto issue_u = [&](int v, long long pov) {
     const unsigned so = (unsigned)(v & 3) * (PLH * SZ);
-    const long long o = pov + go;
-    cp_async_s(aU + so, P.uj + o);
-    cp_async_s(aU + so + TL::RU * PLH * SZ, P.u0j + o);
+    const T* up = P.uj + pov;
+    const T* u0p = P.u0j + pov;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      cp_async_s(sb + so + (TL::RF * PLH + eo[j]) * SZ, up + go[j]);
+      cp_async_s(sb + so + ((TL::RF + TL::RU) * PLH + eo[j]) * SZ, u0p + go[j]);
+    }
     if (MOM && hU) {
-      const long long oh = pov + gh;
-      cp_async_s(aUh + so, P.uj + oh);
-      cp_async_s(aUh + so + TL::RU * PLH * SZ, P.u0j + oh);
+      cp_async_s(aUh + so, up + gh);
+      cp_async_s(aUh + so + TL::RU * PLH * SZ, u0p + gh);
     }
   };
   auto issue_ru = [&](int v, long long pmv, long long pov) {
     const unsigned d = aR + (unsigned)((v & 3) * 3) * (NC * SZ);
-    const T* r0 = P.rhou_in + go;
-    cp_async_s(d, r0 + cA + pov);
-    cp_async_s(d + NC * SZ, r0 + pmv);
-    cp_async_s(d + 2 * NC * SZ, r0 + cC + pmv);
+    const T* ra = P.rhou_in + cA + pov;
+    const T* rx = P.rhou_in + pmv;
+    const T* rc = P.rhou_in + cC + pmv;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      cp_async_s(d + j * NT * SZ, ra + go[j]);
+      cp_async_s(d + (NC + j * NT) * SZ, rx + go[j]);
+      cp_async_s(d + (2 * NC + j * NT) * SZ, rc + go[j]);
+    }
   };
   auto issue_uold = [&](int v, long long pmv) {
     const unsigned d = aO + (unsigned)((v & 1) * 3) * (NC * SZ);
-    const T* o0 = P.uOld + go + pmv;
-    cp_async_s(d, o0 + cA);
-    cp_async_s(d + NC * SZ, o0);
-    cp_async_s(d + 2 * NC * SZ, o0 + cC);
+    const T* o0 = P.uOld + pmv;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      cp_async_s(d + j * NT * SZ, o0 + cA + go[j]);
+      cp_async_s(d + (NC + j * NT) * SZ, o0 + go[j]);
+      cp_async_s(d + (2 * NC + j * NT) * SZ, o0 + cC + go[j]);
+    }
   };
-  int cbo_n = 0, cbh_n = 0;  // c̄ of the next plane (own column, halo entry), read one plane ahead
+  int cbo_n[CPT], cbh_n = 0;  // c̄ of the next plane (own columns, halo entry), read one plane ahead
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) cbo_n[j] = 0;
   auto load_cbar = [&](long long pmv) {
     if (!P.first) {
-      cbo_n = (int)P.cbar[pmv + go];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) cbo_n[j] = (int)P.cbar[pmv + go[j]];
       if (MOM && hU) cbh_n = (int)P.cbar[pmv + gh];
     }
   };
 
   // ---- rolling register state -------------------------------------------------------------------------------------------------------
-  T usA[4], usX[4], usC[4];  // u★ at planes k-1, k, k+1, k+2
+  T usA[CPT][4], usX[CPT][4], usC[CPT][4];  // u★ at planes k-1, k, k+1, k+2
+  T FloA[CPT], FloX[CPT], FloC[CPT], FFlo[CPT], Mlo[CPT], dilm1[CPT], uk[CPT], u0k[CPT];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) usA[i] = usX[i] = usC[i] = T(0);
-  T FloA = T(0), FloX = T(0), FloC = T(0), FFlo = T(0), Mlo = T(0), dilm1 = T(0);
+  for (int j = 0; j < CPT; ++j) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) usA[j][i] = usX[j][i] = usC[j][i] = T(0);
+    FloA[j] = FloX[j] = FloC[j] = FFlo[j] = Mlo[j] = dilm1[j] = T(0);
+  }
   T rmax = -INFINITY, rmin = INFINITY;
   unsigned int amax = 0, amin = 0;
   int rnan = 0;
@@ -179,7 +203,9 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
   cp_async_wait_all();
   __syncthreads();
   long long pmA = pm(ks + 1), pmB = pm(ks + 2), pmC = pm(ks + 3), poB = po(ks + 2), poC = po(ks + 3);  // pm(k+1..k+3), po(k+2..k+3)
-  T uk = sU[(ks & 3) * PLH + eo], u0k = sU0[(ks & 3) * PLH + eo];  // face velocities at face k (own column)
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) { uk[j] = sU[(ks & 3) * PLH + eo[j]]; u0k[j] = sU0[(ks & 3) * PLH + eo[j]]; }
+  long long lk0 = (long long)(ks - 1) * sA;  // (k-1)*sA, rolled with the march
 
 #pragma unroll 1
   for (int k = ks; k < k1; ++k) {
@@ -188,7 +214,10 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
       cp_async_wait_all();
       __syncthreads();  // S1: everything issued during step k-1 has landed; all reads of step k-1 are done
     }
-    const int cbo = cbo_n, cbh = cbh_n;
+    int cbo[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) cbo[j] = cbo_n[j];
+    const int cbh = cbh_n;
     const bool dq = dirAf(q), dp = dirAf(p), dpm = dirAf(k);
     // A. next plane's copies (HBM latency hides behind this plane's arithmetic)
     issue_f(k + 3, pmC);
@@ -205,41 +234,57 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
 
     const T* Fk = sF + (k & 7) * PLH;
     const T* Fp = sF + (p & 7) * PLH;
-    // B. u★ of plane q = k+2 (flow.jl:197): BC!(ρu/ρ(f̄))
-    if (MOM) {
-      const T* Fq = sF + (q & 7) * PLH;
-      const T* R = sR + ((q & 3) * 3) * NC + tid;
-      const T fq = Fq[eo];
-      const T ra = t_div(R[0], lin_interp((fq + Fp[eo]) / T(2), lr, omlr));
-      const T rx = t_div(R[NC], lin_interp((fq + Fq[eo - 1]) / T(2), lr, omlr));
-      const T rc = t_div(R[2 * NC], lin_interp((fq + Fq[eo - WX]) / T(2), lr, omlr));
-      usA[3] = dq ? AA : ra;  // Dirichlet planes of BC!
-      usX[3] = dirX ? AXv : rx;
-      usC[3] = dirC ? ACv : rc;
-    }
-    // C. VOF flux + mass flux through face p = k+1 (advection.jl:108-137): own column, then the halo entry
-    const bool needp = p <= nA && (perA || p >= 2);
+    const T* Fq = sF + (q & 7) * PLH;
     const T* Up = sU + (p & 3) * PLH;
     const T* U0p = sU0 + (p & 3) * PLH;
     T* Mp = sM + (p & 1) * PLH;
-    const T up1 = Up[eo], u0p1 = U0p[eo];
-    T FFhi = T(0), Mhi = T(0);
-    bool marked = false;
-    if (needp) {
-      const T dl = P.hdt * (up1 + u0p1);  // δt/2*(u+u⁰)
-      if (dl != T(0)) {
-        const bool up = dl > T(0);
-        const T fc = up ? Fk[eo] : Fp[eo];  // upwind cell
-        const int cu = up ? k : p;
-        const bool ghost = !perA && (cu < 2 || cu > nA - 1);
-        if (ghost || fullorempty(fc)) {
-          FFhi = fc * dl;
-          Mhi = dl * lr + omlr * FFhi;
-          if (MOM) Mhi = Mhi * P.idt;
-        } else { sList[atomicAdd(sCnt, 1)] = eo; marked = true; }
+    const bool needp = p <= nA && (perA || p >= 2);
+    T FFhi[CPT], Mhi[CPT], div[CPT], fK[CPT], dilk[CPT], up1[CPT], u0p1[CPT];
+    int cb[CPT];
+    bool marked[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      const int e = eo[j];
+      // B. u★ of plane q = k+2 (flow.jl:197): BC!(ρu/ρ(f̄))
+      if (MOM) {
+        const T* R = sR + ((q & 3) * 3) * NC + tid + j * NT;
+        const T fq = Fq[e];
+        const T ra = t_div(R[0], lin_interp((fq + Fp[e]) / T(2), lr, omlr));
+        const T rx = t_div(R[NC], lin_interp((fq + Fq[e - 1]) / T(2), lr, omlr));
+        const T rc = t_div(R[2 * NC], lin_interp((fq + Fq[e - WX]) / T(2), lr, omlr));
+        usA[j][3] = dq ? AA : ra;  // Dirichlet planes of BC!
+        usX[j][3] = dirX ? AXv : rx;
+        usC[j][3] = dirC[j] ? ACv : rc;
+      }
+      // C. VOF flux + mass flux through face p = k+1 (advection.jl:108-137)
+      up1[j] = Up[e]; u0p1[j] = U0p[e];
+      FFhi[j] = T(0); Mhi[j] = T(0); marked[j] = false;
+      if (needp) {
+        const T dl = P.hdt * (up1[j] + u0p1[j]);  // δt/2*(u+u⁰)
+        if (dl != T(0)) {
+          const bool up = dl > T(0);
+          const T fc = up ? Fk[e] : Fp[e];  // upwind cell
+          const int cu = up ? k : p;
+          const bool ghost = !perA && (cu < 2 || cu > nA - 1);
+          if (ghost || fullorempty(fc)) {
+            FFhi[j] = fc * dl;
+            Mhi[j] = dl * lr + omlr * FFhi[j];
+            if (MOM) Mhi[j] = Mhi[j] * P.idt;
+          } else { sList[atomicAdd(sCnt, 1)] = e; marked[j] = true; }
+        }
+      }
+      Mp[e] = Mhi[j];
+      // D. dilation of plane k (flow.jl:216)
+      div[j] = (up1[j] - uk[j]) + (u0p1[j] - u0k[j]);  // ∂(d,I,u)+∂(d,I,u⁰)
+      fK[j] = Fk[e];
+      cb[j] = P.first ? ((fK[j] < T(0.5)) ? 0 : 1) : cbo[j];  // flow.jl:172 (c̄ from the incoming f)
+      dilk[j] = T(0);
+      if (MOM) {
+        dilk[j] = (lin_interp(T(cb[j]), lr, omlr) * div[j]) / T(2);
+        sDil[(k & 1) * PLH + e] = dilk[j];
       }
     }
-    Mp[eo] = Mhi;
+    // C/D for the halo entry (mass flux and dilation that the x-1 / c-1 neighbours of the tile edge need)
     if (MOM && hU) {
       T m = T(0);
       if (needp) {
@@ -256,22 +301,11 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
         }
       }
       Mp[eh] = m;
-    }
-    // D. dilation of plane k (flow.jl:216): own column, then the halo entry
-    const T div = (up1 - uk) + (u0p1 - u0k);  // ∂(d,I,u)+∂(d,I,u⁰)
-    const T fK = Fk[eo];
-    const int cb = P.first ? ((fK < T(0.5)) ? 0 : 1) : cbo;  // flow.jl:172 (c̄ from the incoming f)
-    T dilk = T(0);
-    if (MOM) {
-      dilk = (lin_interp(T(cb), lr, omlr) * div) / T(2);
-      sDil[(k & 1) * PLH + eo] = dilk;
-      if (hU) {
-        const T* Uk = sU + (k & 3) * PLH;
-        const T* U0k = sU0 + (k & 3) * PLH;
-        const T dh = (Up[eh] - Uk[eh]) + (U0p[eh] - U0k[eh]);
-        const int ch = P.first ? ((Fk[eh] < T(0.5)) ? 0 : 1) : cbh;
-        sDil[(k & 1) * PLH + eh] = (lin_interp(T(ch), lr, omlr) * dh) / T(2);
-      }
+      const T* Uk = sU + (k & 3) * PLH;
+      const T* U0k = sU0 + (k & 3) * PLH;
+      const T dh = (Up[eh] - Uk[eh]) + (U0p[eh] - U0k[eh]);
+      const int ch = P.first ? ((Fk[eh] < T(0.5)) ? 0 : 1) : cbh;
+      sDil[(k & 1) * PLH + eh] = (lin_interp(T(ch), lr, omlr) * dh) / T(2);
     }
     __syncthreads();  // S2: mass flux of face p, dilation of plane k and the interface list are complete
     {
@@ -290,81 +324,90 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
           Mp[e] = m;
         }
         __syncthreads();
-        if (marked) { FFhi = sFX[eo]; Mhi = Mp[eo]; }
-      }
-    }
-    // G. SynDRoM momentum flux through face p of the three momentum cells of this column (flow.jl:20-57,223)
-    T FhiA = T(0), FhiX = T(0), FhiC = T(0);
-    if (MOM) {
-      const T Mc = dp ? AA : Mhi;  // velocity BC! on ρuf (flow.jl:207)
-      const bool Lvar = !perA && p == 2, Rvar = !perA && p == nA;
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        T Mo;
-        if (r == 0) Mo = dpm ? AA : Mlo;
-        else if (r == 1) Mo = dp ? AA : Mp[eo - 1];
-        else Mo = dp ? AA : Mp[eo - WX];
-        const T Psi = (Mc + Mo) / T(2);
-        const T* us = (r == 0) ? usA : ((r == 1) ? usX : usC);
-        const bool pos = Psi > T(0);
-        T uu, cc, dd;
-        if (Lvar) {  // ϕuL
-          if (pos) { uu = T(2) * us[1] - us[2]; cc = us[1]; dd = us[2]; }
-          else { uu = us[3]; cc = us[2]; dd = us[1]; }
-        } else if (Rvar) {  // ϕuR
-          if (Psi < T(0)) { uu = T(2) * us[2] - us[1]; cc = us[2]; dd = us[1]; }
-          else { uu = us[0]; cc = us[1]; dd = us[2]; }
-        } else {  // ϕu
-          uu = pos ? us[0] : us[3];
-          cc = pos ? us[1] : us[2];
-          dd = pos ? us[2] : us[1];
-        }
-        // donor momentum cell: plane k (Ψ>0) or p; its face-centred old f (dρ after f2face!+BCv!, flow.jl:205)
-        const T* Fd = pos ? Fk : Fp;
-        T fo;
-        if (r == 0) {
-          const T* Fdm = pos ? sF + ((k - 1) & 7) * PLH : Fk;
-          fo = (Fd[eo] + Fdm[eo]) / T(2);
-          if (Lvar && pos) fo = (sF[(q & 7) * PLH + eo] + Fp[eo]) / T(2);  // donor index 1: BCv! copies plane 3 = (f(3)+f(2))/2
-          if (Rvar && !pos) fo = __ldg(P.drho + cA + (long long)(nA - 1) * sA + go);  // donor index nA: never written by f2face!
-        } else if (r == 1) fo = (Fd[eo] + Fd[eo - 1]) / T(2);
-        else fo = (Fd[eo] + Fd[eo - WX]) / T(2);
-        const T fl = syndrom_flux(P.lim, Psi, uu, cc, dd, lin_interp(fo, lr, omlr), dt);
-        if (r == 0) FhiA = fl; else if (r == 1) FhiX = fl; else FhiC = fl;
+        for (int j = 0; j < CPT; ++j)
+          if (marked[j]) { FFhi[j] = sFX[eo[j]]; Mhi[j] = Mp[eo[j]]; }
       }
     }
-    // H. update of cell k
-    if (k >= k0 && valid) {
-      const long long lk = (long long)(k - 1) * sA + go;
-      if (P.first) P.cbar[lk] = (int8_t)cb;
-      T fn = fK + ((FFlo - FFhi) + ((T(cb) * div) * dt) / T(2));  // advection.jl:83
-      if (fn != fn) rnan = 1;
-      if (fn > rmax) { rmax = fn; amax = (unsigned int)lk; }
-      if (fn < rmin) { rmin = fn; amin = (unsigned int)lk; }
-      fn = (fn < P.tol) ? T(0) : ((fn > P.onemtol) ? T(1) : fn);  // cleanWisp!
-      P.f_out[lk] = fn;
-      if (!MOM && P.rhouf_j != nullptr) {
-        P.rhouf_j[lk] = Mlo;
-        if (k == nA - 1) P.rhouf_j[lk + sA] = Mhi;  // inside_uWB includes the upper boundary face
-      }
+    const long long lkp = lk0;  // (k-1)*sA
+    lk0 += sA;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      const int e = eo[j];
+      // G. SynDRoM momentum flux through face p of the three momentum cells of this column (flow.jl:20-57,223)
+      T FhiA = T(0), FhiX = T(0), FhiC = T(0);
       if (MOM) {
-        const T* R = sR + ((k & 3) * 3) * NC + tid;
-        const T* O = sO + ((k & 1) * 3) * NC + tid;
-        const T* Dk = sDil + (k & 1) * PLH;
-        const T dNa = (!perA && k == 2) ? dilk : dilm1;  // BCf! (Neumann) on ρ̄∂ⱼuⱼ along the sweep direction
-        // r = Φ[I] - Φ[I+δj] + uOld*ϕ(i,I,ρ̄∂ⱼuⱼ);  ρu += δt*r          flow.jl:223-231
-        const T rA = (FloA - FhiA) + O[0] * ((dilk + dNa) / T(2));
-        const T rX = (FloX - FhiX) + O[NC] * ((dilk + Dk[eo - 1]) / T(2));
-        const T rC = (FloC - FhiC) + O[2 * NC] * ((dilk + Dk[eo - WX]) / T(2));
-        P.rhou_out[cA + lk] = R[0] + dt * rA;
-        P.rhou_out[lk] = R[NC] + dt * rX;
-        P.rhou_out[cC + lk] = R[2 * NC] + dt * rC;
-      }
-    }
-    // I. roll the register pipeline
-    FloA = FhiA; FloX = FhiX; FloC = FhiC; FFlo = FFhi; Mlo = Mhi; dilm1 = dilk; uk = up1; u0k = u0p1;
+        const T Mc = dp ? AA : Mhi[j];  // velocity BC! on ρuf (flow.jl:207)
+        const bool Lvar = !perA && p == 2, Rvar = !perA && p == nA;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { usA[i] = usA[i + 1]; usX[i] = usX[i + 1]; usC[i] = usC[i + 1]; }
+        for (int r = 0; r < 3; ++r) {
+          T Mo;
+          if (r == 0) Mo = dpm ? AA : Mlo[j];
+          else if (r == 1) Mo = dp ? AA : Mp[e - 1];
+          else Mo = dp ? AA : Mp[e - WX];
+          const T Psi = (Mc + Mo) / T(2);
+          const T* us = (r == 0) ? usA[j] : ((r == 1) ? usX[j] : usC[j]);
+          const bool pos = Psi > T(0);
+          T uu, cc, dd;
+          if (Lvar) {  // ϕuL
+            if (pos) { uu = T(2) * us[1] - us[2]; cc = us[1]; dd = us[2]; }
+            else { uu = us[3]; cc = us[2]; dd = us[1]; }
+          } else if (Rvar) {  // ϕuR
+            if (Psi < T(0)) { uu = T(2) * us[2] - us[1]; cc = us[2]; dd = us[1]; }
+            else { uu = us[0]; cc = us[1]; dd = us[2]; }
+          } else {  // ϕu
+            uu = pos ? us[0] : us[3];
+            cc = pos ? us[1] : us[2];
+            dd = pos ? us[2] : us[1];
+          }
+          // donor momentum cell: plane k (Ψ>0) or p; its face-centred old f (dρ after f2face!+BCv!, flow.jl:205)
+          const T* Fd = pos ? Fk : Fp;
+          T fo;
+          if (r == 0) {
+            const T* Fdm = pos ? sF + ((k - 1) & 7) * PLH : Fk;
+            fo = (Fd[e] + Fdm[e]) / T(2);
+            if (Lvar && pos) fo = (Fq[e] + Fp[e]) / T(2);  // donor index 1: BCv! copies plane 3 = (f(3)+f(2))/2
+            if (Rvar && !pos) fo = __ldg(P.drho + cA + (long long)(nA - 1) * sA + go[j]);  // donor index nA: never written by f2face!
+          } else if (r == 1) fo = (Fd[e] + Fd[e - 1]) / T(2);
+          else fo = (Fd[e] + Fd[e - WX]) / T(2);
+          const T fl = syndrom_flux(P.lim, Psi, uu, cc, dd, lin_interp(fo, lr, omlr), dt);
+          if (r == 0) FhiA = fl; else if (r == 1) FhiX = fl; else FhiC = fl;
+        }
+      }
+      // H. update of cell k
+      if (k >= k0 && valid[j]) {
+        const long long lk = lkp + go[j];
+        if (P.first) P.cbar[lk] = (int8_t)cb[j];
+        T fn = fK[j] + ((FFlo[j] - FFhi[j]) + ((T(cb[j]) * div[j]) * dt) / T(2));  // advection.jl:83
+        if (fn != fn) rnan = 1;
+        if (fn > rmax) { rmax = fn; amax = (unsigned int)lk; }
+        if (fn < rmin) { rmin = fn; amin = (unsigned int)lk; }
+        fn = (fn < P.tol) ? T(0) : ((fn > P.onemtol) ? T(1) : fn);  // cleanWisp!
+        P.f_out[lk] = fn;
+        if (!MOM && P.rhouf_j != nullptr) {
+          P.rhouf_j[lk] = Mlo[j];
+          if (k == nA - 1) P.rhouf_j[lk + sA] = Mhi[j];  // inside_uWB includes the upper boundary face
+        }
+        if (MOM) {
+          const T* R = sR + ((k & 3) * 3) * NC + tid + j * NT;
+          const T* O = sO + ((k & 1) * 3) * NC + tid + j * NT;
+          const T* Dk = sDil + (k & 1) * PLH;
+          const T dNa = (!perA && k == 2) ? dilk[j] : dilm1[j];  // BCf! (Neumann) on ρ̄∂ⱼuⱼ along the sweep direction
+          // r = Φ[I] - Φ[I+δj] + uOld*ϕ(i,I,ρ̄∂ⱼuⱼ);  ρu += δt*r          flow.jl:223-231
+          const T rA = (FloA[j] - FhiA) + O[0] * ((dilk[j] + dNa) / T(2));
+          const T rX = (FloX[j] - FhiX) + O[NC] * ((dilk[j] + Dk[e - 1]) / T(2));
+          const T rC = (FloC[j] - FhiC) + O[2 * NC] * ((dilk[j] + Dk[e - WX]) / T(2));
+          P.rhou_out[cA + lk] = R[0] + dt * rA;
+          P.rhou_out[lk] = R[NC] + dt * rX;
+          P.rhou_out[cC + lk] = R[2 * NC] + dt * rC;
+        }
+      }
+      // I. roll the register pipeline
+      FloA[j] = FhiA; FloX[j] = FhiX; FloC[j] = FhiC; FFlo[j] = FFhi[j]; Mlo[j] = Mhi[j]; dilm1[j] = dilk[j];
+      uk[j] = up1[j]; u0k[j] = u0p1[j];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { usA[j][i] = usA[j][i + 1]; usX[j][i] = usX[j][i + 1]; usC[j][i] = usC[j][i + 1]; }
+    }
     if (tid == 0) *sCnt = 0;
   }
 

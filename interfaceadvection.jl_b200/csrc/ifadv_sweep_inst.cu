@@ -86,14 +86,14 @@ static int launch_march_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
 }
 
 // v3: register-marching kernel for sweeps along y / z (3-D only)
-template <class T, int J, int TC, bool MOM, int MINB>
+template <class T, int J, int CPT, bool MOM, int MINB>
 static int launch_along_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
-  constexpr int NT = 32 * TC;
+  constexpr int NT = 256, TC = (NT / 32) * CPT;
   using TL = ATile<TC>;
   SweepP<T> P;
   fill_params<T>(c, q, J, P);
   const size_t smem = TL::template smem_bytes<T>(MOM);
-  auto kern = along_kernel<T, J, TC, MOM, NT, MINB>;
+  auto kern = along_kernel<T, J, CPT, MOM, NT, MINB>;
   static bool attr_set = false;
   if (!attr_set) {
     CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -117,9 +117,10 @@ static int launch_along_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
 template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   if constexpr (D == 3) {
     if (c->use_march == 1 && q.j != 0) {
-      constexpr int MB = (sizeof(T) == 4) ? 3 : 2;
-      if (q.j == 1) return launch_along_t<T, 1, 8, MOM, MB>(c, st, q);
-      return launch_along_t<T, 2, 8, MOM, MB>(c, st, q);
+      // Float32: two columns per thread (2 CTAs/SM, twice the ILP, half the per-plane overhead); Float64: one
+      constexpr int CP = (sizeof(T) == 4) ? 2 : 1;
+      if (q.j == 1) return launch_along_t<T, 1, CP, MOM, 2>(c, st, q);
+      return launch_along_t<T, 2, CP, MOM, 2>(c, st, q);
     }
     if (c->use_march) {
       // tile shapes sized so that 25 shared planes leave 3 (f32) / 2-3 (f64) CTAs per SM
