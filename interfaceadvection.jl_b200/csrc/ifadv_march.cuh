@@ -75,6 +75,15 @@ template <class T> IFADV_DI void cp_async(T* smem_dst, const T* gsrc) {
   if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc));
   else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc));
 }
+template <class T> IFADV_DI void cp_async_s(unsigned saddr, const T* gsrc) {
+  if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(saddr), "l"(gsrc));
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(gsrc));
+}
+// branch-free index maps for plane indices that stay within one period of the box (chunks do)
+IFADV_DI int wrap1(int v, int n) { const int m = n - 2; v += (v < 2) ? m : 0; v -= (v > n - 1) ? m : 0; return v; }
+IFADV_DI int map1(int v, int n, bool per) { return per ? wrap1(v, n) : min(max(v, 2), n - 1); }
+IFADV_DI int own1(int v, int n, bool per) { return per ? wrap1(v, n) : min(max(v, 1), n); }
+
 IFADV_DI void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 IFADV_DI void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
@@ -107,8 +116,7 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
   const long long st3[3] = {1, g.s1, g.s2};
   const long long sA = st3[J], sB = st3[DB], sC = st3[DC];
   const bool perA = (g.per >> J) & 1u, perB = (g.per >> DB) & 1u, perC = (g.per >> DC) & 1u;
-  const long long S = g.S;
-  const long long cA = (long long)J * S, cB = (long long)DB * S, cC = (long long)DC * S;
+  const long long cA = P.coff[J], cB = P.coff[DB], cC = P.coff[DC];
 
   // blockIdx.x tiles x, blockIdx.y tiles the other in-plane dimension, blockIdx.z chunks of the march direction
   const int ox = 2 + blockIdx.x * (AX ? TA : TB), oo = 2 + blockIdx.y * (AX ? TB : TA);
@@ -185,29 +193,34 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
   const T AA = P.A[J], AB = P.A[DB], AC = P.A[DC];
 
   // ---- asynchronous plane loads ---------------------------------------------------------------------------------------------------
+  constexpr unsigned SZ = sizeof(T);
+  const unsigned sb = (unsigned)__cvta_generic_to_shared(sm);
   auto issue_f = [&](int vc) {
-    const T* fp = P.f_in + (long long)(mapc(vc, nC, perC) - 1) * sC;
-    T* dF = sF + (vc & 3) * PL;
+    const T* fp = P.f_in + (long long)(map1(vc, nC, perC) - 1) * sC;
+    const unsigned dF = sb + (unsigned)(vc & 3) * (PL * SZ);
 #pragma unroll
     for (int t = 0; t < TR; ++t) {
-      const int e = ent(t);
-      if (flg[t] & MF_VALID) cp_async(dF + e, fp + gmm[t]);
+      if (flg[t] & MF_VALID) cp_async_s(dF + ent(t) * SZ, fp + gmm[t]);
     }
   };
   auto issue_rest = [&](int vc, bool full) {
-    const long long pm = (long long)(mapc(vc, nC, perC) - 1) * sC;
-    const long long po = (long long)((perC ? wrapc(vc, nC) : min(max(vc, 1), nC)) - 1) * sC;
-    const int s2 = vc & 1;
+    const long long pm = (long long)(map1(vc, nC, perC) - 1) * sC;
+    const long long po = (long long)(own1(vc, nC, perC) - 1) * sC;
+    const unsigned s2 = (unsigned)(vc & 1);
     const T* up = P.uj + pm;
     const T* u0p = P.u0j + pm;
-    T* dU = sU + s2 * PL;
-    T* dU0 = sU0 + s2 * PL;
+    const unsigned dU = sb + (unsigned)((sU - sm) + s2 * PL) * SZ;
+    const unsigned dU0 = sb + (unsigned)((sU0 - sm) + s2 * PL) * SZ;
+    const unsigned dR = sb + (unsigned)((sRU - sm) + s2 * 3 * PL) * SZ;
+    const T* ra = P.rhou_in + cA + pm;
+    const T* rb = P.rhou_in + cB + pm;
+    const T* rc = P.rhou_in + cC + po;
 #pragma unroll
     for (int t = 0; t < TR; ++t) {
-      const int e = ent(t);
+      const unsigned e4 = ent(t) * SZ;
       if (flg[t] & MF_U) {
-        cp_async(dU + e, up + gom[t]);
-        cp_async(dU0 + e, u0p + gom[t]);
+        cp_async_s(dU + e4, up + gom[t]);
+        cp_async_s(dU0 + e4, u0p + gom[t]);
       }
       if (MOM && full && (flg[t] & MF_CELL)) {  // uOld of the next plane: pull the lines into L2/L1 ahead of the update stage
         const T* uo = P.uOld + (long long)(vc - 1) * sC + gmm[t];
@@ -216,10 +229,9 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
         asm volatile("prefetch.global.L1 [%0];" ::"l"(uo + cC));
       }
       if (MOM && full && (flg[t] & MF_US)) {
-        T* dR = sRU + (s2 * 3) * PL + e;
-        cp_async(dR, P.rhou_in + cA + pm + gom[t]);
-        cp_async(dR + PL, P.rhou_in + cB + pm + gmm[t]);
-        cp_async(dR + 2 * PL, P.rhou_in + cC + po + gmm[t]);
+        cp_async_s(dR + e4, ra + gom[t]);
+        cp_async_s(dR + e4 + PL * SZ, rb + gmm[t]);
+        cp_async_s(dR + e4 + 2 * PL * SZ, rc + gmm[t]);
       }
     }
   };
@@ -228,7 +240,7 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
   int cbn[TR];
   auto load_cbar = [&](int vc) {
     if (MOM && !P.first) {
-      const long long pm = (long long)(mapc(vc, nC, perC) - 1) * sC;
+      const long long pm = (long long)(map1(vc, nC, perC) - 1) * sC;
 #pragma unroll
       for (int t = 0; t < TR; ++t) cbn[t] = (flg[t] & MF_DIL) ? (int)P.cbar[pm + gmm[t]] : 0;
     }
@@ -374,7 +386,7 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
   };
 
   // ---- P4: cell update -------------------------------------------------------------------------------------------------------------------------
-  double rmax = -INFINITY, rmin = INFINITY;
+  T rmax = -INFINITY, rmin = INFINITY;
   unsigned int amax = 0, amin = 0;
   int rnan = 0;
   auto update_stage = [&](int vc) {
@@ -398,12 +410,9 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
         if (P.first) P.cbar[lk] = (int8_t)cb;
         // f[I] += fᶠ[I]-fᶠ[I+δ] + c̄[I]*(∂u+∂u⁰)*δt/2          advection.jl:83
         T fn = fK + ((sFF[e] - sFF[e + SA]) + ((T(cb) * div) * dt) / T(2));
-        {
-          const double fd = (double)fn;
-          if (fn != fn) rnan = 1;
-          if (fd > rmax) { rmax = fd; amax = (unsigned int)lk; }
-          if (fd < rmin) { rmin = fd; amin = (unsigned int)lk; }
-        }
+        if (fn != fn) rnan = 1;
+        if (fn > rmax) { rmax = fn; amax = (unsigned int)lk; }
+        if (fn < rmin) { rmin = fn; amin = (unsigned int)lk; }
         fn = (fn < P.tol) ? T(0) : ((fn > P.onemtol) ? T(1) : fn);  // cleanWisp!
         P.f_out[lk] = fn;
         if (!MOM && P.rhouf_j != nullptr) {
@@ -492,7 +501,7 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
   if (P.red != nullptr) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-      const double omax = __shfl_xor_sync(0xffffffffu, rmax, off), omin = __shfl_xor_sync(0xffffffffu, rmin, off);
+      const T omax = __shfl_xor_sync(0xffffffffu, rmax, off), omin = __shfl_xor_sync(0xffffffffu, rmin, off);
       const unsigned int oamax = __shfl_xor_sync(0xffffffffu, amax, off), oamin = __shfl_xor_sync(0xffffffffu, amin, off);
       const int onan = __shfl_xor_sync(0xffffffffu, rnan, off);
       if (omax > rmax) { rmax = omax; amax = oamax; }
@@ -501,11 +510,11 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
     }
     if ((tid & 31) == 0) {
       if (rmax > -INFINITY) {
-        atomicMax(P.red + 0, ord_key(rmax));
+        atomicMax(P.red + 0, ord_key((double)rmax));
         atomicMax(P.red + 2, ((unsigned long long)ord_key32((float)rmax) << 32) | amax);
       }
       if (rmin < INFINITY) {
-        atomicMin(P.red + 1, ord_key(rmin));
+        atomicMin(P.red + 1, ord_key((double)rmin));
         atomicMin(P.red + 3, ((unsigned long long)ord_key32((float)rmin) << 32) | amin);
       }
       if (rnan) atomicAdd(P.red + 4, 1ull);
