@@ -255,3 +255,87 @@ def test_rejects_unsupported(ia):
         ia.BC(ud, lambda i, x, t: 0.0)
     with pytest.raises(ia.IfadvError):
         ia.BCf(torch.zeros(4, 4, dtype=torch.float64))  # CPU tensor: no fallback
+
+
+def _fresh_context_env(ia, kernel):
+    """Contexts read IFADV_KERNEL at creation: drop the cache so the next call builds one with the requested kernel family."""
+    import os
+    from interfaceadvection.jl_b200 import api
+    api._contexts.clear()
+    if kernel is None:
+        os.environ.pop("IFADV_KERNEL", None)
+    else:
+        os.environ["IFADV_KERNEL"] = kernel
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+def test_kernel_families_agree(ia, T):
+    """The three generations of the fused sweep (v1 tile, plane-marching, register-marching) implement the same
+    arithmetic: bit-identical in Float64, and within a few ulp in Float32 (the v1 tile kernel is built exact, the
+    marching kernels with IFADV_FAST_F32)."""
+    st = make_state((70, 40, 36), "C3", T, perdir=(2,), uBC=(0.0, 0.0, 0.0))
+    a0 = alloc_cmom(st)
+    O.u2rhou(a0["rhou"], st["u"], st["f"], st["lam_rho"]); O.BC(a0["rhou"], st["uBC"], False, st["perdir"])
+    rhou0 = a0["rhou"].copy(order="F")
+    res = {}
+    try:
+        for kern in ("tile", "march", None):
+            _fresh_context_env(ia, kern)
+            sc, f_c, ru_c = run_cuda_cmom(ia, st, st["f"], st["u"], st["u"], st["u"], rhou0, 1.0, (3, 1, 2))
+            res[kern] = (f_c, ru_c)
+    finally:
+        _fresh_context_env(ia, None)
+    f_o = st["f"].copy(order="F")
+    so, rep, ao = oracle_cmom_call(st, f_o, st["u"], st["u"], st["u"], rhou0, 1.0, (3, 1, 2))
+    for kern, (f_c, ru_c) in res.items():
+        assert np.abs(f_c - f_o).max() <= TOL[T], kern
+        assert np.abs(inside(ru_c, 3) - inside(ao["rhou"], 3)).max() <= TOL[T], kern
+    if T == np.float64:
+        assert np.array_equal(res["tile"][0], res[None][0]) and np.array_equal(res["march"][0], res[None][0])
+        assert np.array_equal(inside(res["tile"][1], 3), inside(res[None][1], 3))
+        assert np.array_equal(inside(res["march"][1], 3), inside(res[None][1], 3))
+
+
+def test_full_size_properties_enright_256(ia):
+    """BASELINE config 2 at full size (3-D Enright/LeVeque 256³, Float32, pure VOF, walls): size-independent properties.
+    The velocity is the discrete curl of a vector potential, so Σf must be conserved to round-off, f must stay in
+    [0,1] and the ghost layer must equal BCf! of the interior."""
+    from interfaceadvection.jl_b200 import configs
+    N = (256, 256, 256)
+    dev = torch.device("cuda", 0)
+    case = configs.make_case("C2_enright_256", device=dev)
+    sim = ia.TwoPhaseSimulation(N, (0, 0, 0), 256.0, T=torch.float32, InterfaceSDF=case["sdf"], perdir=(), U=1.0, dt=1.0, device=dev)
+    sim.flow.u.copy_(case["u"]); ia.BC(sim.flow.u, (0, 0, 0), False, ()); sim.flow.u0.copy_(sim.flow.u)
+    V0 = ia.sum_inside(sim.intf.f)
+    for n in range(6):
+        st = ia.advect(sim.flow, sim.intf)
+        sim.flow.dt.append(1.0)
+        assert st == 0
+    V1 = ia.sum_inside(sim.intf.f)
+    assert abs(V1 - V0) <= 2e-6 * V0, (V0, V1)          # Float32 round-off over 18 sweeps of 16.7 M cells
+    f = sim.intf.f
+    assert float(f.min()) >= 0.0 and float(f.max()) <= 1.0
+    g = f.clone(memory_format=torch.preserve_format); ia.BCf(g, ())
+    assert torch.equal(g, f)
+
+
+def test_full_size_properties_dambreak(ia):
+    """BASELINE config 3 (3-D dam break 512x256x256, Float32, walls, λρ = 1e-3, full CMOM + SynDRoM): mass conservation,
+    boundedness and finite momentum over two CMOM advection steps at full size."""
+    from interfaceadvection.jl_b200 import configs
+    N = (512, 256, 256)
+    dev = torch.device("cuda", 0)
+    case = configs.make_case("C3_dambreak_512x256x256", device=dev)
+    sim = ia.TwoPhaseSimulation(N, (0, 0, 0), 512.0, T=torch.float32, lam_rho=1e-3, InterfaceSDF=case["sdf"], perdir=(), U=1.0, dt=1.0,
+                                device=dev)
+    sim.flow.u.copy_(case["u"]); ia.BC(sim.flow.u, (0, 0, 0), False, ())
+    V0 = ia.sum_inside(sim.intf.f)
+    for _ in range(2):
+        ia.mom_advect_step(sim.flow, sim.intf, 1.0, check=True)
+        sim.flow.dt.append(1.0)
+    V1 = ia.sum_inside(sim.intf.f)
+    assert abs(V1 - V0) <= 2e-6 * V0
+    assert float(sim.intf.f.min()) >= 0.0 and float(sim.intf.f.max()) <= 1.0
+    assert bool(torch.isfinite(sim.intf.rhou[1:-1, 1:-1, 1:-1]).all())
+    del sim
+    torch.cuda.empty_cache()
