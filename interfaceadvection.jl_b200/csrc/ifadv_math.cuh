@@ -185,8 +185,15 @@ template <class T> IFADV_DI T limiter(int lam, T u, T c, T d) {
 // ϕq, the SynDRoM flux (src/flow.jl:37-57) for mass flux Psi, stencil (uu,cc,dd) and donor density mOld
 template <class T> IFADV_DI T syndrom_flux(int lam, T Psi, T uu, T cc, T dd, T mOld, T dt) {
   T vd = limiter(lam, uu, cc, dd);
-  T va = T(2) * cc - vd;
   T mOut = t_abs(Psi) * dt;
+#ifdef IFADV_FAST_F32
+  if (sizeof(T) == 4) {
+    // (vb+vd)/2 = l2*cc + (1-l2)*vd in exact arithmetic; branch-free, within Float32 round-off of the reference order
+    const T l2 = (mOut > mOld) ? T(1) : t_div(mOut, mOld);
+    return Psi * (vd + l2 * (cc - vd));
+  }
+#endif
+  T va = T(2) * cc - vd;
   if (mOut > mOld) return Psi * cc;
   T l2 = t_div(t_abs(mOut), mOld);
   T l1 = T(1) - l2;
