@@ -73,7 +73,8 @@ int64_t ifadv_launch_count(const ifadv_ctx* ctx);
 const char* ifadv_version(void);
 /* Measurement aid for bench.py: while enabled, every fused sweep launch is bracketed by CUDA events recorded on
  * the launching stream (up to 4096 launches).  ifadv_profile_read synchronises those events, returns the summed
- * kernel time in ms and the number of launches, and resets the pool. */
+ * kernel time in ms and the number of launches -- index 0: standard sweeps (13s+1 B/cell), index 1: fused first
+ * sweeps of ifadv_u2rhou_advect_vof_rhouu (10s+1 B/cell); both arrays have 2 entries -- and resets the pool. */
 int ifadv_profile(ifadv_ctx* ctx, int enable);
 int ifadv_profile_read(ifadv_ctx* ctx, double* total_ms, int64_t* launches);
 
@@ -96,6 +97,16 @@ int ifadv_advect_vof_rhouu(ifadv_ctx* ctx, void* stream, void* f, void* ff, void
                            const void* u0, double dt, int8_t* cbar, void* rhou, void* r, void* Phi, void* rhouf, void* uStar,
                            const void* uOld, void* dilaU, const void* drho, double lambda_rho, int limiter, int normal_scheme,
                            const double uBC[3], unsigned perdir_mask, int exitBC, const int dirO[3], ifadv_report* report);
+
+/* Fused form of the three calls MPFMomStep! makes back to back (src/flow.jl:61,69-70 and :89-92):
+ *     f .= f_src;  u2ρu!(ρu,uOld,f,λρ);  BC!(ρu,uBC,false,perdir);  advectVOFρuu!(f,…,ρu,…,uOld,…)
+ * Both call sites build ρu from the very velocity array they pass as uOld, so the first directional sweep can form
+ * ρu = BC!(uOld·ρ(f̄)) on the fly: the u2ρu! pass, the BC! launch, the f⁰←f copy and three of the thirteen input streams
+ * of sweep 1 disappear.  Results are bit-identical to the three separate calls.  f_src may equal f.  ρu is output only. */
+int ifadv_u2rhou_advect_vof_rhouu(ifadv_ctx* ctx, void* stream, const void* f_src, void* f, void* ff, void* Phi, const void* u,
+                                  const void* u0, double dt, int8_t* cbar, void* rhou, void* r, void* rhouf, const void* uOld,
+                                  const void* drho, double lambda_rho, int limiter, int normal_scheme, const double uBC[3],
+                                  unsigned perdir_mask, const int dirO[3], ifadv_report* report);
 
 /* ---- secondary seams on the path ------------------------------------------------------------------------ */
 /* u2ρu!(ρu,u,f,λρ) / ρu2u!(u,ρu,f,λρ)                                           src/VOFutil.jl:198-211 */

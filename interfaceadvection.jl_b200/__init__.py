@@ -8,5 +8,5 @@ bench.py.  PyTorch only supplies device memory and streams.  There is no CPU fal
 from ._lib import Context, IfadvError, Report, LIMITERS, NORMAL_SCHEMES, LIB_PATH, IFADV_NO_RHOUF  # noqa: F401
 from .api import (  # noqa: F401
     BC, BCf, MPCFL, MPFMomStep, Flow, TwoPhaseSimulation, advect, advectVOF, advectVOFrhouu, advectfq, applyVOF, cVOF,
-    from_numpy, jl_empty, mom_advect_step, jl_zeros, rhou2u, sim_step, sim_time, sum_inside, to_numpy, u2rhou, context_for,
+    from_numpy, jl_empty, mom_advect_step, u2rhou_advectfq, jl_zeros, rhou2u, sim_step, sim_time, sum_inside, to_numpy, u2rhou, context_for,
 )

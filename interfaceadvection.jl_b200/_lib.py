@@ -47,6 +47,8 @@ def lib():
         L.ifadv_advect_vof.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, dbl, vp, vp, dbl, i32, u32, i32p, i32, rep]
         L.ifadv_advect_vof_rhouu.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, i32, i32,
                                              dblp, u32, i32, i32p, rep]
+        L.ifadv_u2rhou_advect_vof_rhouu.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp, dbl, i32, i32, dblp, u32,
+                                                    i32p, rep]
         L.ifadv_u2rhou.argtypes = [vp, vp, vp, vp, vp, dbl]
         L.ifadv_rhou2u.argtypes = [vp, vp, vp, vp, vp, dbl]
         L.ifadv_bc_vec.argtypes = [vp, vp, vp, dblp, i32, u32]
@@ -117,9 +119,10 @@ class Context:
         return self._chk(lib().ifadv_profile(self._h, int(bool(enable))))
 
     def profile_read(self):
-        ms, n = C.c_double(), C.c_int64()
-        self._chk(lib().ifadv_profile_read(self._h, C.byref(ms), C.byref(n)))
-        return ms.value, int(n.value)
+        """-> ((ms_standard, n_standard), (ms_fused_first, n_fused_first))"""
+        ms, n = (C.c_double * 2)(), (C.c_int64 * 2)()
+        self._chk(lib().ifadv_profile_read(self._h, ms, n))
+        return (ms[0], int(n[0])), (ms[1], int(n[1]))
 
     def advect_vof(self, stream, f, ff, alpha, nhat, u, u0, dt, cbar, rhouf, lam_rho, scheme, perdir, dirO, flags=0, report=None):
         r = C.byref(report) if report is not None else None
@@ -132,6 +135,13 @@ class Context:
         return self._chk(lib().ifadv_advect_vof_rhouu(self._h, stream, f, ff, alpha, nhat, u, u0, float(dt), cbar, rhou, r_, Phi, rhouf,
                                                       uStar, uOld, dilaU, drho, float(lam_rho), int(limiter), int(scheme),
                                                       _d3(uBC, self.D), perdir_mask(perdir), int(bool(exitBC)), _i3(dirO, self.D), r))
+
+    def u2rhou_advect_vof_rhouu(self, stream, f_src, f, ff, Phi, u, u0, dt, cbar, rhou, r_, rhouf, uOld, drho, lam_rho, limiter, scheme,
+                                uBC, perdir, dirO, report=None):
+        r = C.byref(report) if report is not None else None
+        return self._chk(lib().ifadv_u2rhou_advect_vof_rhouu(self._h, stream, f_src, f, ff, Phi, u, u0, float(dt), cbar, rhou, r_, rhouf,
+                                                             uOld, drho, float(lam_rho), int(limiter), int(scheme),
+                                                             _d3(uBC, self.D), perdir_mask(perdir), _i3(dirO, self.D), r))
 
     def u2rhou(self, stream, rhou, u, f, lam_rho):
         return self._chk(lib().ifadv_u2rhou(self._h, stream, rhou, u, f, float(lam_rho)))

@@ -307,23 +307,43 @@ def MPCFL(a: Flow, c: cVOF, dt_max=1.0, safety=0.8) -> float:
                                   gnorm=gnorm, dt_max=dt_max, safety=safety)
 
 
-def mom_advect_step(a: Flow, c: cVOF, dt=None, project: Optional[Callable] = None, check=False):
+def u2rhou_advectfq(a: Flow, c: cVOF, f_src, f, u1, u2, uOld, dt=None, check=False):
+    """Fused  f .= f_src; u2ρu!(c.ρu,uOld,f,λρ); BC!(c.ρu,…); advectfq!(a,c,f,u¹,u²,uOld,dt)  -- the three calls MPFMomStep! makes
+    back to back at src/flow.jl:61,69-70 and :89-92 (ifadv_u2rhou_advect_vof_rhouu; bit-identical to the separate calls)."""
+    if a.exitBC:
+        raise IfadvError("exitBC=true is not supported by the B200 path")
+    dt = a.dt[-1] if dt is None else dt
+    rep = Report() if check else None
+    st = context_for(f).u2rhou_advect_vof_rhouu(_stream(f), _p(f_src), _p(f), _p(c.ff), _p(a.sigma), _p(u1), _p(u2), dt, _p(c.cbar),
+                                                _p(c.rhou), _p(a.f), _p(c.rhouf), _p(uOld), _p(c.drho), c.lam_rho, _lim(a.lam),
+                                                _ns(c.normalScheme), a.uBC, a.perdir, _dirO(a, a.D), rep)
+    return _report(st, rep) if check else st
+
+
+def mom_advect_step(a: Flow, c: cVOF, dt=None, project: Optional[Callable] = None, check=False, fused=True):
     """The transport half of MPFMomStep! (src/flow.jl:61,69-70,74,89-92): two u2ρu!+BC!+advectfq! groups and the
-    midpoint f⁰.  This is one "advection step" of the benchmark metric; MPCFL is separate."""
+    midpoint f⁰.  This is one "advection step" of the benchmark metric; MPCFL is separate.
+    fused=True issues each group through the fused entry point (same results bit for bit, fewer passes)."""
     dt = a.dt[-1] if dt is None else dt
     ctx, s = context_for(c.f), _stream(c.f)
-    _copy(a.u0, a.u)
-    _copy(c.f0, c.f)                                                  # :61
-    u2rhou(c.rhou, a.u0, c.f0, c.lam_rho)
-    BC(c.rhou, a.uBC, a.exitBC, a.perdir)                             # :69
-    advectfq(a, c, c.f0, a.u0, a.u, a.u, dt, check=check)             # :70
+    _copy(a.u0, a.u)                                                  # :61
+    if fused:
+        u2rhou_advectfq(a, c, c.f, c.f0, a.u0, a.u, a.u, dt, check=check)   # :61 (f⁰←f), :69, :70
+    else:
+        _copy(c.f0, c.f)                                              # :61
+        u2rhou(c.rhou, a.u0, c.f0, c.lam_rho)
+        BC(c.rhou, a.uBC, a.exitBC, a.perdir)                         # :69
+        advectfq(a, c, c.f0, a.u0, a.u, a.u, dt, check=check)         # :70
     ctx.axpby(s, _p(c.f0), 0.5, _p(c.f0), 0.5, _p(c.f))               # :74
     if project is not None:
         project(a, c, "predictor")                                    # :75-82 (WaterLily side)
     _copy(c.f0, c.f)                                                  # :89
-    u2rhou(c.rhou, a.u0, c.f, c.lam_rho)
-    BC(c.rhou, a.uBC, a.exitBC, a.perdir)                             # :91
-    advectfq(a, c, c.f, a.u, a.u, a.u0, dt, check=check)              # :92
+    if fused:
+        u2rhou_advectfq(a, c, c.f, c.f, a.u, a.u, a.u0, dt, check=check)    # :91, :92
+    else:
+        u2rhou(c.rhou, a.u0, c.f, c.lam_rho)
+        BC(c.rhou, a.uBC, a.exitBC, a.perdir)                         # :91
+        advectfq(a, c, c.f, a.u, a.u, a.u0, dt, check=check)          # :92
     if project is not None:
         project(a, c, "corrector")                                    # :95-106 (WaterLily side)
 

@@ -36,7 +36,7 @@ template <class T, int J, int PLH, int WX> struct ABox {
   }
 };
 
-template <class T, int J, int CPT, bool MOM, int NT, int MINB>
+template <class T, int J, int CPT, bool MOM, bool FUSED, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, const int chunk) {
   constexpr int TR = NT / 32;      // rows of threads
   constexpr int TCT = TR * CPT;    // tile rows: a thread owns CPT columns, rows tc, tc+TR, ...
@@ -135,11 +135,13 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
       cp_async_s(aUh + so + TL::RU * PLH * SZ, u0p + gh);
     }
   };
+  constexpr bool fused = MOM && FUSED;
+  const T* rsrc = fused ? P.uOld : P.rhou_in;  // fused sweep 1: the ρu ring carries uOld, ρu = BC!(uOld*ρ(f̄)) is formed on the fly
   auto issue_ru = [&](int v, long long pmv, long long pov) {
     const unsigned d = aR + (unsigned)((v & 3) * 3) * (NC * SZ);
-    const T* ra = P.rhou_in + cA + pov;
-    const T* rx = P.rhou_in + pmv;
-    const T* rc = P.rhou_in + cC + pmv;
+    const T* ra = rsrc + cA + pov;
+    const T* rx = rsrc + pmv;
+    const T* rc = rsrc + cC + pmv;
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
       cp_async_s(d + j * NT * SZ, ra + go[j]);
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
   issue_u(ks, po(ks)); issue_u(ks + 1, po(ks + 1));
   if (MOM) {
     issue_ru(ks, pm(ks), po(ks)); issue_ru(ks + 1, pm(ks + 1), po(ks + 1)); issue_ru(ks + 2, pm(ks + 2), po(ks + 2));
-    issue_uold(ks, pm(ks));
+    if (!fused) issue_uold(ks, pm(ks));
   }
   cp_async_commit();
   load_cbar(pm(ks));
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
     // A. next plane's copies (HBM latency hides behind this plane's arithmetic)
     issue_f(k + 3, pmC);
     issue_u(k + 2, poB);
-    if (MOM) { issue_ru(k + 3, pmC, poC); issue_uold(k + 1, pmA); }
+    if (MOM) { issue_ru(k + 3, pmC, poC); if (!fused) issue_uold(k + 1, pmA); }
     cp_async_commit();
     load_cbar(pmA);
     pmA = pmB; pmB = pmC; poB = poC;
@@ -240,9 +242,12 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
       if (MOM) {
         const T* R = sR + ((q & 3) * 3) * NC + tid + j * NT;
         const T fq = Fq[e];
-        const T ra = t_div(R[0], lin_interp((fq + Fp[e]) / T(2), lr, omlr));
-        const T rx = t_div(R[NC], lin_interp((fq + Fq[e - 1]) / T(2), lr, omlr));
-        const T rc = t_div(R[2 * NC], lin_interp((fq + Fq[e - WX]) / T(2), lr, omlr));
+        const T ha = lin_interp((fq + Fp[e]) / T(2), lr, omlr), hx = lin_interp((fq + Fq[e - 1]) / T(2), lr, omlr),
+                hc = lin_interp((fq + Fq[e - WX]) / T(2), lr, omlr);
+        // fused: ρu = u*ρ (u2ρu!, VOFutil.jl:208-211) and straight back to u★ = ρu/ρ, rounding as the two passes would
+        const T ra = t_div(fused ? R[0] * ha : R[0], ha);
+        const T rx = t_div(fused ? R[NC] * hx : R[NC], hx);
+        const T rc = t_div(fused ? R[2 * NC] * hc : R[2 * NC], hc);
         usA[j][3] = dq ? AA : ra;  // Dirichlet planes of BC!
         usX[j][3] = dirX ? AXv : rx;
         usC[j][3] = dirC[j] ? ACv : rc;
@@ -381,16 +386,23 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
         }
         if (MOM) {
           const T* R = sR + ((k & 3) * 3) * NC + tid + j * NT;
-          const T* O = sO + ((k & 1) * 3) * NC + tid + j * NT;
+          const T* O = fused ? R : sO + ((k & 1) * 3) * NC + tid + j * NT;
           const T* Dk = sDil + (k & 1) * PLH;
           const T dNa = (!perA && k == 2) ? dilk[j] : dilm1[j];  // BCf! (Neumann) on ρ̄∂ⱼuⱼ along the sweep direction
+          T qA = R[0], qX = R[NC], qC = R[2 * NC];  // ρu before the sweep
+          if (fused) {  // u2ρu! + BC!(ρu,uBC): Dirichlet plane 2 of the normal component holds uBC
+            const T* Fm = sF + ((k - 1) & 7) * PLH;
+            qA = dpm ? AA : qA * lin_interp((fK[j] + Fm[e]) / T(2), lr, omlr);
+            qX = dirX ? AXv : qX * lin_interp((fK[j] + Fk[e - 1]) / T(2), lr, omlr);
+            qC = dirC[j] ? ACv : qC * lin_interp((fK[j] + Fk[e - WX]) / T(2), lr, omlr);
+          }
           // r = Φ[I] - Φ[I+δj] + uOld*ϕ(i,I,ρ̄∂ⱼuⱼ);  ρu += δt*r          flow.jl:223-231
           const T rA = (FloA[j] - FhiA) + O[0] * ((dilk[j] + dNa) / T(2));
           const T rX = (FloX[j] - FhiX) + O[NC] * ((dilk[j] + Dk[e - 1]) / T(2));
           const T rC = (FloC[j] - FhiC) + O[2 * NC] * ((dilk[j] + Dk[e - WX]) / T(2));
-          P.rhou_out[cA + lk] = R[0] + dt * rA;
-          P.rhou_out[lk] = R[NC] + dt * rX;
-          P.rhou_out[cC + lk] = R[2 * NC] + dt * rC;
+          P.rhou_out[cA + lk] = qA + dt * rA;
+          P.rhou_out[lk] = qX + dt * rX;
+          P.rhou_out[cC + lk] = qC + dt * rC;
         }
       }
       // I. roll the register pipeline

@@ -278,15 +278,28 @@ static int advect_vof_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* al, const
   return 0;
 }
 
+template <class T> static int u2rhou_t(ifadv_ctx* c, cudaStream_t st, T* out, const T* in, const T* f, double lr, bool to_rhou);
+template <class T> static int bcvec_t(ifadv_ctx* c, cudaStream_t st, T* a, const double* A, int saveexit, unsigned per);
+
+// f_src / fused: the fused entry (ifadv_u2rhou_advect_vof_rhouu).  In 3-D the first sweep reads f_src and forms
+// ρu = BC!(uOld*ρ(f̄)) on the fly; in 2-D the three reference calls are simply issued back to back.
 template <class T>
 static int advect_vof_rhouu_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* Phi, const T* u, const T* u0, double dt, int8_t* cbar, T* rhou,
                               T* r, T* rhouf, const T* uOld, const T* drho, double lr, int lim, int ns, const double* uBC, unsigned per,
-                              const int* dirO, ifadv_report* rep) {
+                              const int* dirO, ifadv_report* rep, const T* f_src = nullptr, int fused = 0) {
   const int D = c->D;
   c->g.per = per;
+  if (fused && (D == 2 || c->use_march == 0)) {
+    if (f_src && f_src != f) CU_CHECK(c, cudaMemcpyAsync(f, f_src, sizeof(T) * c->g.S, cudaMemcpyDeviceToDevice, st));
+    int rc0 = u2rhou_t<T>(c, st, rhou, uOld, f, lr, true);
+    if (rc0) return rc0;
+    if ((rc0 = bcvec_t<T>(c, st, rhou, uBC, 0, per))) return rc0;
+    f_src = nullptr;
+    fused = 0;
+  }
   red_init_kernel<<<1, 32, 0, st>>>(c->red_dev, 3);
   c->launches++;
-  T* fb[4] = {f, ff, (D == 3) ? Phi : f, f};        // f -> fᶠ -> Φ -> f
+  T* fb[4] = {(f_src && fused) ? const_cast<T*>(f_src) : f, ff, (D == 3) ? Phi : f, f};  // f -> fᶠ -> Φ -> f
   T* rb[4] = {rhou, r, (D == 3) ? rhouf : rhou, rhou};  // ρu -> r -> ρuf -> ρu
   for (int s = 0; s < D; ++s) {
     SweepCfg<T> q{};
@@ -294,6 +307,7 @@ static int advect_vof_rhouu_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* Phi
     q.rhou_in = rb[s]; q.rhou_out = rb[s + 1];
     q.u = u; q.u0 = u0; q.uOld = uOld; q.drho = drho; q.cbar = cbar; q.rhouf = nullptr;
     q.dt = dt; q.lr = lr; q.scheme = ns; q.lim = lim; q.first = (s == 0); q.j = dirO[s] - 1;
+    q.fused = (s == 0) ? fused : 0;
     for (int i = 0; i < 3; ++i) q.A[i] = (i < D) ? uBC[i] : 0.0;
     q.red = c->red_dev + 8 * s;
     int rc = launch_sweep<T, true>(c, st, q);
@@ -372,7 +386,7 @@ int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int dev
   for (auto& p : c->w) p = nullptr;
   c->pin_f = c->pin_u = c->pin_ru = nullptr;
   c->own_stream = nullptr;
-  c->prof_on = 0; c->prof_n = 0; c->prof_ev = nullptr;
+  c->prof_on = 0; c->prof_n = 0; c->prof_ev = nullptr; c->prof_tag = nullptr;
   {
     const char* e = getenv("IFADV_KERNEL");
     // default: register-marching (y,z sweeps) + plane-marching (x sweep); "march": plane-marching for all; "tile": v1
@@ -398,7 +412,7 @@ int ifadv_destroy(ifadv_ctx* c) {
   if (c->pin_u) cudaFreeHost(c->pin_u);
   if (c->pin_ru) cudaFreeHost(c->pin_ru);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
-  if (c->prof_ev) { for (int k = 0; k < 2 * IFADV_PROF_MAX; ++k) cudaEventDestroy(c->prof_ev[k]); delete[] c->prof_ev; }
+  if (c->prof_ev) { for (int k = 0; k < 2 * IFADV_PROF_MAX; ++k) cudaEventDestroy(c->prof_ev[k]); delete[] c->prof_ev; delete[] c->prof_tag; }
   delete c;
   return 0;
 }
@@ -407,6 +421,7 @@ int ifadv_profile(ifadv_ctx* c, int enable) {
   if (!c) return -2;
   if (enable && !c->prof_ev) {
     c->prof_ev = new cudaEvent_t[2 * IFADV_PROF_MAX];
+    c->prof_tag = new unsigned char[IFADV_PROF_MAX];
     for (int k = 0; k < 2 * IFADV_PROF_MAX; ++k) CU_CHECK(c, cudaEventCreate(&c->prof_ev[k]));
   }
   c->prof_on = enable ? 1 : 0;
@@ -415,15 +430,17 @@ int ifadv_profile(ifadv_ctx* c, int enable) {
 }
 int ifadv_profile_read(ifadv_ctx* c, double* total_ms, int64_t* launches) {
   if (!c || !total_ms || !launches) return -2;
-  double tot = 0.0;
+  double tot[2] = {0.0, 0.0};
+  int64_t cnt[2] = {0, 0};
   for (int k = 0; k < c->prof_n; ++k) {
     float ms = 0.f;
     CU_CHECK(c, cudaEventSynchronize(c->prof_ev[2 * k + 1]));
     CU_CHECK(c, cudaEventElapsedTime(&ms, c->prof_ev[2 * k], c->prof_ev[2 * k + 1]));
-    tot += ms;
+    tot[c->prof_tag[k] ? 1 : 0] += ms;
+    cnt[c->prof_tag[k] ? 1 : 0]++;
   }
-  *total_ms = tot;
-  *launches = c->prof_n;
+  total_ms[0] = tot[0]; total_ms[1] = tot[1];
+  launches[0] = cnt[0]; launches[1] = cnt[1];
   c->prof_n = 0;
   return 0;
 }
@@ -465,6 +482,25 @@ int ifadv_advect_vof_rhouu(ifadv_ctx* c, void* stream, void* f, void* ff, void* 
   return advect_vof_rhouu_t<double>(c, st, (double*)f, (double*)ff, (double*)Phi, (const double*)u, (const double*)u0, dt, cbar,
                                     (double*)rhou, (double*)r, (double*)rhouf, (const double*)uOld, (const double*)drho, lambda_rho, limiter,
                                     normal_scheme, uBC, perdir_mask, dirO, report);
+}
+
+int ifadv_u2rhou_advect_vof_rhouu(ifadv_ctx* c, void* stream, const void* f_src, void* f, void* ff, void* Phi, const void* u, const void* u0,
+                                  double dt, int8_t* cbar, void* rhou, void* r, void* rhouf, const void* uOld, const void* drho,
+                                  double lambda_rho, int limiter, int normal_scheme, const double uBC[3], unsigned perdir_mask,
+                                  const int dirO[3], ifadv_report* report) {
+  int rc = check_common(c, normal_scheme, dirO);
+  if (rc) return rc;
+  if (limiter < 0 || limiter > 10) return fail(c, -2, "invalid limiter");
+  if (!f_src || !f || !ff || !u || !u0 || !cbar || !rhou || !r || !uOld || !drho || !uBC || (c->D == 3 && (!Phi || !rhouf)))
+    return fail(c, -2, "null array");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->dtype == IFADV_F32)
+    return advect_vof_rhouu_t<float>(c, st, (float*)f, (float*)ff, (float*)Phi, (const float*)u, (const float*)u0, dt, cbar, (float*)rhou,
+                                     (float*)r, (float*)rhouf, (const float*)uOld, (const float*)drho, lambda_rho, limiter, normal_scheme,
+                                     uBC, perdir_mask, dirO, report, (const float*)f_src, 1);
+  return advect_vof_rhouu_t<double>(c, st, (double*)f, (double*)ff, (double*)Phi, (const double*)u, (const double*)u0, dt, cbar,
+                                    (double*)rhou, (double*)r, (double*)rhouf, (const double*)uOld, (const double*)drho, lambda_rho, limiter,
+                                    normal_scheme, uBC, perdir_mask, dirO, report, (const double*)f_src, 1);
 }
 
 int ifadv_u2rhou(ifadv_ctx* c, void* stream, void* rhou, const void* u, const void* f, double lr) {
@@ -607,22 +643,17 @@ int ifadv_mom_advect_step_host(ifadv_ctx* c, void* f_host, const void* u_host, v
   if (!pu) memcpy(c->pin_u, u_host, vb);
   CU_CHECK(c, cudaMemcpyAsync(f, pf ? f_host : c->pin_f, sb, cudaMemcpyHostToDevice, st));
   CU_CHECK(c, cudaMemcpyAsync(u, pu ? u_host : c->pin_u, vb, cudaMemcpyHostToDevice, st));
-  // copyto!(u⁰,u); copyto!(f⁰,f)                                           flow.jl:61
+  // copyto!(u⁰,u)                                                          flow.jl:61
   CU_CHECK(c, cudaMemcpyAsync(u0, u, vb, cudaMemcpyDeviceToDevice, st));
-  CU_CHECK(c, cudaMemcpyAsync(f0, f, sb, cudaMemcpyDeviceToDevice, st));
   int rc;
-  // predictor                                                             flow.jl:69-70
-  if ((rc = ifadv_u2rhou(c, st, ru, u0, f0, lambda_rho))) return rc;
-  if ((rc = ifadv_bc_vec(c, st, ru, uBC, 0, perdir_mask))) return rc;
-  if ((rc = ifadv_advect_vof_rhouu(c, st, f0, ff, nullptr, nullptr, u0, u, dt, cbar, ru, r, Phi, ruf, nullptr, u, nullptr, drho, lambda_rho,
-                                   limiter, normal_scheme, uBC, perdir_mask, 0, dirO, nullptr)) < 0) return rc;
+  // predictor: copyto!(f⁰,f); u2ρu!(ρu,u⁰,f⁰); BC!; advectfq!(f⁰; u⁰,u,uOld=u)     flow.jl:61,69-70 (fused entry)
+  if ((rc = ifadv_u2rhou_advect_vof_rhouu(c, st, f, f0, ff, Phi, u0, u, dt, cbar, ru, r, ruf, u, drho, lambda_rho, limiter, normal_scheme,
+                                          uBC, perdir_mask, dirO, nullptr)) < 0) return rc;
   if ((rc = ifadv_axpby(c, st, f0, 0.5, f0, 0.5, f))) return rc;  // flow.jl:74
-  // corrector                                                             flow.jl:89-92
+  // corrector: copyto!(f⁰,f); u2ρu!(ρu,u⁰,f); BC!; advectfq!(f; u,u,uOld=u⁰)         flow.jl:89-92
   CU_CHECK(c, cudaMemcpyAsync(f0, f, sb, cudaMemcpyDeviceToDevice, st));
-  if ((rc = ifadv_u2rhou(c, st, ru, u0, f, lambda_rho))) return rc;
-  if ((rc = ifadv_bc_vec(c, st, ru, uBC, 0, perdir_mask))) return rc;
-  rc = ifadv_advect_vof_rhouu(c, st, f, ff, nullptr, nullptr, u, u, dt, cbar, ru, r, Phi, ruf, nullptr, u0, nullptr, drho, lambda_rho, limiter,
-                              normal_scheme, uBC, perdir_mask, 0, dirO, report);
+  rc = ifadv_u2rhou_advect_vof_rhouu(c, st, f, f, ff, Phi, u, u, dt, cbar, ru, r, ruf, u0, drho, lambda_rho, limiter, normal_scheme, uBC,
+                                     perdir_mask, dirO, report);
   if (rc < 0) return rc;
   CU_CHECK(c, cudaMemcpyAsync(pf ? f_host : c->pin_f, f, sb, cudaMemcpyDeviceToHost, st));
   CU_CHECK(c, cudaMemcpyAsync(pr ? rhou_host : c->pin_ru, ru, vb, cudaMemcpyDeviceToHost, st));

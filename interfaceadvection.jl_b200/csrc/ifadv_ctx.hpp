@@ -30,6 +30,7 @@ struct ifadv_ctx {
   int use_march;  // 1: register-marching (y,z) + plane-marching (x) kernels (default); 2: plane-marching only; 0: v1 tile kernel
   int prof_on, prof_n;
   cudaEvent_t* prof_ev;  // 2 * IFADV_PROF_MAX events
+  unsigned char* prof_tag;  // per launch: 1 = fused first sweep (10s+1 B/cell), 0 = standard sweep (13s+1 B/cell)
 };
 #define IFADV_PROF_MAX 4096
 
@@ -51,6 +52,7 @@ template <class T> struct SweepCfg {
   double dt, lr;
   double A[3];
   int scheme, lim, first, j;  // j 0-based
+  int fused;                  // see SweepP::fused
   unsigned long long* red;
 };
 

@@ -100,7 +100,7 @@ template <class T, int J, int PL, int SA, int SB> struct SBox {
   }
 };
 
-template <class T, int J, int TA, int TB, bool MOM, int NT, int MINB>
+template <class T, int J, int TA, int TB, bool MOM, bool FUSED, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, const int chunk) {
   using TL = MTile<J, TA, TB, NT>;
   constexpr bool AX = TL::AX;
@@ -212,9 +212,10 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
     const unsigned dU = sb + (unsigned)((sU - sm) + s2 * PL) * SZ;
     const unsigned dU0 = sb + (unsigned)((sU0 - sm) + s2 * PL) * SZ;
     const unsigned dR = sb + (unsigned)((sRU - sm) + s2 * 3 * PL) * SZ;
-    const T* ra = P.rhou_in + cA + pm;
-    const T* rb = P.rhou_in + cB + pm;
-    const T* rc = P.rhou_in + cC + po;
+    const T* rsrc = (MOM && FUSED) ? P.uOld : P.rhou_in;  // fused sweep 1: the ρu planes carry uOld
+    const T* ra = rsrc + cA + pm;
+    const T* rb = rsrc + cB + pm;
+    const T* rc = rsrc + cC + po;
 #pragma unroll
     for (int t = 0; t < TR; ++t) {
       const unsigned e4 = ent(t) * SZ;
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
         cp_async_s(dU + e4, up + gom[t]);
         cp_async_s(dU0 + e4, u0p + gom[t]);
       }
-      if (MOM && full && (flg[t] & MF_CELL)) {  // uOld of the next plane: pull the lines into L2/L1 ahead of the update stage
+      if (MOM && full && !FUSED && (flg[t] & MF_CELL)) {  // uOld of the next plane: pull the lines into L2/L1 ahead of the update stage
         const T* uo = P.uOld + (long long)(vc - 1) * sC + gmm[t];
         asm volatile("prefetch.global.L1 [%0];" ::"l"(uo + cA));
         asm volatile("prefetch.global.L1 [%0];" ::"l"(uo + cB));
@@ -318,9 +319,12 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
       const unsigned fl = flg[t];
       if (fl & MF_US) {
         const T fc = cF[e];
-        const T ra = t_div(cR[e], lin_interp((fc + cF[e - SA]) / T(2), lr, omlr));
-        const T rb = t_div(cR[PL + e], lin_interp((fc + cF[e - SB]) / T(2), lr, omlr));
-        const T rc = t_div(cR[2 * PL + e], lin_interp((fc + pF[e]) / T(2), lr, omlr));
+        const T ha = lin_interp((fc + cF[e - SA]) / T(2), lr, omlr), hb = lin_interp((fc + cF[e - SB]) / T(2), lr, omlr),
+                hc = lin_interp((fc + pF[e]) / T(2), lr, omlr);
+        constexpr bool fu = MOM && FUSED;  // ρu = u*ρ (u2ρu!) formed on the fly, then u★ = ρu/ρ
+        const T ra = t_div(fu ? cR[e] * ha : cR[e], ha);
+        const T rb = t_div(fu ? cR[PL + e] * hb : cR[PL + e], hb);
+        const T rc = t_div(fu ? cR[2 * PL + e] * hc : cR[2 * PL + e], hc);
         sUs[e] = (fl & MF_DIRA) ? AA : ra;  // Dirichlet planes of BC!
         sUs[PL + e] = (fl & MF_DIRB) ? AB : rb;
         sUs[2 * PL + e] = dirC ? AC : rc;
@@ -423,15 +427,27 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
           const T dK = sDil[s2 * PL + e];
           const T* cR = sRU + (s2 * 3) * PL;
           const long long co[3] = {cA, cB, cC};
+          constexpr bool fu = MOM && FUSED;
+          const T* pF = sF + ((vc - 1) & 3) * PL;
+          const bool dirCc = !perC && (vc == 2 || vc == nC);
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
             T dN;
             if (r == 0) dN = sDil[s2 * PL + e - SA];
             else if (r == 1) dN = sDil[s2 * PL + e - SB];
             else dN = sDil[(s2 ^ 1) * PL + e];
+            const T src = cR[r * PL + e];  // ρu before the sweep, or uOld in the fused first sweep
+            T q = src, uo;
+            if (fu) {  // u2ρu! + BC!(ρu,uBC): Dirichlet plane 2 of the normal component holds uBC
+              const T fn2 = (r == 0) ? cF[e - SA] : ((r == 1) ? cF[e - SB] : pF[e]);
+              const bool dir = (r == 0) ? ((fl & MF_LVAR) != 0) : ((r == 1) ? ((fl & MF_DIRB) != 0) : dirCc);
+              const T Ar = (r == 0) ? AA : ((r == 1) ? AB : AC);
+              q = dir ? Ar : src * lin_interp((fK + fn2) / T(2), lr, omlr);
+              uo = src;
+            } else uo = __ldg(P.uOld + co[r] + lk);
             // r = Φ[I] - Φ[I+δj] + uOld*ϕ(i,I,ρ̄∂ⱼuⱼ);  ρu += δt*r          flow.jl:223-231
-            const T rr = (sFl[r * PL + e] - sFl[r * PL + e + SA]) + __ldg(P.uOld + co[r] + lk) * ((dK + dN) / T(2));
-            P.rhou_out[co[r] + lk] = cR[r * PL + e] + dt * rr;
+            const T rr = (sFl[r * PL + e] - sFl[r * PL + e + SA]) + uo * ((dK + dN) / T(2));
+            P.rhou_out[co[r] + lk] = q + dt * rr;
           }
         }
       }

@@ -50,6 +50,7 @@ template <class T> struct SweepP {
   long long coff[3];  // component offsets d*S
   Geo g;
   int scheme, lim, first;
+  int fused;  // sweep 1 of the fused entry: ρu_in = BC!(uOld*ρ(f̄)) is formed on the fly (u2ρu! + BC! folded in)
   unsigned long long* red;  // [0] max key, [1] min key, [2] argmax pack, [3] argmin pack, [4] nan count
 };
 

@@ -34,7 +34,7 @@ static int launch_sweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
   if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
   kern<<<grid, NT, smem, st>>>(P);
-  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_n++; }
+  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_tag[c->prof_n] = (unsigned char)(q.fused ? 1 : 0); c->prof_n++; }
   c->launches++;
   CU_CHECK(c, cudaGetLastError());
   return 0;
@@ -49,19 +49,19 @@ template <class T> static void fill_params(ifadv_ctx* c, const SweepCfg<T>& q, i
   P.dt = (T)q.dt; P.hdt = P.dt / T(2); P.idt = T(1) / P.dt; P.lr = (T)q.lr; P.omlr = T(1) - P.lr;
   P.tol = T(10) * std::numeric_limits<T>::epsilon(); P.onemtol = T(1) - P.tol;
   for (int i = 0; i < 3; ++i) P.A[i] = (T)q.A[i];
-  P.g = c->g; P.scheme = q.scheme; P.lim = q.lim; P.first = q.first; P.red = q.red;
+  P.g = c->g; P.scheme = q.scheme; P.lim = q.lim; P.first = q.first; P.red = q.red; P.fused = q.fused;
   for (int i = 0; i < 3; ++i) P.coff[i] = (long long)i * c->g.S;
 }
 
 // v2: plane-marching kernel (3-D only)
-template <class T, int J, int TA, int TB, bool MOM, int MINB>
+template <class T, int J, int TA, int TB, bool MOM, bool FUSED, int MINB>
 static int launch_march_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   constexpr int NT = 256;
   using TL = MTile<J, TA, TB, NT>;
   SweepP<T> P;
   fill_params<T>(c, q, J, P);
   const size_t smem = TL::template smem_bytes<T>(MOM);
-  auto kern = march_kernel<T, J, TA, TB, MOM, NT, MINB>;
+  auto kern = march_kernel<T, J, TA, TB, MOM, FUSED, NT, MINB>;
   static bool attr_set = false;
   if (!attr_set) {
     CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -79,21 +79,21 @@ static int launch_march_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
   if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
   kern<<<grid, NT, smem, st>>>(P, chunk);
-  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_n++; }
+  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_tag[c->prof_n] = (unsigned char)(q.fused ? 1 : 0); c->prof_n++; }
   c->launches++;
   CU_CHECK(c, cudaGetLastError());
   return 0;
 }
 
 // v3: register-marching kernel for sweeps along y / z (3-D only)
-template <class T, int J, int CPT, bool MOM, int MINB>
+template <class T, int J, int CPT, bool MOM, bool FUSED, int MINB>
 static int launch_along_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   constexpr int NT = 256, TC = (NT / 32) * CPT;
   using TL = ATile<TC>;
   SweepP<T> P;
   fill_params<T>(c, q, J, P);
   const size_t smem = TL::template smem_bytes<T>(MOM);
-  auto kern = along_kernel<T, J, CPT, MOM, NT, MINB>;
+  auto kern = along_kernel<T, J, CPT, MOM, FUSED, NT, MINB>;
   static bool attr_set = false;
   if (!attr_set) {
     CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -108,7 +108,7 @@ static int launch_along_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
   if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
   kern<<<grid, NT, smem, st>>>(P, chunk);
-  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_n++; }
+  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_tag[c->prof_n] = (unsigned char)(q.fused ? 1 : 0); c->prof_n++; }
   c->launches++;
   CU_CHECK(c, cudaGetLastError());
   return 0;
@@ -119,17 +119,26 @@ template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStrea
     if (c->use_march == 1 && q.j != 0) {
       // Float32: two columns per thread (2 CTAs/SM, twice the ILP, half the per-plane overhead); Float64: one
       constexpr int CP = (sizeof(T) == 4) ? 2 : 1;
-      if (q.j == 1) return launch_along_t<T, 1, CP, MOM, 2>(c, st, q);
-      return launch_along_t<T, 2, CP, MOM, 2>(c, st, q);
+      if (MOM && q.fused) {
+        if (q.j == 1) return launch_along_t<T, 1, CP, MOM, MOM, 2>(c, st, q);
+        return launch_along_t<T, 2, CP, MOM, MOM, 2>(c, st, q);
+      }
+      if (q.j == 1) return launch_along_t<T, 1, CP, MOM, false, 2>(c, st, q);
+      return launch_along_t<T, 2, CP, MOM, false, 2>(c, st, q);
     }
     if (c->use_march) {
       // tile shapes sized so that 25 shared planes leave 3 (f32) / 2-3 (f64) CTAs per SM
       constexpr int TO = (sizeof(T) == 4) ? 16 : 8;
       constexpr int TBX = (sizeof(T) == 4) ? 16 : 8;
       constexpr int MB = 2;
-      if (q.j == 0) return launch_march_t<T, 0, 32, TBX, MOM, MB>(c, st, q);
-      if (q.j == 1) return launch_march_t<T, 1, TO, 32, MOM, MB>(c, st, q);
-      return launch_march_t<T, 2, TO, 32, MOM, MB>(c, st, q);
+      if (MOM && q.fused) {
+        if (q.j == 0) return launch_march_t<T, 0, 32, TBX, MOM, MOM, MB>(c, st, q);
+        if (q.j == 1) return launch_march_t<T, 1, TO, 32, MOM, MOM, MB>(c, st, q);
+        return launch_march_t<T, 2, TO, 32, MOM, MOM, MB>(c, st, q);
+      }
+      if (q.j == 0) return launch_march_t<T, 0, 32, TBX, MOM, false, MB>(c, st, q);
+      if (q.j == 1) return launch_march_t<T, 1, TO, 32, MOM, false, MB>(c, st, q);
+      return launch_march_t<T, 2, TO, 32, MOM, false, MB>(c, st, q);
     }
   }
   if constexpr (D == 2) {

@@ -339,3 +339,31 @@ def test_full_size_properties_dambreak(ia):
     assert bool(torch.isfinite(sim.intf.rhou[1:-1, 1:-1, 1:-1]).all())
     del sim
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("N,kind,perdir,uBC", [((40, 24, 20), "C3", (), (0, 0, 0)), ((32, 24, 20), "C4", (1, 2, 3), (0, 0, 0)),
+                                               ((36, 20, 18), "C2", (2,), (0.1, 0.0, 0.0)), ((24, 16), "C1", (), (0, 0))])
+def test_fused_entry_equals_separate_calls(ia, T, N, kind, perdir, uBC):
+    """ifadv_u2rhou_advect_vof_rhouu == f.=f_src; u2ρu!; BC!; advectVOFρuu!  (bit-identical in Float64, <= tol in Float32),
+    and both match the oracle's transport half of MPFMomStep!."""
+    D = len(N)
+    TT = getattr(torch, np.dtype(T).name)
+    st = make_state(N, kind, T, perdir=perdir, uBC=uBC, scale_u=0.6)
+    f_o = st["f"].copy(order="F")
+    dirO = dirO_for(0, D)
+    ru_o = oracle_mom_advect_step(st, f_o, st["u"], 1.0, dirO)
+    out = {}
+    for fused in (False, True):
+        flow = ia.Flow(st["N"], st["uBC"], T=TT, dt=1.0, perdir=st["perdir"])
+        intf = ia.cVOF(st["N"], T=TT, lam_rho=st["lam_rho"], perdir=st["perdir"])
+        flow.u.copy_(ia.from_numpy(st["u"])); intf.f.copy_(ia.from_numpy(st["f"]))
+        ia.mom_advect_step(flow, intf, 1.0, fused=fused)
+        out[fused] = (ia.to_numpy(intf.f), ia.to_numpy(intf.rhou), ia.to_numpy(intf.f0))
+    for fused in (False, True):
+        assert np.abs(out[fused][0] - f_o).max() <= TOL[T]
+        assert np.abs(inside(out[fused][1], D) - inside(ru_o, D)).max() <= TOL[T] * max(1.0, np.abs(ru_o).max())
+    if T == np.float64:
+        assert np.array_equal(out[True][0], out[False][0])
+        assert np.array_equal(inside(out[True][1], D), inside(out[False][1], D))
+        assert np.array_equal(out[True][2], out[False][2])
