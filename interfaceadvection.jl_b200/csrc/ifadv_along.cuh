@@ -242,8 +242,8 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
       if (MOM) {
         const T* R = sR + ((q & 3) * 3) * NC + tid + j * NT;
         const T fq = Fq[e];
-        const T ha = lin_interp((fq + Fp[e]) / T(2), lr, omlr), hx = lin_interp((fq + Fq[e - 1]) / T(2), lr, omlr),
-                hc = lin_interp((fq + Fq[e - WX]) / T(2), lr, omlr);
+        const T ha = rho_face(fq, Fp[e], lr, omlr), hx = rho_face(fq, Fq[e - 1], lr, omlr),
+                hc = rho_face(fq, Fq[e - WX], lr, omlr);
         // fused: ρu = u*ρ (u2ρu!, VOFutil.jl:208-211) and straight back to u★ = ρu/ρ, rounding as the two passes would
         const T ra = t_div(fused ? R[0] * ha : R[0], ha);
         const T rx = t_div(fused ? R[NC] * hx : R[NC], hx);
@@ -392,9 +392,9 @@ __global__ void __launch_bounds__(NT, MINB) along_kernel(const SweepP<T> P, cons
           T qA = R[0], qX = R[NC], qC = R[2 * NC];  // ρu before the sweep
           if (fused) {  // u2ρu! + BC!(ρu,uBC): Dirichlet plane 2 of the normal component holds uBC
             const T* Fm = sF + ((k - 1) & 7) * PLH;
-            qA = dpm ? AA : qA * lin_interp((fK[j] + Fm[e]) / T(2), lr, omlr);
-            qX = dirX ? AXv : qX * lin_interp((fK[j] + Fk[e - 1]) / T(2), lr, omlr);
-            qC = dirC[j] ? ACv : qC * lin_interp((fK[j] + Fk[e - WX]) / T(2), lr, omlr);
+            qA = dpm ? AA : qA * rho_face(fK[j], Fm[e], lr, omlr);
+            qX = dirX ? AXv : qX * rho_face(fK[j], Fk[e - 1], lr, omlr);
+            qC = dirC[j] ? ACv : qC * rho_face(fK[j], Fk[e - WX], lr, omlr);
           }
           // r = Φ[I] - Φ[I+δj] + uOld*ϕ(i,I,ρ̄∂ⱼuⱼ);  ρu += δt*r          flow.jl:223-231
           const T rA = (FloA[j] - FhiA) + O[0] * ((dilk[j] + dNa) / T(2));

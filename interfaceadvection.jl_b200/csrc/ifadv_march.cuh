@@ -319,8 +319,8 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
       const unsigned fl = flg[t];
       if (fl & MF_US) {
         const T fc = cF[e];
-        const T ha = lin_interp((fc + cF[e - SA]) / T(2), lr, omlr), hb = lin_interp((fc + cF[e - SB]) / T(2), lr, omlr),
-                hc = lin_interp((fc + pF[e]) / T(2), lr, omlr);
+        const T ha = rho_face(fc, cF[e - SA], lr, omlr), hb = rho_face(fc, cF[e - SB], lr, omlr),
+                hc = rho_face(fc, pF[e], lr, omlr);
         constexpr bool fu = MOM && FUSED;  // ρu = u*ρ (u2ρu!) formed on the fly, then u★ = ρu/ρ
         const T ra = t_div(fu ? cR[e] * ha : cR[e], ha);
         const T rb = t_div(fu ? cR[PL + e] * hb : cR[PL + e], hb);
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(NT, MINB) march_kernel(const SweepP<T> P, cons
               const T fn2 = (r == 0) ? cF[e - SA] : ((r == 1) ? cF[e - SB] : pF[e]);
               const bool dir = (r == 0) ? ((fl & MF_LVAR) != 0) : ((r == 1) ? ((fl & MF_DIRB) != 0) : dirCc);
               const T Ar = (r == 0) ? AA : ((r == 1) ? AB : AC);
-              q = dir ? Ar : src * lin_interp((fK + fn2) / T(2), lr, omlr);
+              q = dir ? Ar : src * rho_face(fK, fn2, lr, omlr);
               uo = src;
             } else uo = __ldg(P.uOld + co[r] + lk);
             // r = Φ[I] - Φ[I+δj] + uOld*ϕ(i,I,ρ̄∂ⱼuⱼ);  ρu += δt*r          flow.jl:223-231

@@ -48,6 +48,14 @@ IFADV_DI float t_div6(float a) { return a / 6.0f; }
 template <class T> IFADV_DI bool fullorempty(T fc) { return fc == T(0) || fc == T(1); }      // VOFutil.jl:151
 template <class T> IFADV_DI T lin_interp(T f, T lam, T oml) { return lam + oml * f; }        // VOFutil.jl:166, oml = 1-λ
 
+// ρ at a face: linInterpProp(ϕ(d,I,f),λρ) = λ + (1-λ)*((a+b)/2)   (VOFutil.jl:176).  Fast Float32 folds the halving into the FMA.
+template <class T> IFADV_DI T rho_face(T a, T b, T lam, T oml) {
+#ifdef IFADV_FAST_F32
+  if (sizeof(T) == 4) return fmaf((float)oml * 0.5f, (float)(a + b), (float)lam);
+#endif
+  return lam + oml * ((a + b) / T(2));
+}
+
 // ---- PLIC: src/PLIC.jl --------------------------------------------------------------------------------
 template <class T> IFADV_DI void sort2(T& a, T& b) { if (!(a < b)) t_swap(a, b); }           // :178
 template <class T> IFADV_DI void sort3(T& a, T& b, T& c) {                                   // :186-191
