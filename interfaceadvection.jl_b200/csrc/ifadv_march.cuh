@@ -79,8 +79,8 @@ template <class T> IFADV_DI void cp_async_s(unsigned saddr, const T* gsrc) {
   if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(saddr), "l"(gsrc));
   else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(gsrc));
 }
-// branch-free index maps for plane indices that stay within one period of the box (chunks do)
-IFADV_DI int wrap1(int v, int n) { const int m = n - 2; v += (v < 2) ? m : 0; v -= (v > n - 1) ? m : 0; return v; }
+// index maps for (block-uniform) plane indices; the warm-up of a chunk may reach several periods below a tiny periodic box
+IFADV_DI int wrap1(int v, int n) { return wrapc(v, n); }
 IFADV_DI int map1(int v, int n, bool per) { return per ? wrap1(v, n) : min(max(v, 2), n - 1); }
 IFADV_DI int own1(int v, int n, bool per) { return per ? wrap1(v, n) : min(max(v, 1), n); }
 

@@ -24,10 +24,11 @@ static int launch_sweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   P.g = c->g; P.scheme = q.scheme; P.lim = q.lim; P.first = q.first; P.red = q.red;
   const size_t smem = TL::template smem_bytes<T>(MOM);
   auto kern = sweep_kernel<T, D, J, TX, TY, TZ, MOM, NT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // per device (one context per device): opt in to the large dynamic shared-memory carve-out once
+  static unsigned long long attr_devs = 0ull;
+  if (!((attr_devs >> (c->device & 63)) & 1ull)) {
     CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_devs |= 1ull << (c->device & 63);
   }
   dim3 grid((unsigned)((c->g.n[0] - 2 + TL::T0 - 1) / TL::T0), (unsigned)((c->g.n[1] - 2 + TL::T1 - 1) / TL::T1),
             (unsigned)(D == 3 ? (c->g.n[2] - 2 + TL::T2 - 1) / TL::T2 : 1));
@@ -62,10 +63,11 @@ static int launch_march_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   fill_params<T>(c, q, J, P);
   const size_t smem = TL::template smem_bytes<T>(MOM);
   auto kern = march_kernel<T, J, TA, TB, MOM, FUSED, NT, MINB>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // per device (one context per device): opt in to the large dynamic shared-memory carve-out once
+  static unsigned long long attr_devs = 0ull;
+  if (!((attr_devs >> (c->device & 63)) & 1ull)) {
     CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_devs |= 1ull << (c->device & 63);
   }
   constexpr int DB = (J == 0) ? 1 : 0, DC = (J == 2) ? 1 : 2;
   const int nx = c->g.n[0] - 2, no = c->g.n[(J == 2) ? 2 : 1] - 2, nc = c->g.n[DC] - 2;
@@ -94,10 +96,11 @@ static int launch_along_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   fill_params<T>(c, q, J, P);
   const size_t smem = TL::template smem_bytes<T>(MOM);
   auto kern = along_kernel<T, J, CPT, MOM, FUSED, NT, MINB>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // per device (one context per device): opt in to the large dynamic shared-memory carve-out once
+  static unsigned long long attr_devs = 0ull;
+  if (!((attr_devs >> (c->device & 63)) & 1ull)) {
     CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_devs |= 1ull << (c->device & 63);
   }
   constexpr int DCC = (J == 1) ? 2 : 1;
   const int nx = c->g.n[0] - 2, ncc = c->g.n[DCC] - 2, na = c->g.n[J] - 2;

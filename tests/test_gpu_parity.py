@@ -367,3 +367,26 @@ def test_fused_entry_equals_separate_calls(ia, T, N, kind, perdir, uBC):
         assert np.array_equal(out[True][0], out[False][0])
         assert np.array_equal(inside(out[True][1], D), inside(out[False][1], D))
         assert np.array_equal(out[True][2], out[False][2])
+
+
+@pytest.mark.parametrize("N,perdir", [((6, 5, 4), (1, 2, 3)), ((5, 4, 6), ()), ((33, 3, 3), (1,)), ((4, 4), (1, 2)), ((3, 7), ())])
+def test_tiny_and_ragged_grids(ia, N, perdir):
+    """Edge cases: grids smaller than a tile / a chunk warm-up / a periodic stencil reach, odd extents."""
+    T = np.float64
+    D = len(N)
+    rng = np.random.default_rng(20261017)
+    Ng = tuple(n + 2 for n in N)
+    f = np.asfortranarray(np.clip(rng.random(Ng) * 1.6 - 0.3, 0, 1)); O.BCf(f, perdir)
+    u = np.asfortranarray(rng.normal(size=Ng + (D,)) * 0.08); O.BC(u, (0,) * D, False, perdir)
+    st = dict(N=N, D=D, Ng=Ng, dtype=T, perdir=tuple(perdir), uBC=(0.0,) * D, f=f, u=u, lam_rho=0.01)
+    f_o = f.copy(order="F")
+    dirO = dirO_for(1, D)
+    ru_o = oracle_mom_advect_step(st, f_o, u, 1.0, dirO)
+    TT = torch.float64
+    flow = ia.Flow(N, st["uBC"], T=TT, dt=1.0, perdir=perdir)
+    flow.dt.append(1.0)
+    intf = ia.cVOF(N, T=TT, lam_rho=0.01, perdir=perdir)
+    flow.u.copy_(ia.from_numpy(u)); intf.f.copy_(ia.from_numpy(f))
+    ia.mom_advect_step(flow, intf, 1.0)
+    assert np.abs(ia.to_numpy(intf.f) - f_o).max() <= 1e-12
+    assert np.abs(inside(ia.to_numpy(intf.rhou), D) - inside(ru_o, D)).max() <= 1e-12
