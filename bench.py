@@ -276,6 +276,7 @@ def run_b200(args):
     for c in runner.contexts:
         (a, b), (a1, b1) = c.profile_read()
         kms += a; kn += b; fms += a1; fn_ += b1
+        per_dir = c.profile_read_dirs()
         c.profile(False)
     launches = sum(c.launches for c in runner.contexts) - l0
     if dist is not None:
@@ -313,6 +314,7 @@ def run_b200(args):
                 "traffic": traffic, "kernel": "ifadv::along_kernel / ifadv::march_kernel (fused VOF+CMOM directional sweep, standard 13s+1 B/cell form)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_launch, "avg_launch_ms": avg_ms, "launches_timed": kn,
                 "sweep_share_of_step": ((kms + fms) / ms) if ms else None, "fused_first_sweep": fused_info,
+                "ms_per_launch_by_direction": per_dir,
                 "step_frac_of_roofline": (algorithmic_bytes_per_cell_step(D, s) * cells_gpu / (ms / args.steps * 1e-3) / 1e9) / peak}
 
     # ---- e2e: the reference-facing C-ABI call with HOST buffers (H2D/D2H inside the timed region) ----

@@ -77,6 +77,9 @@ const char* ifadv_version(void);
  * sweeps of ifadv_u2rhou_advect_vof_rhouu (10s+1 B/cell); both arrays have 2 entries -- and resets the pool. */
 int ifadv_profile(ifadv_ctx* ctx, int enable);
 int ifadv_profile_read(ifadv_ctx* ctx, double* total_ms, int64_t* launches);
+/* per sweep direction, accumulated by the ifadv_profile_read calls since the last call: 6 entries, index 2*j + fused
+ * (j = 0-based sweep direction); resets the accumulators. */
+int ifadv_profile_read_dirs(ifadv_ctx* ctx, double* total_ms, int64_t* launches);
 
 /* ---- the hot path --------------------------------------------------------------------------------------- */
 /* advectVOF!(f,fᶠ,α,n̂,u,u⁰,Δt,c̄,ρuf,λρ,normalScheme; perdir,dirO)            src/advection.jl:34-78

@@ -42,6 +42,7 @@ def lib():
         L.ifadv_launch_count.argtypes = [vp]
         L.ifadv_profile.argtypes = [vp, i32]
         L.ifadv_profile_read.argtypes = [vp, dblp, i64p]
+        L.ifadv_profile_read_dirs.argtypes = [vp, dblp, i64p]
         L.ifadv_create.argtypes = [C.POINTER(vp), i32, i64p, i32, i32]
         L.ifadv_destroy.argtypes = [vp]
         L.ifadv_advect_vof.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, dbl, vp, vp, dbl, i32, u32, i32p, i32, rep]
@@ -123,6 +124,17 @@ class Context:
         ms, n = (C.c_double * 2)(), (C.c_int64 * 2)()
         self._chk(lib().ifadv_profile_read(self._h, ms, n))
         return (ms[0], int(n[0])), (ms[1], int(n[1]))
+
+    def profile_read_dirs(self):
+        """-> {"x": ms/launch, "x_fused": ..} accumulated by the profile_read calls since the last call"""
+        ms, n = (C.c_double * 6)(), (C.c_int64 * 6)()
+        self._chk(lib().ifadv_profile_read_dirs(self._h, ms, n))
+        out = {}
+        for j, nm in enumerate("xyz"):
+            for fu in (0, 1):
+                if n[2 * j + fu]:
+                    out[nm + ("_fused_first" if fu else "")] = ms[2 * j + fu] / n[2 * j + fu]
+        return out
 
     def advect_vof(self, stream, f, ff, alpha, nhat, u, u0, dt, cbar, rhouf, lam_rho, scheme, perdir, dirO, flags=0, report=None):
         r = C.byref(report) if report is not None else None

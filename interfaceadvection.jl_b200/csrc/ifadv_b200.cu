@@ -387,10 +387,12 @@ int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int dev
   c->pin_f = c->pin_u = c->pin_ru = nullptr;
   c->own_stream = nullptr;
   c->prof_on = 0; c->prof_n = 0; c->prof_ev = nullptr; c->prof_tag = nullptr;
+  for (int k = 0; k < 8; ++k) { c->prof_dir_ms[k] = 0.0; c->prof_dir_n[k] = 0; }
   {
     const char* e = getenv("IFADV_KERNEL");
     // default: register-marching (y,z sweeps) + plane-marching (x sweep); "march": plane-marching for all; "tile": v1
     c->use_march = (e && std::string(e) == "tile") ? 0 : ((e && std::string(e) == "march") ? 2 : 1);
+    c->use_along2 = (e && std::string(e) == "along1") ? 0 : 1;  // "along1": the first register-marching kernel for y/z sweeps
   }
   if (cudaMalloc(&c->red_dev, sizeof(unsigned long long) * 24) != cudaSuccess ||
       cudaMallocHost(&c->red_host, sizeof(unsigned long long) * 24) != cudaSuccess ||
@@ -436,12 +438,19 @@ int ifadv_profile_read(ifadv_ctx* c, double* total_ms, int64_t* launches) {
     float ms = 0.f;
     CU_CHECK(c, cudaEventSynchronize(c->prof_ev[2 * k + 1]));
     CU_CHECK(c, cudaEventElapsedTime(&ms, c->prof_ev[2 * k], c->prof_ev[2 * k + 1]));
-    tot[c->prof_tag[k] ? 1 : 0] += ms;
-    cnt[c->prof_tag[k] ? 1 : 0]++;
+    tot[(c->prof_tag[k] & 1) ? 1 : 0] += ms;
+    cnt[(c->prof_tag[k] & 1) ? 1 : 0]++;
+    c->prof_dir_ms[(c->prof_tag[k] >> 1) & 7] += ms;
+    c->prof_dir_n[(c->prof_tag[k] >> 1) & 7]++;
   }
   total_ms[0] = tot[0]; total_ms[1] = tot[1];
   launches[0] = cnt[0]; launches[1] = cnt[1];
   c->prof_n = 0;
+  return 0;
+}
+int ifadv_profile_read_dirs(ifadv_ctx* c, double* total_ms, int64_t* launches) {
+  if (!c || !total_ms || !launches) return -2;
+  for (int k = 0; k < 6; ++k) { total_ms[k] = c->prof_dir_ms[k]; launches[k] = c->prof_dir_n[k]; c->prof_dir_ms[k] = 0.0; c->prof_dir_n[k] = 0; }
   return 0;
 }
 

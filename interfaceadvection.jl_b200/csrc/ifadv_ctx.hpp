@@ -28,9 +28,12 @@ struct ifadv_ctx {
   cudaStream_t own_stream;
   // optional per-launch CUDA-event timing of the fused sweep (ifadv_profile)
   int use_march;  // 1: register-marching (y,z) + plane-marching (x) kernels (default); 2: plane-marching only; 0: v1 tile kernel
+  int use_along2;  // 1 (default): lean register-marching kernel ifadv_along2.cuh for y/z sweeps; 0: ifadv_along.cuh
   int prof_on, prof_n;
   cudaEvent_t* prof_ev;  // 2 * IFADV_PROF_MAX events
-  unsigned char* prof_tag;  // per launch: 1 = fused first sweep (10s+1 B/cell), 0 = standard sweep (13s+1 B/cell)
+  unsigned char* prof_tag;  // per launch: bit 0 = fused first sweep (10s+1 B/cell) / standard sweep (13s+1 B/cell); bits 1.. = 2*j + fused
+  double prof_dir_ms[8];    // accumulated by ifadv_profile_read: index 2*j + fused
+  int64_t prof_dir_n[8];
 };
 #define IFADV_PROF_MAX 4096
 

@@ -161,8 +161,7 @@ template <class T> IFADV_DI T sweby(T u, T c, T d, T gam) {
   T m2 = t_min(s * (c - u), (s * gam) * (d - c));
   return c + (s * t_max(T(0), t_max(m1, m2))) / T(2);
 }
-template <class T> IFADV_DI T limiter(int lam, T u, T c, T d) {
-  if (lam == 2) return median3(t_div6(T(7) * c + d - T(2) * u), c, median3(T(2) * c - u, c, d));  // Koren, the default: no jump table
+template <class T> __device__ __noinline__ T limiter_other(int lam, T u, T c, T d) {
   switch (lam) {
     case 0: return c;
     case 1: return median3((T(3) * c - u) / T(2), c, (c + d) / T(2));
@@ -190,9 +189,12 @@ template <class T> IFADV_DI T limiter(int lam, T u, T c, T d) {
   }
   return c;
 }
+template <class T> IFADV_DI T limiter(int lam, T u, T c, T d) {
+  if (lam == 2) return median3(t_div6(T(7) * c + d - T(2) * u), c, median3(T(2) * c - u, c, d));  // Koren, the default: inline
+  return limiter_other(lam, u, c, d);  // the other limiters: one out-of-line copy per translation unit
+}
 // ϕq, the SynDRoM flux (src/flow.jl:37-57) for mass flux Psi, stencil (uu,cc,dd) and donor density mOld
-template <class T> IFADV_DI T syndrom_flux(int lam, T Psi, T uu, T cc, T dd, T mOld, T dt) {
-  T vd = limiter(lam, uu, cc, dd);
+template <class T> IFADV_DI T syndrom_blend(T vd, T Psi, T cc, T mOld, T dt) {
   T mOut = t_abs(Psi) * dt;
 #ifdef IFADV_FAST_F32
   if (sizeof(T) == 4) {
@@ -207,6 +209,14 @@ template <class T> IFADV_DI T syndrom_flux(int lam, T Psi, T uu, T cc, T dd, T m
   T l1 = T(1) - l2;
   T vb = l2 * va + l1 * vd;
   return (Psi * (vb + vd)) / T(2);
+}
+template <class T> IFADV_DI T syndrom_flux(int lam, T Psi, T uu, T cc, T dd, T mOld, T dt) {
+  return syndrom_blend(limiter(lam, uu, cc, dd), Psi, cc, mOld, dt);
+}
+// compile-time Koren (the package default, flow.jl): no limiter dispatch in the kernel body
+template <bool KOREN, class T> IFADV_DI T syndrom_flux_t(int lam, T Psi, T uu, T cc, T dd, T mOld, T dt) {
+  if (KOREN) return syndrom_blend(median3(t_div6(T(7) * cc + dd - T(2) * uu), cc, median3(T(2) * cc - uu, cc, dd)), Psi, cc, mOld, dt);
+  return syndrom_blend(limiter_other(lam, uu, cc, dd), Psi, cc, mOld, dt);
 }
 
 // ---- interface normals: src/normalEstimation.jl -------------------------------------------------------
@@ -405,7 +415,7 @@ template <class T, int D, class BX> __device__ void interface_normal(int scheme,
 
 // PLIC volume flux through a face swept by dl, from the upwind cell with volume fraction fc
 // (general branch of getVOFFlux!, src/advection.jl:131-134).  d = face direction (0-based).
-template <class T, int D, class BX> __device__ __noinline__ T plic_face_flux(int scheme, const BX B, T fc, int d, T dl) {
+template <class T, int D, class BX> IFADV_DI T plic_face_flux_inl(int scheme, const BX B, T fc, int d, T dl) {
   T n[3];
   interface_normal<T, D>(scheme, B, n);
   T sumAbs = T(0);
@@ -419,6 +429,10 @@ template <class T, int D, class BX> __device__ __noinline__ T plic_face_flux(int
 #pragma unroll
   for (int i = 0; i < 3; ++i) m[i] = (i < D) ? n[i] * ((i == d) ? t_abs(dl) : T(1)) : T(0);
   return get_volume_fraction<T, D>(m, a) * dl;
+}
+// out-of-line copy (one ABI call per use; keeps kernels whose live state is small compact)
+template <class T, int D, class BX> __device__ __noinline__ T plic_face_flux(int scheme, const BX B, T fc, int d, T dl) {
+  return plic_face_flux_inl<T, D, BX>(scheme, B, fc, d, dl);
 }
 
 }  // namespace ifadv

@@ -37,6 +37,8 @@ IFADV_DI long long lin3(const Geo& g, int x, int y, int z) { return (long long)(
 template <class T> struct SweepP {
   const T* f_in;
   T* f_out;
+  const T* u;     // u[:, 1] (all components)
+  const T* u0;    // u⁰[:, 1]
   const T* uj;    // u[:, j]
   const T* u0j;   // u⁰[:, j]
   int8_t* cbar;   // written when first, read otherwise

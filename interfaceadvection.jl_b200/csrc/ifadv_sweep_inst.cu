@@ -5,6 +5,7 @@
 #include "ifadv_ctx.hpp"
 #include "ifadv_march.cuh"
 #include "ifadv_along.cuh"
+#include "ifadv_along2.cuh"
 
 namespace ifadv {
 
@@ -14,6 +15,7 @@ static int launch_sweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   using TL = Tile<D, J, TX, TY, TZ>;
   SweepP<T> P;
   P.f_in = q.f_in; P.f_out = q.f_out;
+  P.u = q.u; P.u0 = q.u0;
   P.uj = q.u + (long long)J * c->g.S; P.u0j = q.u0 + (long long)J * c->g.S;
   P.cbar = q.cbar;
   P.rhou_in = q.rhou_in; P.rhou_out = q.rhou_out; P.uOld = q.uOld; P.drho = q.drho;
@@ -35,7 +37,7 @@ static int launch_sweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
   if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
   kern<<<grid, NT, smem, st>>>(P);
-  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_tag[c->prof_n] = (unsigned char)(q.fused ? 1 : 0); c->prof_n++; }
+  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_tag[c->prof_n] = (unsigned char)((q.fused ? 1 : 0) | ((2 * q.j + (q.fused ? 1 : 0)) << 1)); c->prof_n++; }
   c->launches++;
   CU_CHECK(c, cudaGetLastError());
   return 0;
@@ -43,6 +45,7 @@ static int launch_sweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
 
 template <class T> static void fill_params(ifadv_ctx* c, const SweepCfg<T>& q, int J, SweepP<T>& P) {
   P.f_in = q.f_in; P.f_out = q.f_out;
+  P.u = q.u; P.u0 = q.u0;
   P.uj = q.u + (long long)J * c->g.S; P.u0j = q.u0 + (long long)J * c->g.S;
   P.cbar = q.cbar;
   P.rhou_in = q.rhou_in; P.rhou_out = q.rhou_out; P.uOld = q.uOld; P.drho = q.drho;
@@ -81,7 +84,7 @@ static int launch_march_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
   if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
   kern<<<grid, NT, smem, st>>>(P, chunk);
-  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_tag[c->prof_n] = (unsigned char)(q.fused ? 1 : 0); c->prof_n++; }
+  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_tag[c->prof_n] = (unsigned char)((q.fused ? 1 : 0) | ((2 * q.j + (q.fused ? 1 : 0)) << 1)); c->prof_n++; }
   c->launches++;
   CU_CHECK(c, cudaGetLastError());
   return 0;
@@ -111,7 +114,37 @@ static int launch_along_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
   if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
   kern<<<grid, NT, smem, st>>>(P, chunk);
-  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_tag[c->prof_n] = (unsigned char)(q.fused ? 1 : 0); c->prof_n++; }
+  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_tag[c->prof_n] = (unsigned char)((q.fused ? 1 : 0) | ((2 * q.j + (q.fused ? 1 : 0)) << 1)); c->prof_n++; }
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+// v4: lean register-marching kernel (static ring slots, one barrier per plane) for sweeps along y / z (3-D only)
+template <class T, int J, int CPT, bool MOM, bool FUSED, bool KOREN, int MINB>
+static int launch_along2_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  constexpr int NT = 256, TC = (NT / 32) * CPT;
+  using TL = ATile<TC>;
+  SweepP<T> P;
+  fill_params<T>(c, q, J, P);
+  if ((unsigned long long)c->g.S * 3ull >= 0xffffffffull) { c->err = "grid too large for 32-bit element offsets"; return -2; }
+  const size_t smem = TL::template smem_bytes<T>(MOM);
+  auto kern = along2_kernel<T, J, CPT, MOM, FUSED, KOREN, NT, MINB>;
+  static unsigned long long attr_devs = 0ull;
+  if (!((attr_devs >> (c->device & 63)) & 1ull)) {
+    CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_devs |= 1ull << (c->device & 63);
+  }
+  constexpr int DCC = (J == 1) ? 2 : 1;
+  const int nx = c->g.n[0] - 2, ncc = c->g.n[DCC] - 2, na = c->g.n[J] - 2;
+  const long long tiles = (long long)((nx + 31) / 32) * ((ncc + TC - 1) / TC);
+  int chunk = 128;  // a multiple of 4 (4 warm-up planes per chunk)
+  while (chunk > 16 && tiles * ((na + chunk - 1) / chunk) < 148 * 8) chunk >>= 1;
+  dim3 grid((unsigned)((nx + 31) / 32), (unsigned)((ncc + TC - 1) / TC), (unsigned)((na + chunk - 1) / chunk));
+  const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
+  if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
+  kern<<<grid, NT, smem, st>>>(P, chunk);
+  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_tag[c->prof_n] = (unsigned char)((q.fused ? 1 : 0) | ((2 * q.j + (q.fused ? 1 : 0)) << 1)); c->prof_n++; }
   c->launches++;
   CU_CHECK(c, cudaGetLastError());
   return 0;
@@ -119,6 +152,16 @@ static int launch_along_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
 
 template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   if constexpr (D == 3) {
+    if (c->use_march == 1 && c->use_along2 && q.j != 0) {
+      constexpr int CP = (sizeof(T) == 4) ? 2 : 1;
+      const bool koren = !MOM || q.lim == 2;  // the package default limiter is compiled in; the others go through limiter_other
+      if (MOM && q.fused) {
+        if (q.j == 1) return koren ? launch_along2_t<T, 1, CP, MOM, MOM, true, 2>(c, st, q) : launch_along2_t<T, 1, CP, MOM, MOM, !MOM, 2>(c, st, q);
+        return koren ? launch_along2_t<T, 2, CP, MOM, MOM, true, 2>(c, st, q) : launch_along2_t<T, 2, CP, MOM, MOM, !MOM, 2>(c, st, q);
+      }
+      if (q.j == 1) return koren ? launch_along2_t<T, 1, CP, MOM, false, true, 2>(c, st, q) : launch_along2_t<T, 1, CP, MOM, false, !MOM, 2>(c, st, q);
+      return koren ? launch_along2_t<T, 2, CP, MOM, false, true, 2>(c, st, q) : launch_along2_t<T, 2, CP, MOM, false, !MOM, 2>(c, st, q);
+    }
     if (c->use_march == 1 && q.j != 0) {
       // Float32: two columns per thread (2 CTAs/SM, twice the ILP, half the per-plane overhead); Float64: one
       constexpr int CP = (sizeof(T) == 4) ? 2 : 1;
