@@ -6,6 +6,7 @@
 #include "ifadv_march.cuh"
 #include "ifadv_along.cuh"
 #include "ifadv_along2.cuh"
+#include "ifadv_xsweep.cuh"
 
 namespace ifadv {
 
@@ -150,8 +151,46 @@ static int launch_along2_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) 
   return 0;
 }
 
+// v4: lean plane-marching kernel for CMOM sweeps along x (3-D only)
+template <class T, int CPT, bool FUSED, bool KOREN, int MINB>
+static int launch_xsweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  constexpr int NT = 256, TY = (NT / 32) * CPT;
+  using TL = XTile<TY>;
+  SweepP<T> P;
+  fill_params<T>(c, q, 0, P);
+  if ((unsigned long long)c->g.S * 3ull >= 0xffffffffull) { c->err = "grid too large for 32-bit element offsets"; return -2; }
+  const size_t smem = TL::template smem_bytes<T>();
+  auto kern = xsweep_kernel<T, CPT, FUSED, KOREN, NT, MINB>;
+  static unsigned long long attr_devs = 0ull;
+  if (!((attr_devs >> (c->device & 63)) & 1ull)) {
+    CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_devs |= 1ull << (c->device & 63);
+  }
+  const int nx = c->g.n[0] - 2, ny = c->g.n[1] - 2, nz = c->g.n[2] - 2;
+  const long long tiles = (long long)((nx + 31) / 32) * ((ny + TY - 1) / TY);
+  int chunk = 128;  // 3-6 warm-up planes per chunk
+  while (chunk > 16 && tiles * ((nz + chunk - 1) / chunk) < 148 * 8) chunk >>= 1;
+  dim3 grid((unsigned)((nx + 31) / 32), (unsigned)((ny + TY - 1) / TY), (unsigned)((nz + chunk - 1) / chunk));
+  const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
+  if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
+  kern<<<grid, NT, smem, st>>>(P, chunk);
+  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_tag[c->prof_n] = (unsigned char)((q.fused ? 1 : 0) | ((2 * q.j + (q.fused ? 1 : 0)) << 1)); c->prof_n++; }
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
 template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   if constexpr (D == 3) {
+    if constexpr (MOM) {
+      if (c->use_march == 1 && c->use_along2 && q.j == 0) {
+        constexpr int CP = (sizeof(T) == 4) ? 2 : 1;
+        constexpr int MB = (sizeof(T) == 4) ? 2 : 1;
+        const bool koren = q.lim == 2;
+        if (q.fused) return koren ? launch_xsweep_t<T, CP, true, true, MB>(c, st, q) : launch_xsweep_t<T, CP, true, false, MB>(c, st, q);
+        return koren ? launch_xsweep_t<T, CP, false, true, MB>(c, st, q) : launch_xsweep_t<T, CP, false, false, MB>(c, st, q);
+      }
+    }
     if (c->use_march == 1 && c->use_along2 && q.j != 0) {
       constexpr int CP = (sizeof(T) == 4) ? 2 : 1;
       const bool koren = !MOM || q.lim == 2;  // the package default limiter is compiled in; the others go through limiter_other
