@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
   constexpr int DCC = (J == 1) ? 2 : 1;  // global dimension of the cross direction c
   constexpr int WX = TL::WX, PLH = TL::PLH, NC = TL::NC;
   constexpr bool fused = MOM && FUSED;
+  const bool first = fused ? true : (P.first != 0);  // the fused sweep is always sweep 1
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sm = reinterpret_cast<T*>(smem_raw);
   // element offsets of the shared arrays
@@ -135,9 +136,7 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
   T dilm1[CPT], dil0[CPT], dv0[CPT];               // dilation of planes k-1, k; c̄(∂u+∂u⁰)δt/2 of plane k
   T f0[CPT], f1[CPT], u1[CPT], u01[CPT];           // f(k), f(k+1); u_a, u⁰_a at face k+1
   T h0[3][CPT], h1[3][CPT];                        // ρ at the lower a / x / c faces of cells k, k+1
-  int cbn[CPT];                                    // c̄ of the next dilation plane (non-first sweeps, read one step ahead)
   bool mk[CPT];                                    // face k+1 of this column is an interface face (reconstructed lane-dense)
-  int cbh = 0;
 #pragma unroll
   for (int j = 0; j < CPT; ++j) {
 #pragma unroll
@@ -147,7 +146,7 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
       Flo[r][j] = T(0); h0[r][j] = T(1); h1[r][j] = T(1);
     }
     FFlo[j] = Mlo[j] = FFhi[j] = Mhi[j] = dilm1[j] = dil0[j] = dv0[j] = T(0);
-    cbn[j] = 0; mk[j] = false;
+    mk[j] = false;
   }
   T rmax = -INFINITY, rmin = INFINITY;
   unsigned int amax = 0, amin = 0;
@@ -199,11 +198,6 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
       }
     }
     cp_async_commit();
-    if (!P.first) {
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) cbn[j] = (int)P.cbar[pm(ks + 1) + go[j]];
-      if (MOM && hU) cbh = (int)P.cbar[pm(ks + 1) + gh];
-    }
     // the M / Dil rings are read one step after they are written: start from zeros
     for (int i = tid; i < 2 * PLH; i += NT) { sm[OM + i] = T(0); if (MOM) sm[ODIL + i] = T(0); }
     cp_async_wait_all();
@@ -235,6 +229,17 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
     auto s4 = [&](int d) -> unsigned { return FAST ? (unsigned)((I + d) & 3) : (unsigned)((rel + d) & 3); };
     auto s2 = [&](int d) -> unsigned { return FAST ? (unsigned)((I + d) & 1) : (unsigned)((rel + d) & 1); };
 
+    // c̄(k+1) for this step's dilation: the read is issued before the barrier, so its latency overlaps the wait
+    int cb1[CPT];
+    int cbh1 = 0;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) cb1[j] = 0;
+    if (!first) {
+      const unsigned oc1 = FAST ? lkU + sA : pm(k + 1);
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) cb1[j] = (int)P.cbar[go[j] + oc1];
+      if (MOM && hU) cbh1 = (int)P.cbar[gh + oc1];
+    }
     cp_async_wait_all();
     __syncthreads();  // S1: the copies issued during step k-1 have landed; every read / write of step k-1 is done
 
@@ -248,12 +253,10 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
 
     // A. next planes' copies: f(k+3), u_a/u⁰_a(k+3), ρu(k+3), uOld(k+1), c̄(k+2).  One 64-bit base per array; component offsets
     //    and the plane lookahead are part of the 32-bit element offsets (block-uniform part + go[j]).
-    int cb1[CPT];  // c̄(k+1)
-    int cbh1 = 0;
     {
-      unsigned oM3, oO3, oM1, oM2;  // offsets of plane k+3 (mapped / as stored), k+1, k+2
-      if (FAST) { oM3 = oO3 = lkU + 3 * sA; oM1 = lkU + sA; oM2 = lkU + 2 * sA; }  // lkU = (k-1)*sA = offset of plane k
-      else { oM3 = pm(k + 3); oO3 = po(k + 3); oM1 = pm(k + 1); oM2 = pm(k + 2); }
+      unsigned oM3, oO3, oM1;  // offsets of plane k+3 (mapped / as stored), k+1, k+2
+      if (FAST) { oM3 = oO3 = lkU + 3 * sA; oM1 = lkU + sA; }  // lkU = (k-1)*sA = offset of plane k
+      else { oM3 = pm(k + 3); oO3 = po(k + 3); oM1 = pm(k + 1); }
       const unsigned dF = (OF + sF8(3)) * SZ, dU = (OU + s4(3) * PLH) * SZ, dU0 = (OU0 + s4(3) * PLH) * SZ;
       const unsigned dR = (OR + s4(3) * 3 * NC) * SZ, dO = (OO + s2(1) * 3 * NC) * SZ;
       const unsigned oA3 = oO3 + cA, oC3 = oM3 + cC, oA1 = oM1 + cA, oC1 = oM1 + cC;
@@ -279,15 +282,6 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
         cp_async_s(seh + dU0, u0base + (gh + oA3));
       }
       cp_async_commit();
-      // c̄: this step's dilation (plane k+1) uses the value read one step ago; read c̄(k+2) for the next step
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) cb1[j] = cbn[j];
-      cbh1 = cbh;
-      if (!P.first) {
-#pragma unroll
-        for (int j = 0; j < CPT; ++j) cbn[j] = (int)P.cbar[go[j] + oM2];
-        if (MOM && hU) cbh = (int)P.cbar[gh + oM2];
-      }
     }
 
     // P. lane-dense PLIC reconstruction of the interface faces k+1 marked in step k-1 (general branch of getVOFFlux!, advection.jl:131-134)
@@ -363,7 +357,7 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
       sm[wM + e] = Mn[j];
       // D. dilation of plane k+1 (flow.jl:216)
       const T div1 = (u2[j] - u1[j]) + (u02[j] - u01[j]);  // ∂(d,I,u)+∂(d,I,u⁰)
-      if (P.first) cb1[j] = (f1[j] < T(0.5)) ? 0 : 1;  // flow.jl:172 (c̄ from the incoming f)
+      if (first) cb1[j] = (f1[j] < T(0.5)) ? 0 : 1;  // flow.jl:172 (c̄ from the incoming f)
       dv1[j] = ((cb1[j] ? div1 : T(0)) * dt) / T(2);   // c̄[I]*(∂u+∂u⁰)*δt/2 of advection.jl:83 for the update of cell k+1
       dil1[j] = T(0);
       if (MOM) {
@@ -390,7 +384,7 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
       }
       sm[wM + eh] = m;
       const T dh = (uh2 - sm[pU + eh]) + (u0h2 - sm[pU0 + eh]);
-      const int ch = P.first ? ((fh1 < T(0.5)) ? 0 : 1) : cbh1;
+      const int ch = first ? ((fh1 < T(0.5)) ? 0 : 1) : cbh1;
       sm[wD + eh] = ((ch ? lam1 : lr) * dh) / T(2);
     }
 
@@ -437,7 +431,7 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
       // H. update of cell k
       if (store && valid[j]) {
         const unsigned lk = lk0 + go[j];
-        if (P.first) P.cbar[lk] = (int8_t)((f0[j] < T(0.5)) ? 0 : 1);
+        if (first) P.cbar[lk] = (int8_t)((f0[j] < T(0.5)) ? 0 : 1);
         T fn = f0[j] + ((FFlo[j] - FFhi[j]) + dv0[j]);  // advection.jl:83
         rmax = max_nan(rmax, fn);
         rmin = t_min(rmin, fn);

@@ -88,6 +88,7 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
   const T lr = P.lr, omlr = P.omlr, dt = P.dt;
   const T lam1 = lin_interp(T(1), lr, omlr);
   const T AA = P.A[0], AB = P.A[1], AC = P.A[2];
+  const bool first = FUSED ? true : (P.first != 0);  // the fused sweep is always sweep 1
   const T* const rsrc = FUSED ? P.uOld : P.rhou_in;  // fused sweep 1: the ρu ring carries uOld, ρu = BC!(uOld*ρ(f̄)) on the fly
   if (tid < 4) sCnt[tid] = 0;
 
@@ -169,23 +170,21 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
   // ---- rolling register state per own cell (values entering step k) ----------------------------------------------------------------
   T us1[3][CPT];            // own u★ of plane k+1
   T h1[3][CPT], h0[3][CPT]; // ρ at the lower x / y / z faces of the own cell in planes k+1, k (h0 only in the fused sweep)
-  T M1[CPT], M0[CPT];       // own mass flux (lower x-face) of planes k+1, k
-  T FF1[CPT], FF0[CPT];     // own fᶠ of planes k+1, k
+  T M1[CPT];                // own mass flux (lower x-face) of plane k+1 (plane k: shared M ring)
+  T FF1[CPT];               // own fᶠ of plane k+1 (plane k: the Φ/fᶠ buffer written in S2)
   T dv1[CPT], dv0[CPT];     // c̄(∂u+∂u⁰)δt/2 of planes k+1, k
   T Fl0[3][CPT];            // own SynDRoM fluxes of plane k
-  T f1[CPT], f0[CPT];
-  int cbn[CPT];
+  T f1[CPT];                // own f(k+1) (f(k): shared f ring)
   bool mk1[CPT];
   T hFF1 = T(0);            // halo face x+32: fᶠ of plane k+1
   bool hmk1 = false;
-  int cbh = 0;
 #pragma unroll
   for (int j = 0; j < CPT; ++j) {
 #pragma unroll
     for (int r = 0; r < 3; ++r) { us1[r][j] = T(0); h1[r][j] = h0[r][j] = T(1); Fl0[r][j] = T(0); }
-    M1[j] = M0[j] = FF1[j] = FF0[j] = dv1[j] = dv0[j] = T(0);
-    f1[j] = f0[j] = T(0);
-    cbn[j] = 0; mk1[j] = false;
+    M1[j] = FF1[j] = dv1[j] = dv0[j] = T(0);
+    f1[j] = T(0);
+    mk1[j] = false;
   }
   T rmax = -INFINITY, rmin = INFINITY;
   unsigned int amax = 0, amin = 0;
@@ -197,19 +196,15 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
   __syncthreads();
   issue(pm(ks + 2), po(ks + 2), 2, 0);
   cp_async_commit();
-  if (!P.first) {
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) cbn[j] = (int)P.cbar[gm[j] + pm(ks + 2)];
-    if (hDIL) cbh = (int)P.cbar[ghm + pm(ks + 2)];
-  }
   for (int i = tid; i < 4 * PL; i += NT) { sm[OM + i] = T(0); sm[ODIL + i] = T(0); }
   for (int i = tid; i < 6 * PL; i += NT) sm[OUS + i] = T(0);
   for (int i = tid; i < 8 * PL; i += NT) sm[OFL + i] = T(0);
 #pragma unroll
-  for (int j = 0; j < CPT; ++j) { f0[j] = sm[OF + e0 + j * TR * WX]; f1[j] = sm[OF + PL + e0 + j * TR * WX]; }
+  for (int j = 0; j < CPT; ++j) f1[j] = sm[OF + PL + e0 + j * TR * WX];
 
   unsigned lkU = (unsigned)(ks - 1) * s2;  // (k-1)*s2, offset of plane k
   unsigned pm3 = pm(ks + 3), po3 = po(ks + 3);  // offsets of plane k+3 (mapped / as stored), rolled with the march
+  unsigned pm2 = pm(ks + 2);                    // mapped offset of plane k+2 (c̄)
 
   // SynDRoM fluxes through the lower x-face of the cell at entry e, plane k+1 (ring phase I): shared by own cells and the halo face x+32
   auto face_flux = [&](auto ic, const int k, const int e, const unsigned flg, const unsigned yoff_drho, const T Mown, const T Mprev,
@@ -262,45 +257,27 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
   auto step = [&](auto ic, const int k) {
     constexpr int I = decltype(ic)::value;  // (k-ks)&3
     const int rel = k - ks;
+    // c̄(k+2) for this step's dilation: the read is issued before the barrier, so its latency overlaps the wait
+    int cb2[CPT];
+    int cbh2 = 0;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) cb2[j] = 0;
+    if (!first) {
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) cb2[j] = (int)P.cbar[gm[j] + pm2];
+      if (hDIL) cbh2 = (int)P.cbar[ghm + pm2];
+    }
     cp_async_wait_all();
     __syncthreads();  // the copies issued during step k-1 have landed; every read / write of step k-1 is done
 
     const bool store = k >= k0;
     const bool dirC2 = dirCf(k + 2), dirC0 = dirCf(k);
-    // A. copies of plane k+3.  ρu (and uOld) of plane k for the update at the end of this step are re-read through L2 into
-    //    registers (the shared ρu ring only holds the plane u★ is formed from); c̄ of plane k+3 is read one step ahead.
+    // A. copies of plane k+3
     issue(pm3, po3, (I + 3) & 3, (I + 3) & 1);
     cp_async_commit();
-    T q0[3][CPT], uo[3][CPT];
-    int cb2[CPT];
-    const int cbh2 = cbh;
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      cb2[j] = cbn[j];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) q0[r][j] = uo[r][j] = T(0);
-    }
-    if (store) {
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const unsigned o = gm[j] + lkU;
-        q0[0][j] = __ldg(rsrc + o);
-        q0[1][j] = __ldg(rsrc + (o + cB));
-        q0[2][j] = __ldg(rsrc + (o + cC));
-        if (!FUSED) {
-          uo[0][j] = __ldg(P.uOld + o);
-          uo[1][j] = __ldg(P.uOld + (o + cB));
-          uo[2][j] = __ldg(P.uOld + (o + cC));
-        }
-      }
-    }
-    if (!P.first) {
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) cbn[j] = (int)P.cbar[gm[j] + pm3];
-      if (hDIL) cbh = (int)P.cbar[ghm + pm3];
-    }
     {  // offsets of plane k+4: one stride further unless the plane is within the boundary band (block-uniform)
       const int v = k + 4;
+      pm2 = pm3;
       if (v >= 3 && v <= nC - 1) { pm3 += s2; po3 += s2; }
       else { pm3 = pm(v); po3 = po(v); }
     }
@@ -382,7 +359,7 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
       // S1(k+2): VOF flux, mass flux, dilation
       vof_face(e, cflg, fxm, f2[j], FF2[j], M2[j], mk2[j]);
       const T div = (sm[qU + e + 1] - sm[qU + e]) + (sm[qU0 + e + 1] - sm[qU0 + e]);  // ∂(d,I,u)+∂(d,I,u⁰)
-      if (P.first) cb2[j] = (f2[j] < T(0.5)) ? 0 : 1;                                  // flow.jl:172 (c̄ from the incoming f)
+      if (first) cb2[j] = (f2[j] < T(0.5)) ? 0 : 1;                                  // flow.jl:172 (c̄ from the incoming f)
       dv2[j] = ((cb2[j] ? div : T(0)) * dt) / T(2);                                   // c̄[I]*(∂u+∂u⁰)*δt/2 of advection.jl:83
       sm[wD + e] = ((cb2[j] ? lam1 : lr) * div) / T(2);                               // flow.jl:216
     }
@@ -405,18 +382,38 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
         if (hDIL) {
           const int e2 = (XB && (hflg & XF_DILSH)) ? eh + 1 : eh;  // BCf! (Neumann) on ρ̄∂ⱼuⱼ along the sweep direction, flow.jl:217
           const T div = (sm[qU + e2 + 1] - sm[qU + e2]) + (sm[qU0 + e2 + 1] - sm[qU0 + e2]);
-          const int cb = P.first ? ((fh < T(0.5)) ? 0 : 1) : cbh2;
+          const int cb = first ? ((fh < T(0.5)) ? 0 : 1) : cbh2;
           sm[wD + eh] = ((cb ? lam1 : lr) * div) / T(2);
         }
       }
     }
 
+    T q0[3][CPT], uo[3][CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) q0[r][j] = uo[r][j] = T(0);
+    }
+    if (store) {
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const unsigned o = gm[j] + lkU;
+        q0[0][j] = __ldg(rsrc + o);
+        q0[1][j] = __ldg(rsrc + (o + cB));
+        q0[2][j] = __ldg(rsrc + (o + cC));
+        if (!FUSED) {
+          uo[0][j] = __ldg(P.uOld + o);
+          uo[1][j] = __ldg(P.uOld + (o + cB));
+          uo[2][j] = __ldg(P.uOld + (o + cC));
+        }
+      }
+    }
     // S2(k+1): SynDRoM momentum flux through the lower x-face of the own cells and of the halo face x+32
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
       const int e = e0 + j * TR * WX;
       T ucr[3] = {us1[0][j], us1[1][j], us1[2][j]}, hw[3] = {h1[0][j], h1[1][j], h1[2][j]}, fl[3];
-      face_flux(ic, k, e, cflg, gm[j] - (unsigned)(mapc(vx, nA, perA) - 1), M1[j], M0[j], ucr, hw, fl);
+      face_flux(ic, k, e, cflg, gm[j] - (unsigned)(mapc(vx, nA, perA) - 1), M1[j], sm[OM + (I & 3) * PL + e], ucr, hw, fl);
 #pragma unroll
       for (int r = 0; r < 3; ++r) { Fl1[r][j] = fl[r]; sm[wFL + r * PL + e] = fl[r]; }
       sm[wFL + 3 * PL + e] = FF1[j];
@@ -434,7 +431,8 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
       sm[wFL + 3 * PL + eh] = hFF1;
     }
 
-    // S3(k): update of the own cells
+    // S3(k): update of the own cells.  ρu (and uOld) of plane k are re-read through L2 into registers (the shared ρu ring only
+    // holds the plane u★ is formed from); the reads are in flight while the SynDRoM fluxes above are evaluated.
     const unsigned lk0 = lkU;
     lkU += s2;
 #pragma unroll
@@ -442,8 +440,9 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
       const int e = e0 + j * TR * WX;
       if (store && valid[j]) {
         const unsigned lk = lk0 + gm[j];  // owned cells are interior: the mapped offset is the cell itself
-        if (P.first) P.cbar[lk] = (int8_t)((f0[j] < T(0.5)) ? 0 : 1);
-        T fn = f0[j] + ((FF0[j] - sm[rFL + 3 * PL + e + 1]) + dv0[j]);  // advection.jl:83
+        const T f0 = sm[OF + (I & 3) * PL + e];
+        if (first) P.cbar[lk] = (int8_t)((f0 < T(0.5)) ? 0 : 1);
+        T fn = f0 + ((sm[rFL + 3 * PL + e] - sm[rFL + 3 * PL + e + 1]) + dv0[j]);  // advection.jl:83
         rmax = max_nan(rmax, fn);
         rmin = t_min(rmin, fn);
         if (fn > T(1) || fn < T(0)) {  // only cells outside [0,1] can be reported (reportFillError, advection.jl:145-189)
@@ -474,8 +473,8 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
       for (int r = 0; r < 3; ++r) {
         Fl0[r][j] = Fl1[r][j]; us1[r][j] = us2[r][j]; h0[r][j] = h1[r][j]; h1[r][j] = h2[r][j];
       }
-      FF0[j] = FF1[j]; FF1[j] = FF2[j]; M0[j] = M1[j]; M1[j] = M2[j]; mk1[j] = mk2[j];
-      dv0[j] = dv1[j]; dv1[j] = dv2[j]; f0[j] = f1[j]; f1[j] = f2[j];
+      FF1[j] = FF2[j]; M1[j] = M2[j]; mk1[j] = mk2[j];
+      dv0[j] = dv1[j]; dv1[j] = dv2[j]; f1[j] = f2[j];
     }
     hFF1 = hFF2; hmk1 = hmk2;
   };
