@@ -1,15 +1,29 @@
-// ifadv_sweep_inst.cu -- instantiates the fused sweep kernels for ONE (T, D, MOM) combination, chosen with
-// -DIFADV_T=float|double -DIFADV_D=2|3 -DIFADV_MOM=0|1, so that the instantiations compile in parallel.
+// ifadv_sweep_inst.cu -- instantiates the fused sweep kernels for ONE (T, D, MOM, family) combination, chosen with
+// -DIFADV_T=float|double -DIFADV_D=2|3 -DIFADV_MOM=0|1 -DIFADV_FAM=0..4, so that the instantiations compile in parallel:
+//   FAM 0  dispatcher (launch_sweep_dim) + v1 tile kernel        FAM 1  plane-marching kernel (march)
+//   FAM 2  register-marching kernel (along)                      FAM 3  lean register marching (along2), y / z sweeps
+//   FAM 4  lean plane marching along x (xsweep, CMOM only)       families 1-4 exist for 3-D grids only
 #include <limits>
 
 #include "ifadv_ctx.hpp"
+#ifndef IFADV_FAM
+#error "compile with -DIFADV_FAM=0..4"
+#endif
+#if IFADV_FAM == 0
+#include "ifadv_sweep.cuh"
+#elif IFADV_FAM == 1
 #include "ifadv_march.cuh"
+#elif IFADV_FAM == 2
 #include "ifadv_along.cuh"
+#elif IFADV_FAM == 3
 #include "ifadv_along2.cuh"
+#else
 #include "ifadv_xsweep.cuh"
+#endif
 
 namespace ifadv {
 
+#if IFADV_FAM == 0
 template <class T, int D, int J, int TX, int TY, int TZ, bool MOM>
 static int launch_sweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   constexpr int NT = 256;
@@ -44,6 +58,8 @@ static int launch_sweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   return 0;
 }
 
+#endif
+
 template <class T> static void fill_params(ifadv_ctx* c, const SweepCfg<T>& q, int J, SweepP<T>& P) {
   P.f_in = q.f_in; P.f_out = q.f_out;
   P.u = q.u; P.u0 = q.u0;
@@ -58,6 +74,7 @@ template <class T> static void fill_params(ifadv_ctx* c, const SweepCfg<T>& q, i
   for (int i = 0; i < 3; ++i) P.coff[i] = (long long)i * c->g.S;
 }
 
+#if IFADV_FAM == 1
 // v2: plane-marching kernel (3-D only)
 template <class T, int J, int TA, int TB, bool MOM, bool FUSED, int MINB>
 static int launch_march_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
@@ -91,6 +108,9 @@ static int launch_march_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   return 0;
 }
 
+#endif
+
+#if IFADV_FAM == 2
 // v3: register-marching kernel for sweeps along y / z (3-D only)
 template <class T, int J, int CPT, bool MOM, bool FUSED, int MINB>
 static int launch_along_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
@@ -121,6 +141,9 @@ static int launch_along_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   return 0;
 }
 
+#endif
+
+#if IFADV_FAM == 3
 // v4: lean register-marching kernel (static ring slots, one barrier per plane) for sweeps along y / z (3-D only)
 template <class T, int J, int CPT, bool MOM, bool FUSED, bool KOREN, int MINB>
 static int launch_along2_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
@@ -151,6 +174,9 @@ static int launch_along2_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) 
   return 0;
 }
 
+#endif
+
+#if IFADV_FAM == 4
 // v4: lean plane-marching kernel for CMOM sweeps along x (3-D only)
 template <class T, int CPT, bool FUSED, bool KOREN, int MINB>
 static int launch_xsweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
@@ -180,51 +206,23 @@ static int launch_xsweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) 
   return 0;
 }
 
+#endif
+
+// per-family entry points (3-D only), each defined and explicitly instantiated in its own translation unit
+template <class T, bool MOM> int launch_fam_march(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
+template <class T, bool MOM> int launch_fam_along(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
+template <class T, bool MOM> int launch_fam_along2(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
+template <class T, bool MOM> int launch_fam_xsweep(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
+
+#if IFADV_FAM == 0
 template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   if constexpr (D == 3) {
-    if constexpr (MOM) {
-      if (c->use_march == 1 && c->use_along2 && q.j == 0) {
-        constexpr int CP = (sizeof(T) == 4) ? 2 : 1;
-        constexpr int MB = (sizeof(T) == 4) ? 2 : 1;
-        const bool koren = q.lim == 2;
-        if (q.fused) return koren ? launch_xsweep_t<T, CP, true, true, MB>(c, st, q) : launch_xsweep_t<T, CP, true, false, MB>(c, st, q);
-        return koren ? launch_xsweep_t<T, CP, false, true, MB>(c, st, q) : launch_xsweep_t<T, CP, false, false, MB>(c, st, q);
-      }
+    if (c->use_march == 1 && c->use_along2) {
+      if (q.j != 0) return launch_fam_along2<T, MOM>(c, st, q);
+      if constexpr (MOM) return launch_fam_xsweep<T, MOM>(c, st, q);
     }
-    if (c->use_march == 1 && c->use_along2 && q.j != 0) {
-      constexpr int CP = (sizeof(T) == 4) ? 2 : 1;
-      const bool koren = !MOM || q.lim == 2;  // the package default limiter is compiled in; the others go through limiter_other
-      if (MOM && q.fused) {
-        if (q.j == 1) return koren ? launch_along2_t<T, 1, CP, MOM, MOM, true, 2>(c, st, q) : launch_along2_t<T, 1, CP, MOM, MOM, !MOM, 2>(c, st, q);
-        return koren ? launch_along2_t<T, 2, CP, MOM, MOM, true, 2>(c, st, q) : launch_along2_t<T, 2, CP, MOM, MOM, !MOM, 2>(c, st, q);
-      }
-      if (q.j == 1) return koren ? launch_along2_t<T, 1, CP, MOM, false, true, 2>(c, st, q) : launch_along2_t<T, 1, CP, MOM, false, !MOM, 2>(c, st, q);
-      return koren ? launch_along2_t<T, 2, CP, MOM, false, true, 2>(c, st, q) : launch_along2_t<T, 2, CP, MOM, false, !MOM, 2>(c, st, q);
-    }
-    if (c->use_march == 1 && q.j != 0) {
-      // Float32: two columns per thread (2 CTAs/SM, twice the ILP, half the per-plane overhead); Float64: one
-      constexpr int CP = (sizeof(T) == 4) ? 2 : 1;
-      if (MOM && q.fused) {
-        if (q.j == 1) return launch_along_t<T, 1, CP, MOM, MOM, 2>(c, st, q);
-        return launch_along_t<T, 2, CP, MOM, MOM, 2>(c, st, q);
-      }
-      if (q.j == 1) return launch_along_t<T, 1, CP, MOM, false, 2>(c, st, q);
-      return launch_along_t<T, 2, CP, MOM, false, 2>(c, st, q);
-    }
-    if (c->use_march) {
-      // tile shapes sized so that 25 shared planes leave 3 (f32) / 2-3 (f64) CTAs per SM
-      constexpr int TO = (sizeof(T) == 4) ? 16 : 8;
-      constexpr int TBX = (sizeof(T) == 4) ? 16 : 8;
-      constexpr int MB = 2;
-      if (MOM && q.fused) {
-        if (q.j == 0) return launch_march_t<T, 0, 32, TBX, MOM, MOM, MB>(c, st, q);
-        if (q.j == 1) return launch_march_t<T, 1, TO, 32, MOM, MOM, MB>(c, st, q);
-        return launch_march_t<T, 2, TO, 32, MOM, MOM, MB>(c, st, q);
-      }
-      if (q.j == 0) return launch_march_t<T, 0, 32, TBX, MOM, false, MB>(c, st, q);
-      if (q.j == 1) return launch_march_t<T, 1, TO, 32, MOM, false, MB>(c, st, q);
-      return launch_march_t<T, 2, TO, 32, MOM, false, MB>(c, st, q);
-    }
+    if (c->use_march == 1 && q.j != 0) return launch_fam_along<T, MOM>(c, st, q);
+    if (c->use_march) return launch_fam_march<T, MOM>(c, st, q);
   }
   if constexpr (D == 2) {
     if (q.j == 0) return launch_sweep_t<T, 2, 0, 64, 8, 1, MOM>(c, st, q);
@@ -236,5 +234,60 @@ template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStrea
   }
 }
 template int launch_sweep_dim<IFADV_T, IFADV_D, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
+
+#elif IFADV_FAM == 1
+template <class T, bool MOM> int launch_fam_march(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  // tile shapes sized so that 25 shared planes leave 3 (f32) / 2-3 (f64) CTAs per SM
+  constexpr int TO = (sizeof(T) == 4) ? 16 : 8;
+  constexpr int TBX = (sizeof(T) == 4) ? 16 : 8;
+  constexpr int MB = 2;
+  if (MOM && q.fused) {
+    if (q.j == 0) return launch_march_t<T, 0, 32, TBX, MOM, MOM, MB>(c, st, q);
+    if (q.j == 1) return launch_march_t<T, 1, TO, 32, MOM, MOM, MB>(c, st, q);
+    return launch_march_t<T, 2, TO, 32, MOM, MOM, MB>(c, st, q);
+  }
+  if (q.j == 0) return launch_march_t<T, 0, 32, TBX, MOM, false, MB>(c, st, q);
+  if (q.j == 1) return launch_march_t<T, 1, TO, 32, MOM, false, MB>(c, st, q);
+  return launch_march_t<T, 2, TO, 32, MOM, false, MB>(c, st, q);
+}
+template int launch_fam_march<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
+
+#elif IFADV_FAM == 2
+template <class T, bool MOM> int launch_fam_along(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  // Float32: two columns per thread (2 CTAs/SM, twice the ILP, half the per-plane overhead); Float64: one
+  constexpr int CP = (sizeof(T) == 4) ? 2 : 1;
+  if (MOM && q.fused) {
+    if (q.j == 1) return launch_along_t<T, 1, CP, MOM, MOM, 2>(c, st, q);
+    return launch_along_t<T, 2, CP, MOM, MOM, 2>(c, st, q);
+  }
+  if (q.j == 1) return launch_along_t<T, 1, CP, MOM, false, 2>(c, st, q);
+  return launch_along_t<T, 2, CP, MOM, false, 2>(c, st, q);
+}
+template int launch_fam_along<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
+
+#elif IFADV_FAM == 3
+template <class T, bool MOM> int launch_fam_along2(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  constexpr int CP = (sizeof(T) == 4) ? 2 : 1;
+  const bool koren = !MOM || q.lim == 2;  // the package default limiter is compiled in; the others go through limiter_other
+  if (MOM && q.fused) {
+    if (q.j == 1) return koren ? launch_along2_t<T, 1, CP, MOM, MOM, true, 2>(c, st, q) : launch_along2_t<T, 1, CP, MOM, MOM, !MOM, 2>(c, st, q);
+    return koren ? launch_along2_t<T, 2, CP, MOM, MOM, true, 2>(c, st, q) : launch_along2_t<T, 2, CP, MOM, MOM, !MOM, 2>(c, st, q);
+  }
+  if (q.j == 1) return koren ? launch_along2_t<T, 1, CP, MOM, false, true, 2>(c, st, q) : launch_along2_t<T, 1, CP, MOM, false, !MOM, 2>(c, st, q);
+  return koren ? launch_along2_t<T, 2, CP, MOM, false, true, 2>(c, st, q) : launch_along2_t<T, 2, CP, MOM, false, !MOM, 2>(c, st, q);
+}
+template int launch_fam_along2<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
+
+#else
+template <class T, bool MOM> int launch_fam_xsweep(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  static_assert(MOM, "the pure-VOF x-sweep runs the march kernel");
+  constexpr int CP = (sizeof(T) == 4) ? 2 : 1;
+  constexpr int MB = (sizeof(T) == 4) ? 2 : 1;
+  const bool koren = q.lim == 2;
+  if (q.fused) return koren ? launch_xsweep_t<T, CP, true, true, MB>(c, st, q) : launch_xsweep_t<T, CP, true, false, MB>(c, st, q);
+  return koren ? launch_xsweep_t<T, CP, false, true, MB>(c, st, q) : launch_xsweep_t<T, CP, false, false, MB>(c, st, q);
+}
+template int launch_fam_xsweep<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
+#endif
 
 }  // namespace ifadv
