@@ -141,6 +141,11 @@ int ifadv_apply_vof_samples(ifadv_ctx* ctx, void* stream, void* f, void* alpha, 
 int ifadv_mom_advect_step_host(ifadv_ctx* ctx, void* f_host, const void* u_host, void* rhou_host, double dt, double lambda_rho,
                                int limiter, int normal_scheme, const double uBC[3], unsigned perdir_mask, const int dirO[3],
                                ifadv_report* report);
+/* Bytes the last ifadv_mom_advect_step_host call copied host->device / device->host and the number of z-slabs it was
+ * pipelined over (1 = single pass).  Large 3-D grids that are not periodic in z are split into z-slabs (a quarter of the planes
+ * each, IFADV_HOST_CHUNK=<planes> overrides, 0 disables) extended by 8 overlap planes per interior end, so that the copies of
+ * consecutive slabs overlap the kernels; the result is bit-identical to the single pass.  Needs page-locked host buffers. */
+int ifadv_host_step_bytes(const ifadv_ctx* ctx, int64_t* h2d_bytes, int64_t* d2h_bytes, int* slabs);
 
 #ifdef __cplusplus
 }

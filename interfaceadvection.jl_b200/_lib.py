@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libifadv_b200.so")
+LIB_PATH = os.environ.get("IFADV_LIB") or os.path.join(_HERE, "libifadv_b200.so")  # IFADV_LIB: A/B builds of the same ABI (csrc/Makefile OUT=)
 
 NORMAL_SCHEMES = {"WH": 0, "WY": 1, "Column": 2, "PCD": 3, "SLIC": 4, "MYC": 5, "Y": 6, "CD": 7, "XYLIC": 8}
 LIMITERS = {"upwind": 0, "minmod": 1, "Koren": 2, "vanAlbada1": 3, "Sweby": 4, "superbee": 5, "TVDcen": 6, "TVDdown": 7,
@@ -59,6 +59,7 @@ def lib():
         L.ifadv_sum_inside.argtypes = [vp, vp, vp, dblp]
         L.ifadv_apply_vof_samples.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
         L.ifadv_mom_advect_step_host.argtypes = [vp, vp, vp, vp, dbl, dbl, i32, i32, dblp, u32, i32p, rep]
+        L.ifadv_host_step_bytes.argtypes = [vp, i64p, i64p, i32p]
         _lib = L
     return _lib
 
@@ -182,6 +183,12 @@ class Context:
 
     def apply_vof_samples(self, stream, f, alpha, nhat, sc, sp, sm):
         return self._chk(lib().ifadv_apply_vof_samples(self._h, stream, f, alpha, nhat, sc, sp, sm))
+
+    def host_step_bytes(self):
+        """(h2d_bytes, d2h_bytes, slabs) of the last mom_advect_step_host call (ifadv_host_step_bytes)."""
+        a, b, n = C.c_int64(0), C.c_int64(0), C.c_int(0)
+        lib().ifadv_host_step_bytes(self._h, C.byref(a), C.byref(b), C.byref(n))
+        return int(a.value), int(b.value), int(n.value)
 
     def mom_advect_step_host(self, f_host, u_host, rhou_host, dt, lam_rho, limiter, scheme, uBC, perdir, dirO, report=None):
         r = C.byref(report) if report is not None else None

@@ -9,6 +9,8 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <vector>
+#include <algorithm>
 
 #include "../../include/ifadv.h"
 #include "ifadv_ctx.hpp"
@@ -365,6 +367,8 @@ template <class T> static int axpby_t(ifadv_ctx* c, cudaStream_t st, T* out, dou
 // ------------------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------------------
+namespace { void host_pipe_free(ifadv_ctx* c); }  // z-slab pipeline of the host-buffer entry point, defined below
+
 extern "C" {
 
 const char* ifadv_version(void) { return "ifadv-b200 0.1 (sm_100a)"; }
@@ -386,6 +390,8 @@ int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int dev
   for (auto& p : c->w) p = nullptr;
   c->pin_f = c->pin_u = c->pin_ru = nullptr;
   c->own_stream = nullptr;
+  c->pipe = nullptr;
+  c->host_h2d = c->host_d2h = 0; c->host_slabs = 0;
   c->prof_on = 0; c->prof_n = 0; c->prof_ev = nullptr; c->prof_tag = nullptr;
   for (int k = 0; k < 8; ++k) { c->prof_dir_ms[k] = 0.0; c->prof_dir_n[k] = 0; }
   {
@@ -414,6 +420,7 @@ int ifadv_destroy(ifadv_ctx* c) {
   if (c->pin_u) cudaFreeHost(c->pin_u);
   if (c->pin_ru) cudaFreeHost(c->pin_ru);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  host_pipe_free(c);
   if (c->prof_ev) { for (int k = 0; k < 2 * IFADV_PROF_MAX; ++k) cudaEventDestroy(c->prof_ev[k]); delete[] c->prof_ev; delete[] c->prof_tag; }
   delete c;
   return 0;
@@ -615,11 +622,195 @@ int ifadv_apply_vof_samples(ifadv_ctx* c, void* stream, void* f, void* alpha, vo
 
 // One CMOM advection step on host buffers (what bench.py's e2e leg times).  Work arrays (device):
 // w[0]=f w[1]=f⁰ w[2]=fᶠ w[3]=Φ w[4]=u w[5]=u⁰ w[6]=ρu w[7]=r w[8]=ρuf w[9]=dρ w[10]=c̄
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// z-slab pipeline of the host-buffer entry point: H2D of slab i+1, the advection step of slab i and D2H of slab i-1
+// run concurrently on three streams.  Every slab is the owned planes extended by HOST_W overlap planes per interior
+// side and is advanced by a child context of that shape through the unchanged device entry points; the artificial slab
+// ends contaminate at most 7 (lower) / 4 (upper) planes per advectfq!, which the overlap absorbs, so the
+// owned planes are bit-identical to the single-pass result (tests/test_gpu_parity.py::test_host_entry_pipelined).
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int HOST_W = 8;
+struct HostChunk {
+  int a, b;    // owned storage planes [a, b) (0-based; the first / last chunk also own the ghost plane of their physical end)
+  int lo, hi;  // storage planes [lo, hi) held by the child (including its two ghost planes)
+  ifadv_ctx* ctx;
+  cudaEvent_t ev_in, ev_cmp, ev_out;
+};
+struct HostPipe {
+  std::vector<HostChunk> ch;
+  int nset = 0;
+  void* w[3][11];
+  cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+};
+
+void host_pipe_free(ifadv_ctx* c) {
+  HostPipe* hp = (HostPipe*)c->pipe;
+  if (!hp) return;
+  for (auto& h : hp->ch) {
+    if (h.ctx) ifadv_destroy(h.ctx);
+    cudaEventDestroy(h.ev_in); cudaEventDestroy(h.ev_cmp); cudaEventDestroy(h.ev_out);
+  }
+  for (int k = 0; k < hp->nset; ++k)
+    for (auto& p : hp->w[k]) if (p) cudaFree(p);
+  if (hp->s_in) cudaStreamDestroy(hp->s_in);
+  if (hp->s_cmp) cudaStreamDestroy(hp->s_cmp);
+  if (hp->s_out) cudaStreamDestroy(hp->s_out);
+  delete hp;
+  c->pipe = nullptr;
+}
+
+// planes per slab: IFADV_HOST_CHUNK (0 = single pass); default: a quarter of the interior planes for grids of >= 256 planes
+int host_chunk_planes(const ifadv_ctx* c, unsigned perdir_mask) {
+  if (c->D != 3 || (perdir_mask & 4u)) return 0;  // a periodic z would need wrapped overlaps: single pass
+  const int NI = c->g.n[2] - 2;
+  const char* e = getenv("IFADV_HOST_CHUNK");
+  int cp = e ? atoi(e) : (NI >= 256 ? (NI + 3) / 4 : 0);
+  if (cp <= 0 || cp >= NI) return 0;
+  return cp;
+}
+
+int host_pipe_build(ifadv_ctx* c, int cp) {
+  HostPipe* hp = new HostPipe();
+  c->pipe = hp;
+  for (auto& set : hp->w) for (auto& p : set) p = nullptr;
+  const int n2 = c->g.n[2];
+  size_t maxpl = 0;
+  for (int a = 1; a < n2 - 1; a += cp) {
+    HostChunk h;
+    const int b = std::min(a + cp, n2 - 1);
+    h.lo = std::max(a - HOST_W, 1) - 1;       // child ghost plane below
+    h.hi = std::min(b + HOST_W, n2 - 1) + 1;  // child ghost plane above (exclusive end)
+    h.a = (a == 1) ? 0 : a;
+    h.b = (b == n2 - 1) ? n2 : b;
+    const int64_t ng[3] = {c->g.n[0], c->g.n[1], h.hi - h.lo};
+    h.ctx = nullptr;
+    CU_CHECK(c, cudaEventCreateWithFlags(&h.ev_in, cudaEventDisableTiming));
+    CU_CHECK(c, cudaEventCreateWithFlags(&h.ev_cmp, cudaEventDisableTiming));
+    CU_CHECK(c, cudaEventCreateWithFlags(&h.ev_out, cudaEventDisableTiming));
+    hp->ch.push_back(h);
+    if (ifadv_create(&hp->ch.back().ctx, 3, ng, c->dtype, c->device) != 0) { c->err = "child context creation failed"; return -3; }
+    hp->ch.back().ctx->use_march = c->use_march; hp->ch.back().ctx->use_along2 = c->use_along2;
+    maxpl = std::max(maxpl, (size_t)(h.hi - h.lo));
+  }
+  hp->nset = (int)std::min<size_t>(3, hp->ch.size());
+  const size_t es = (c->dtype == IFADV_F32) ? 4 : 8;
+  const size_t S = (size_t)c->g.s2 * maxpl, sb = es * S, vb = 3 * sb;
+  const size_t sz[11] = {sb, sb, sb, sb, vb, vb, vb, vb, vb, vb, S};
+  CU_CHECK(c, cudaStreamCreateWithFlags(&hp->s_in, cudaStreamNonBlocking));
+  CU_CHECK(c, cudaStreamCreateWithFlags(&hp->s_cmp, cudaStreamNonBlocking));
+  CU_CHECK(c, cudaStreamCreateWithFlags(&hp->s_out, cudaStreamNonBlocking));
+  for (int k = 0; k < hp->nset; ++k) {
+    for (int i = 0; i < 11; ++i) CU_CHECK(c, cudaMalloc(&hp->w[k][i], sz[i]));
+    // dρ keeps its constructor value 1 (cVOF.jl:74)
+    const long long n = (long long)S * 3;
+    if (c->dtype == IFADV_F32) fill_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, hp->s_cmp>>>((float*)hp->w[k][9], 1.f, n);
+    else fill_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, hp->s_cmp>>>((double*)hp->w[k][9], 1.0, n);
+    c->launches++;
+  }
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+int host_step_pipelined(ifadv_ctx* c, char* fh, const char* uh, char* rh, double dt, double lambda_rho, int limiter, int normal_scheme,
+                        const double uBC[3], unsigned perdir_mask, const int dirO[3], ifadv_report* report) {
+  HostPipe* hp = (HostPipe*)c->pipe;
+  const size_t es = (c->dtype == IFADV_F32) ? 4 : 8;
+  const size_t pl = es * (size_t)c->g.s2;  // bytes per plane
+  const size_t Sp = es * (size_t)c->g.S;   // bytes per parent component
+  const int nch = (int)hp->ch.size();
+  int64_t launches0 = 0;
+  for (auto& h : hp->ch) launches0 += h.ctx->launches;
+  c->host_h2d = c->host_d2h = 0; c->host_slabs = nch;
+  for (int i = 0; i < nch; ++i) {
+    HostChunk& h = hp->ch[i];
+    void** w = hp->w[i % hp->nset];
+    void *f = w[0], *f0 = w[1], *ff = w[2], *Phi = w[3], *u = w[4], *u0 = w[5], *ru = w[6], *r = w[7], *ruf = w[8], *drho = w[9];
+    int8_t* cbar = (int8_t*)w[10];
+    const size_t npl = (size_t)(h.hi - h.lo), Sc = pl * npl;  // child planes, bytes per child component
+    // H2D: the buffer set is free once the slab that used it before has been copied out
+    if (i >= hp->nset) CU_CHECK(c, cudaStreamWaitEvent(hp->s_in, hp->ch[i - hp->nset].ev_out, 0));
+    CU_CHECK(c, cudaMemcpyAsync(f, fh + pl * h.lo, Sc, cudaMemcpyHostToDevice, hp->s_in));
+    for (int d = 0; d < 3; ++d)
+      CU_CHECK(c, cudaMemcpyAsync((char*)u + Sc * d, uh + Sp * d + pl * h.lo, Sc, cudaMemcpyHostToDevice, hp->s_in));
+    CU_CHECK(c, cudaEventRecord(h.ev_in, hp->s_in));
+    c->host_h2d += (int64_t)(4 * Sc);
+    // the step of this slab (same sequence as the single-pass entry)
+    CU_CHECK(c, cudaStreamWaitEvent(hp->s_cmp, h.ev_in, 0));
+    CU_CHECK(c, cudaMemcpyAsync(u0, u, 3 * Sc, cudaMemcpyDeviceToDevice, hp->s_cmp));
+    int rc;
+    if ((rc = ifadv_u2rhou_advect_vof_rhouu(h.ctx, hp->s_cmp, f, f0, ff, Phi, u0, u, dt, cbar, ru, r, ruf, u, drho, lambda_rho, limiter,
+                                            normal_scheme, uBC, perdir_mask, dirO, nullptr)) < 0) { c->err = h.ctx->err; return rc; }
+    if ((rc = ifadv_axpby(h.ctx, hp->s_cmp, f0, 0.5, f0, 0.5, f))) { c->err = h.ctx->err; return rc; }
+    CU_CHECK(c, cudaMemcpyAsync(f0, f, Sc, cudaMemcpyDeviceToDevice, hp->s_cmp));
+    if ((rc = ifadv_u2rhou_advect_vof_rhouu(h.ctx, hp->s_cmp, f, f, ff, Phi, u, u, dt, cbar, ru, r, ruf, u0, drho, lambda_rho, limiter,
+                                            normal_scheme, uBC, perdir_mask, dirO, nullptr)) < 0) { c->err = h.ctx->err; return rc; }
+    if (report) CU_CHECK(c, cudaMemcpyAsync(h.ctx->red_host, h.ctx->red_dev, sizeof(unsigned long long) * 24, cudaMemcpyDeviceToHost, hp->s_cmp));
+    CU_CHECK(c, cudaEventRecord(h.ev_cmp, hp->s_cmp));
+    // D2H of the owned planes
+    CU_CHECK(c, cudaStreamWaitEvent(hp->s_out, h.ev_cmp, 0));
+    const size_t off_c = pl * (size_t)(h.a - h.lo), nown = pl * (size_t)(h.b - h.a);
+    CU_CHECK(c, cudaMemcpyAsync(fh + pl * h.a, (char*)f + off_c, nown, cudaMemcpyDeviceToHost, hp->s_out));
+    for (int d = 0; d < 3; ++d)
+      CU_CHECK(c, cudaMemcpyAsync(rh + Sp * d + pl * h.a, (char*)ru + Sc * d + off_c, nown, cudaMemcpyDeviceToHost, hp->s_out));
+    CU_CHECK(c, cudaEventRecord(h.ev_out, hp->s_out));
+    c->host_d2h += (int64_t)(4 * nown);
+  }
+  CU_CHECK(c, cudaStreamSynchronize(hp->s_out));
+  CU_CHECK(c, cudaStreamSynchronize(hp->s_cmp));
+  int status = 0;
+  for (auto& h : hp->ch) c->launches += h.ctx->launches;
+  c->launches -= launches0;
+  if (report) {
+    // worst slab wins; extrema located in the overlap planes of a slab belong to the neighbour (or to the contaminated band) and are skipped
+    const double filltol = 100.0 * ((c->dtype == IFADV_F32) ? (double)std::numeric_limits<float>::epsilon() : std::numeric_limits<double>::epsilon());
+    report->status = 0; report->dir = -1; report->maxf = 0; report->minf = 0;
+    for (int k = 0; k < 3; ++k) report->argmax[k] = report->argmin[k] = 0;
+    bool have = false;
+    for (auto& h : hp->ch) {
+      ifadv_report r;
+      const int st = decode_report(h.ctx, dirO, filltol, &r);
+      if (st < 0) { *report = r; report->argmax[2] += h.lo; report->argmin[2] += h.lo; return st; }
+      auto owned = [&](int64_t z) { const int64_t p = z - 1 + h.lo; return p >= h.a && p < h.b; };
+      int s2 = 0;
+      if ((st & 1) && owned(r.argmax[2])) s2 |= 1;
+      if ((st & 2) && owned(r.argmin[2])) s2 |= 2;
+      if (!have || s2 != 0) {
+        const int keep = report->status;
+        *report = r; report->argmax[2] += h.lo; report->argmin[2] += h.lo;
+        report->status = keep | s2;
+        have = true;
+      }
+      status |= s2;
+    }
+    report->status = status;
+  }
+  return status;
+}
+}  // namespace
+
+extern "C" {
+
 int ifadv_mom_advect_step_host(ifadv_ctx* c, void* f_host, const void* u_host, void* rhou_host, double dt, double lambda_rho, int limiter,
                                int normal_scheme, const double uBC[3], unsigned perdir_mask, const int dirO[3], ifadv_report* report) {
   if (!c || !f_host || !u_host || !rhou_host || !uBC || !dirO) return -2;
   const size_t es = esize(c->dtype), sb = es * c->g.S, vb = sb * c->D;
   CU_CHECK(c, cudaSetDevice(c->device));
+  // large 3-D grids: z-slab pipeline (copies overlap the kernels); buffers must be page-locked for the copies to be asynchronous
+  if (const int cp = host_chunk_planes(c, perdir_mask)) {
+    auto pinned = [](const void* p) {
+      cudaPointerAttributes a;
+      if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+      return a.type == cudaMemoryTypeHost;
+    };
+    if (pinned(f_host) && pinned(u_host) && pinned(rhou_host)) {
+      if (!c->pipe) { const int rb = host_pipe_build(c, cp); if (rb != 0) { host_pipe_free(c); return rb; } }
+      return host_step_pipelined(c, (char*)f_host, (const char*)u_host, (char*)rhou_host, dt, lambda_rho, limiter, normal_scheme, uBC,
+                                 perdir_mask, dirO, report);
+    }
+  }
   if (!c->own_stream) CU_CHECK(c, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   cudaStream_t st = c->own_stream;
   if (!c->w[0]) {
@@ -667,9 +858,18 @@ int ifadv_mom_advect_step_host(ifadv_ctx* c, void* f_host, const void* u_host, v
   CU_CHECK(c, cudaMemcpyAsync(pf ? f_host : c->pin_f, f, sb, cudaMemcpyDeviceToHost, st));
   CU_CHECK(c, cudaMemcpyAsync(pr ? rhou_host : c->pin_ru, ru, vb, cudaMemcpyDeviceToHost, st));
   CU_CHECK(c, cudaStreamSynchronize(st));
+  c->host_h2d = (int64_t)(sb + vb); c->host_d2h = (int64_t)(sb + vb); c->host_slabs = 1;
   if (!pf) memcpy(f_host, c->pin_f, sb);
   if (!pr) memcpy(rhou_host, c->pin_ru, vb);
   return rc;
+}
+
+int ifadv_host_step_bytes(const ifadv_ctx* c, int64_t* h2d, int64_t* d2h, int* slabs) {
+  if (!c) return -2;
+  if (h2d) *h2d = c->host_h2d;
+  if (d2h) *d2h = c->host_d2h;
+  if (slabs) *slabs = c->host_slabs;
+  return 0;
 }
 
 }  // extern "C"

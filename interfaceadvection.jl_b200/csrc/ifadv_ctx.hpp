@@ -26,6 +26,9 @@ struct ifadv_ctx {
   void* pin_u;
   void* pin_ru;
   cudaStream_t own_stream;
+  void* pipe;  // z-slab pipeline of the host-buffer entry point (HostPipe, ifadv_b200.cu), built lazily
+  int64_t host_h2d, host_d2h;  // bytes the last ifadv_mom_advect_step_host call copied in / out
+  int host_slabs;              // z-slabs it was pipelined over (1 = single pass)
   // optional per-launch CUDA-event timing of the fused sweep (ifadv_profile)
   int use_march;  // 1: register-marching (y,z) + plane-marching (x) kernels (default); 2: plane-marching only; 0: v1 tile kernel
   int use_along2;  // 1 (default): lean register-marching kernel ifadv_along2.cuh for y/z sweeps; 0: ifadv_along.cuh

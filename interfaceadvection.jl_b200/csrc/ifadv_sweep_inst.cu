@@ -266,15 +266,20 @@ template <class T, bool MOM> int launch_fam_along(ifadv_ctx* c, cudaStream_t st,
 template int launch_fam_along<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
 
 #elif IFADV_FAM == 3
+#ifndef IFADV_XP_A2CPT
+#define IFADV_XP_A2CPT 2
+#define IFADV_XP_A2MB 2
+#endif
 template <class T, bool MOM> int launch_fam_along2(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
-  constexpr int CP = (sizeof(T) == 4) ? 2 : 1;
+  constexpr int CP = (sizeof(T) == 4) ? IFADV_XP_A2CPT : 1;
+  constexpr int MBX = (sizeof(T) == 4) ? IFADV_XP_A2MB : 2;
   const bool koren = !MOM || q.lim == 2;  // the package default limiter is compiled in; the others go through limiter_other
   if (MOM && q.fused) {
-    if (q.j == 1) return koren ? launch_along2_t<T, 1, CP, MOM, MOM, true, 2>(c, st, q) : launch_along2_t<T, 1, CP, MOM, MOM, !MOM, 2>(c, st, q);
-    return koren ? launch_along2_t<T, 2, CP, MOM, MOM, true, 2>(c, st, q) : launch_along2_t<T, 2, CP, MOM, MOM, !MOM, 2>(c, st, q);
+    if (q.j == 1) return koren ? launch_along2_t<T, 1, CP, MOM, MOM, true, MBX>(c, st, q) : launch_along2_t<T, 1, CP, MOM, MOM, !MOM, MBX>(c, st, q);
+    return koren ? launch_along2_t<T, 2, CP, MOM, MOM, true, MBX>(c, st, q) : launch_along2_t<T, 2, CP, MOM, MOM, !MOM, MBX>(c, st, q);
   }
-  if (q.j == 1) return koren ? launch_along2_t<T, 1, CP, MOM, false, true, 2>(c, st, q) : launch_along2_t<T, 1, CP, MOM, false, !MOM, 2>(c, st, q);
-  return koren ? launch_along2_t<T, 2, CP, MOM, false, true, 2>(c, st, q) : launch_along2_t<T, 2, CP, MOM, false, !MOM, 2>(c, st, q);
+  if (q.j == 1) return koren ? launch_along2_t<T, 1, CP, MOM, false, true, MBX>(c, st, q) : launch_along2_t<T, 1, CP, MOM, false, !MOM, MBX>(c, st, q);
+  return koren ? launch_along2_t<T, 2, CP, MOM, false, true, MBX>(c, st, q) : launch_along2_t<T, 2, CP, MOM, false, !MOM, MBX>(c, st, q);
 }
 template int launch_fam_along2<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
 

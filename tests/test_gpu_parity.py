@@ -391,3 +391,37 @@ def test_tiny_and_ragged_grids(ia, N, perdir):
     ia.mom_advect_step(flow, intf, 1.0)
     assert np.abs(ia.to_numpy(intf.f) - f_o).max() <= 1e-12
     assert np.abs(inside(ia.to_numpy(intf.rhou), D) - inside(ru_o, D)).max() <= 1e-12
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("N,chunk", [((16, 12, 40), 8), ((12, 10, 37), 16), ((8, 8, 20), 3)])
+def test_host_entry_pipelined(ia, T, N, chunk, monkeypatch):
+    """The z-slab pipeline of ifadv_mom_advect_step_host (H2D / step / D2H of consecutive slabs overlap; 8 overlap planes per
+    artificial slab end) returns exactly what the single-pass entry returns, and both match the oracle."""
+    st = make_state(N, "C3", T, perdir=(1,))
+    f_o = st["f"].copy(order="F")
+    ru_o = oracle_mom_advect_step(st, f_o, st["u"], 1.0, (2, 3, 1))
+    TT = getattr(torch, np.dtype(T).name)
+
+    def pinned_like(a):
+        t = torch.empty(a.size, dtype=TT, pin_memory=True)
+        v = t.numpy().reshape(a.shape, order="F")
+        v[...] = a
+        return t, v
+
+    out = {}
+    for mode, env in (("single", "0"), ("pipelined", str(chunk))):
+        monkeypatch.setenv("IFADV_HOST_CHUNK", env)
+        ft, fv = pinned_like(st["f"]); ut, uv = pinned_like(st["u"]); rt, rv = pinned_like(np.zeros_like(st["u"]))
+        ctx = ia.Context(st["Ng"], np.dtype(T).name, 0)
+        rep = ia.Report()
+        rc = ctx.mom_advect_step_host(ft.data_ptr(), ut.data_ptr(), rt.data_ptr(), 1.0, st["lam_rho"], ia.LIMITERS["Koren"],
+                                      ia.NORMAL_SCHEMES["WH"], st["uBC"], st["perdir"], (2, 3, 1), rep)
+        assert rc == 0, mode
+        assert ctx.launches > 0
+        out[mode] = (fv.copy(), inside(rv, 3).copy(), ctx.launches)
+    assert out["pipelined"][2] > out["single"][2]  # several slabs were launched
+    assert np.array_equal(out["single"][0], out["pipelined"][0])
+    assert np.array_equal(out["single"][1], out["pipelined"][1])
+    assert np.abs(out["pipelined"][0] - f_o).max() <= TOL[T]
+    assert np.abs(out["pipelined"][1] - inside(ru_o, 3)).max() <= TOL[T]
