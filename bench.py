@@ -311,7 +311,7 @@ def run_b200(args):
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": traffic, "kernel": "ifadv::along_kernel / ifadv::march_kernel (fused VOF+CMOM directional sweep, standard 13s+1 B/cell form)", "peak_source": peak_src,
+                "traffic": traffic, "kernel": "ifadv::along2_kernel (y, z) / ifadv::xsweep_kernel (x): fused VOF+CMOM directional sweep, standard 13s+1 B/cell form, average over the three directions", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_launch, "avg_launch_ms": avg_ms, "launches_timed": kn,
                 "sweep_share_of_step": ((kms + fms) / ms) if ms else None, "fused_first_sweep": fused_info,
                 "ms_per_launch_by_direction": per_dir,

@@ -425,3 +425,21 @@ def test_host_entry_pipelined(ia, T, N, chunk, monkeypatch):
     assert np.array_equal(out["single"][1], out["pipelined"][1])
     assert np.abs(out["pipelined"][0] - f_o).max() <= TOL[T]
     assert np.abs(out["pipelined"][1] - inside(ru_o, 3)).max() <= TOL[T]
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("Ng", [(7, 5, 3), (18, 14, 12), (9, 7)])
+def test_axpby_midpoint(ia, T, Ng):
+    """f⁰ = (f⁰+f)/2 (flow.jl:74) and the general a*x+b*y form, vector body + scalar tail, in place and out of place."""
+    rng = np.random.default_rng(20261017)
+    x = np.asfortranarray(rng.random(Ng).astype(T)); y = np.asfortranarray(rng.random(Ng).astype(T))
+    ctx = ia.context_for(ia.from_numpy(x))
+    xd, yd = ia.from_numpy(x), ia.from_numpy(y)
+    od = ia.from_numpy(np.zeros_like(x))
+    s = torch.cuda.current_stream().cuda_stream
+    ctx.axpby(s, od.data_ptr(), 0.5, xd.data_ptr(), 0.5, yd.data_ptr())
+    assert np.array_equal(ia.to_numpy(od), (x + y) * T(0.5))
+    ctx.axpby(s, od.data_ptr(), 0.25, xd.data_ptr(), 2.0, yd.data_ptr())
+    assert np.allclose(ia.to_numpy(od), T(0.25) * x + T(2.0) * y, rtol=4 * np.finfo(T).eps, atol=0)
+    ctx.axpby(s, xd.data_ptr(), 0.5, xd.data_ptr(), 0.5, yd.data_ptr())  # in place, as MPFMomStep! uses it
+    assert np.array_equal(ia.to_numpy(xd), (x + y) * T(0.5))
