@@ -133,6 +133,13 @@ int ifadv_sum_inside(ifadv_ctx* ctx, void* stream, const void* f, double* out);
 int ifadv_apply_vof_samples(ifadv_ctx* ctx, void* stream, void* f, void* alpha, void* nhat, const void* sc, const void* sp,
                             const void* sm);
 
+/* Stream overlap aid for MPFMomStep! (src/flow.jl:74,89): the midpoint f⁰=(f⁰+f)/2 and the copy f⁰<-f only READ the f that the
+ * corrector's advectfq! is about to advance, and that call does not write f before its last directional sweep.  A caller that
+ * runs those two field operations on a second stream records an event behind them and passes it here; the NEXT
+ * ifadv_advect_vof_rhouu / ifadv_u2rhou_advect_vof_rhouu call on this context then inserts cudaStreamWaitEvent(stream, event)
+ * before its first write to f (one-shot).  event: cudaEvent_t. */
+int ifadv_defer_f_writes_until(ifadv_ctx* ctx, void* event);
+
 /* ---- host-buffer convenience (what bench.py's e2e leg times) --------------------------------------------- */
 /* One CMOM advection step of MPFMomStep! on HOST arrays (flow.jl:61,69-70,74,89-92 with the forcing and
  * projection left out: velocities are prescribed): copies f,u to the device, runs

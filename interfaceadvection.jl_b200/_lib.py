@@ -60,6 +60,7 @@ def lib():
         L.ifadv_apply_vof_samples.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
         L.ifadv_mom_advect_step_host.argtypes = [vp, vp, vp, vp, dbl, dbl, i32, i32, dblp, u32, i32p, rep]
         L.ifadv_host_step_bytes.argtypes = [vp, i64p, i64p, i32p]
+        L.ifadv_defer_f_writes_until.argtypes = [vp, vp]
         _lib = L
     return _lib
 
@@ -183,6 +184,10 @@ class Context:
 
     def apply_vof_samples(self, stream, f, alpha, nhat, sc, sp, sm):
         return self._chk(lib().ifadv_apply_vof_samples(self._h, stream, f, alpha, nhat, sc, sp, sm))
+
+    def defer_f_writes_until(self, event):
+        """One-shot: the next CMOM advect call waits for `event` (cudaEvent_t handle) before its first write to f."""
+        return self._chk(lib().ifadv_defer_f_writes_until(self._h, event))
 
     def host_step_bytes(self):
         """(h2d_bytes, d2h_bytes, slabs) of the last mom_advect_step_host call (ifadv_host_step_bytes)."""

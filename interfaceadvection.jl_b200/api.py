@@ -320,12 +320,44 @@ def u2rhou_advectfq(a: Flow, c: cVOF, f_src, f, u1, u2, uOld, dt=None, check=Fal
     return _report(st, rep) if check else st
 
 
-def mom_advect_step(a: Flow, c: cVOF, dt=None, project: Optional[Callable] = None, check=False, fused=True):
+_side_streams = {}
+
+
+def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
+    key = dev.index or 0
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=dev)
+    return _side_streams[key]
+
+
+def mom_advect_step(a: Flow, c: cVOF, dt=None, project: Optional[Callable] = None, check=False, fused=True, overlap=True):
     """The transport half of MPFMomStep! (src/flow.jl:61,69-70,74,89-92): two u2ρu!+BC!+advectfq! groups and the
     midpoint f⁰.  This is one "advection step" of the benchmark metric; MPCFL is separate.
-    fused=True issues each group through the fused entry point (same results bit for bit, fewer passes)."""
+    fused=True issues each group through the fused entry point (same results bit for bit, fewer passes).
+    overlap=True (only without a `project` hook, i.e. with prescribed velocities): the three bandwidth-bound field operations
+    of the step run on a second stream underneath the issue-bound sweeps -- u⁰←u (:61) beside the predictor, which reads u for
+    both velocity arguments (u⁰≡u at that point), and the midpoint (:74) + f⁰←f (:89) beside the first two sweeps of the
+    corrector, which does not write f before its last sweep (ifadv_defer_f_writes_until).  Same operations, same results."""
     dt = a.dt[-1] if dt is None else dt
     ctx, s = context_for(c.f), _stream(c.f)
+    if overlap and fused and project is None:
+        main = torch.cuda.current_stream(c.f.device)
+        side = _side_stream(c.f.device)
+        side.wait_stream(main)                                        # u and f are final on the main stream
+        with torch.cuda.stream(side):
+            _copy(a.u0, a.u)                                          # :61
+            ev_u0 = side.record_event()
+        u2rhou_advectfq(a, c, c.f, c.f0, a.u, a.u, a.u, dt, check=check)    # :61 (f⁰←f), :69, :70 with u⁰≡u
+        ev_g1 = main.record_event()
+        with torch.cuda.stream(side):
+            side.wait_event(ev_g1)
+            ctx.axpby(side.cuda_stream, _p(c.f0), 0.5, _p(c.f0), 0.5, _p(c.f))  # :74
+            _copy(c.f0, c.f)                                          # :89
+            ev_f0 = side.record_event()
+        main.wait_event(ev_u0)                                        # the corrector reads u⁰ as uOld
+        ctx.defer_f_writes_until(ev_f0.cuda_event)
+        u2rhou_advectfq(a, c, c.f, c.f, a.u, a.u, a.u0, dt, check=check)    # :91, :92
+        return
     _copy(a.u0, a.u)                                                  # :61
     if fused:
         u2rhou_advectfq(a, c, c.f, c.f0, a.u0, a.u, a.u, dt, check=check)   # :61 (f⁰←f), :69, :70

@@ -320,8 +320,14 @@ static int advect_vof_rhouu_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* Phi
                               const int* dirO, ifadv_report* rep, const T* f_src = nullptr, int fused = 0) {
   const int D = c->D;
   c->g.per = per;
+  // ifadv_defer_f_writes_until: one-shot event this call waits for before its first write to f
+  cudaEvent_t wait_f = c->wait_f;
+  c->wait_f = nullptr;
   if (fused && (D == 2 || c->use_march == 0)) {
-    if (f_src && f_src != f) CU_CHECK(c, cudaMemcpyAsync(f, f_src, sizeof(T) * c->g.S, cudaMemcpyDeviceToDevice, st));
+    if (f_src && f_src != f) {
+      if (wait_f) { CU_CHECK(c, cudaStreamWaitEvent(st, wait_f, 0)); wait_f = nullptr; }
+      CU_CHECK(c, cudaMemcpyAsync(f, f_src, sizeof(T) * c->g.S, cudaMemcpyDeviceToDevice, st));
+    }
     int rc0 = u2rhou_t<T>(c, st, rhou, uOld, f, lr, true);
     if (rc0) return rc0;
     if ((rc0 = bcvec_t<T>(c, st, rhou, uBC, 0, per))) return rc0;
@@ -341,6 +347,7 @@ static int advect_vof_rhouu_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* Phi
     q.fused = (s == 0) ? fused : 0;
     for (int i = 0; i < 3; ++i) q.A[i] = (i < D) ? uBC[i] : 0.0;
     q.red = c->red_dev + 8 * s;
+    if (s == D - 1 && wait_f) CU_CHECK(c, cudaStreamWaitEvent(st, wait_f, 0));  // the last sweep is the first to write f
     int rc = launch_sweep<T, true>(c, st, q);
     if (rc) return rc;
   }
@@ -424,6 +431,7 @@ int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int dev
   c->pin_f = c->pin_u = c->pin_ru = nullptr;
   c->own_stream = nullptr;
   c->pipe = nullptr;
+  c->wait_f = nullptr;
   c->host_h2d = c->host_d2h = 0; c->host_slabs = 0;
   c->prof_on = 0; c->prof_n = 0; c->prof_ev = nullptr; c->prof_tag = nullptr;
   for (int k = 0; k < 8; ++k) { c->prof_dir_ms[k] = 0.0; c->prof_dir_n[k] = 0; }
@@ -895,6 +903,12 @@ int ifadv_mom_advect_step_host(ifadv_ctx* c, void* f_host, const void* u_host, v
   if (!pf) memcpy(f_host, c->pin_f, sb);
   if (!pr) memcpy(rhou_host, c->pin_ru, vb);
   return rc;
+}
+
+int ifadv_defer_f_writes_until(ifadv_ctx* c, void* event) {
+  if (!c) return -2;
+  c->wait_f = (cudaEvent_t)event;
+  return 0;
 }
 
 int ifadv_host_step_bytes(const ifadv_ctx* c, int64_t* h2d, int64_t* d2h, int* slabs) {

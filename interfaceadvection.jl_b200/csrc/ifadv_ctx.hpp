@@ -26,6 +26,7 @@ struct ifadv_ctx {
   void* pin_u;
   void* pin_ru;
   cudaStream_t own_stream;
+  cudaEvent_t wait_f;  // one-shot: the next CMOM advect call waits for it before its first write to f (ifadv_defer_f_writes_until)
   void* pipe;  // z-slab pipeline of the host-buffer entry point (HostPipe, ifadv_b200.cu), built lazily
   int64_t host_h2d, host_d2h;  // bytes the last ifadv_mom_advect_step_host call copied in / out
   int host_slabs;              // z-slabs it was pipelined over (1 = single pass)

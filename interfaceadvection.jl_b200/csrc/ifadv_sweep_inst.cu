@@ -270,9 +270,12 @@ template int launch_fam_along<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_
 #define IFADV_XP_A2CPT 2
 #define IFADV_XP_A2MB 2
 #endif
+#ifndef IFADV_XP_A2MB64
+#define IFADV_XP_A2MB64 1  // Float64: 196 registers without spills at 1 CTA/SM beats 128 registers + 58 spilled at 2 CTAs/SM (+5 %)
+#endif
 template <class T, bool MOM> int launch_fam_along2(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   constexpr int CP = (sizeof(T) == 4) ? IFADV_XP_A2CPT : 1;
-  constexpr int MBX = (sizeof(T) == 4) ? IFADV_XP_A2MB : 2;
+  constexpr int MBX = (sizeof(T) == 4) ? IFADV_XP_A2MB : IFADV_XP_A2MB64;
   const bool koren = !MOM || q.lim == 2;  // the package default limiter is compiled in; the others go through limiter_other
   if (MOM && q.fused) {
     if (q.j == 1) return koren ? launch_along2_t<T, 1, CP, MOM, MOM, true, MBX>(c, st, q) : launch_along2_t<T, 1, CP, MOM, MOM, !MOM, MBX>(c, st, q);

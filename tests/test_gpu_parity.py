@@ -443,3 +443,25 @@ def test_axpby_midpoint(ia, T, Ng):
     assert np.allclose(ia.to_numpy(od), T(0.25) * x + T(2.0) * y, rtol=4 * np.finfo(T).eps, atol=0)
     ctx.axpby(s, xd.data_ptr(), 0.5, xd.data_ptr(), 0.5, yd.data_ptr())  # in place, as MPFMomStep! uses it
     assert np.array_equal(ia.to_numpy(xd), (x + y) * T(0.5))
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+def test_overlapped_step_equals_sequential(ia, T):
+    """mom_advect_step with the field copies / midpoint on a second stream (overlap=True, the default without a projection hook)
+    returns bit for bit what the strictly sequential order of MPFMomStep! returns -- f, f⁰, u⁰ and ρu -- over several steps."""
+    st = make_state((40, 24, 20), "C3", T, perdir=(2,))
+    TT = getattr(torch, np.dtype(T).name)
+    res = {}
+    for ov in (False, True):
+        flow = ia.Flow(st["N"], st["uBC"], T=TT, dt=1.0, perdir=st["perdir"])
+        intf = ia.cVOF(st["N"], T=TT, lam_rho=st["lam_rho"], perdir=st["perdir"])
+        flow.u.copy_(ia.from_numpy(st["u"])); intf.f.copy_(ia.from_numpy(st["f"]))
+        flow.u0.zero_()  # stale on purpose: the step has to refresh it (flow.jl:61)
+        for n in range(3):
+            ia.mom_advect_step(flow, intf, 1.0, overlap=ov)
+            flow.dt.append(1.0)
+            flow.u.mul_(0.9)  # a changing velocity between steps, as a projection would leave it
+        torch.cuda.synchronize()
+        res[ov] = [ia.to_numpy(x) for x in (intf.f, intf.f0, flow.u0, intf.rhou)]
+    for x, y in zip(res[False], res[True]):
+        assert np.array_equal(x, y)
