@@ -342,7 +342,7 @@ def run_b200(args):
             "dtype": "f32" if dtype == "float32" else "f64", "data": "synthetic",
             "config": {"workload": wl, "grid_per_gpu": list(N), "global_grid": [N[0], N[1], N[2] * world] if D == 3 else list(N),
                        "perdir": list(perdir), "limiter": "Koren", "normal_scheme": "WH", "lambda_rho": 1e-3,
-                       "step": "CMOM advection step = 2 x (u2rhou + BC + advectfq) + midpoint f0 = 6 fused sweeps (u2rhou+BC folded into the first sweep of each group)",
+                       "step": "CMOM advection step = 2 x (u2rhou + BC + advectfq) + midpoint f0 = 6 fused sweeps (u2rhou+BC folded into the first sweep of each group); the u0<-u / f0<-f copies and the midpoint run on a second stream underneath the sweeps",
                        "l2": "working set >> 126 MB L2 (inputs larger than L2, no flush needed)",
                        "parallelism": f"z-slab x{world}" if world > 1 else "single GPU",
                        "mass_drift_rel": abs(m1 - m0) / abs(m0) if m0 else None},
@@ -411,9 +411,18 @@ def run_e2e_slabs(ia, torch, dist, N, dtype, perdir, kind, dev, rank, world, ste
     g = r.geom
     Ngl = tuple(r.intf.f.shape)
     fdev = r.intf.f
-    fh = torch.empty(tuple(reversed(Ngl)), dtype=T, pin_memory=True)
-    uh = torch.empty((3,) + tuple(reversed(Ngl)), dtype=T, pin_memory=True)
-    rh = torch.empty((3,) + tuple(reversed(Ngl)), dtype=T, pin_memory=True)
+    # every rank pins 7 fields of its slab (~4 GB at 512^3): if one rank cannot, all ranks skip the leg together
+    ok = torch.ones(1, device=dev)
+    try:
+        fh = torch.empty(tuple(reversed(Ngl)), dtype=T, pin_memory=True)
+        uh = torch.empty((3,) + tuple(reversed(Ngl)), dtype=T, pin_memory=True)
+        rh = torch.empty((3,) + tuple(reversed(Ngl)), dtype=T, pin_memory=True)
+    except Exception as e:  # noqa: BLE001
+        print(f"[bench] rank {rank}: cannot pin the host buffers of the e2e leg: {e}", file=sys.stderr)
+        ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if ok.item() == 0:
+        return None
     fh.copy_(fdev.permute(2, 1, 0)); uh.copy_(r.flow.u.permute(3, 2, 1, 0))
     lperdir = r.perdir
     del r.flow, r.intf.rhou, r.intf.rhouf
