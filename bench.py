@@ -41,7 +41,12 @@ WORKLOADS = {
     "C4_bubble_256_f64": ((256, 256, 256), "float64", (1, 2), "C4"),
     "C4_bubble_128_f32": ((128, 128, 128), "float32", (1, 2), "C4"),
     "C4_bubble_64_f32": ((64, 64, 64), "float32", (1, 2), "C4"),
+    # pure-VOF configs (one step = advect! = D directional sweeps): reported for completeness, single GPU, no e2e / CPU legs
+    "C2_enright_256_f32": ((256, 256, 256), "float32", (), "C2"),
+    "C2_enright_256_f64": ((256, 256, 256), "float64", (), "C2"),
+    "C1_zalesak_128_f64": ((128, 128), "float64", (), "C1"),
 }
+VOF_KINDS = ("C1", "C2")
 CPU_SAMPLE = "C4_bubble_128_f32"  # bounded sample of the same workload for the CPU legs
 
 
@@ -52,6 +57,14 @@ def algorithmic_bytes_per_cell_sweep(D, s):
 def algorithmic_bytes_per_cell_step(D, s):
     # 2 x [D sweeps + c̄ write + u2ρu! (2D+1)s]
     return 2 * (D * algorithmic_bytes_per_cell_sweep(D, s) + 1 + (2 * D + 1) * s)
+
+
+def vof_bytes_per_cell_sweep(D, s):
+    return 4 * s + 1  # reads f,u_d,u⁰_d,c̄ ; writes f   (the optional ρuf[·,d] output of advect! adds s)
+
+
+def vof_bytes_per_cell_step(D, s):
+    return D * vof_bytes_per_cell_sweep(D, s) + 1
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -218,6 +231,11 @@ def run_b200(args):
     D = len(N)
     T = getattr(torch, dtype)
     s = 4 if dtype == "float32" else 8
+    vof = kind in VOF_KINDS
+    if vof:
+        if world > 1:
+            raise SystemExit("the pure-VOF workloads are single-GPU report lines")
+        args.no_e2e = args.no_cpu = True
 
     if world > 1:
         from interfaceadvection.jl_b200 import slab
@@ -228,6 +246,7 @@ def run_b200(args):
                                     dt=1.0, device=dev)
         sim.flow.u.copy_(case["u"])
         ia.BC(sim.flow.u, (0,) * D, False, perdir)
+        sim.flow.u0.copy_(sim.flow.u)
         del case
         ctx = ia.context_for(sim.intf.f)
 
@@ -236,7 +255,10 @@ def run_b200(args):
                 self.n = 0
 
             def step(self):
-                ia.mom_advect_step(sim.flow, sim.intf, 1.0)
+                if vof:
+                    ia.advect(sim.flow, sim.intf, check=False)  # advect!(a,c): pure VOF with u⁰, u (advection.jl:17-23)
+                else:
+                    ia.mom_advect_step(sim.flow, sim.intf, 1.0)
                 sim.flow.dt.append(1.0)  # fixed Δt; advances the sweep-order rotation like push!(Δt) would
 
             contexts = [ctx]
@@ -296,7 +318,7 @@ def run_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
-    bytes_launch = algorithmic_bytes_per_cell_sweep(D, s) * cells_gpu
+    bytes_launch = (vof_bytes_per_cell_sweep(D, s) if vof else algorithmic_bytes_per_cell_sweep(D, s)) * cells_gpu
     avg_ms = kms / max(kn, 1)
     achieved = bytes_launch / (avg_ms * 1e-3) / 1e9 if kn else None
     # fused first sweeps (u2rhou + BC folded in): 3 fewer input streams -> (2D+4)s+1 B per cell
@@ -315,7 +337,11 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch": bytes_launch, "avg_launch_ms": avg_ms, "launches_timed": kn,
                 "sweep_share_of_step": ((kms + fms) / ms) if ms else None, "fused_first_sweep": fused_info,
                 "ms_per_launch_by_direction": per_dir,
-                "step_frac_of_roofline": (algorithmic_bytes_per_cell_step(D, s) * cells_gpu / (ms / args.steps * 1e-3) / 1e9) / peak}
+                "step_frac_of_roofline": ((vof_bytes_per_cell_step(D, s) if vof else algorithmic_bytes_per_cell_step(D, s)) * cells_gpu
+                                          / (ms / args.steps * 1e-3) / 1e9) / peak}
+    if vof:
+        roofline["kernel"] = "fused pure-VOF directional sweep (ifadv::along2_kernel y/z, ifadv::march_kernel x; 2-D: ifadv::sweep_kernel), 4s+1 B/cell"
+        roofline["fused_first_sweep"] = None
 
     # ---- e2e: the reference-facing C-ABI call with HOST buffers (H2D/D2H inside the timed region) ----
     e2e = None
@@ -342,7 +368,7 @@ def run_b200(args):
             "dtype": "f32" if dtype == "float32" else "f64", "data": "synthetic",
             "config": {"workload": wl, "grid_per_gpu": list(N), "global_grid": [N[0], N[1], N[2] * world] if D == 3 else list(N),
                        "perdir": list(perdir), "limiter": "Koren", "normal_scheme": "WH", "lambda_rho": 1e-3,
-                       "step": "CMOM advection step = 2 x (u2rhou + BC + advectfq) + midpoint f0 = 6 fused sweeps (u2rhou+BC folded into the first sweep of each group); the u0<-u / f0<-f copies and the midpoint run on a second stream underneath the sweeps",
+                       "step": "pure-VOF advection step = advect! = D fused sweeps" if vof else "CMOM advection step = 2 x (u2rhou + BC + advectfq) + midpoint f0 = 6 fused sweeps (u2rhou+BC folded into the first sweep of each group); the u0<-u / f0<-f copies and the midpoint run on a second stream underneath the sweeps",
                        "l2": "working set >> 126 MB L2 (inputs larger than L2, no flush needed)",
                        "parallelism": f"z-slab x{world}" if world > 1 else "single GPU",
                        "mass_drift_rel": abs(m1 - m0) / abs(m0) if m0 else None},
