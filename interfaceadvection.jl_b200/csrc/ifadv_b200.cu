@@ -140,45 +140,64 @@ template <class T, bool VEC> __global__ void __launch_bounds__(256) axpby_kernel
   }
 }
 
-// MPCFL's two field reductions (flow.jl:267-271): max flux_out and max maxTotalFlux over inside(σ)
-template <class T, int D> __global__ void cfl_kernel(const T* u, const Geo g, unsigned long long* red) {
-  const int x = 2 + blockIdx.x * blockDim.x + threadIdx.x, y = 2 + blockIdx.y, z = (D == 3) ? 2 + blockIdx.z : 1;
+// Field reductions over inside(f): persistent grid, a warp walks whole x-rows (coalesced), per-lane partials, one atomic per CTA.
+// MPCFL's two reductions (flow.jl:267-271): max flux_out and max maxTotalFlux over inside(σ)
+template <class T, int D> __global__ void __launch_bounds__(256) cfl_kernel(const T* u, const Geo g, unsigned long long* red) {
+  const int ny = g.n[1] - 2, nz = (D == 3) ? g.n[2] - 2 : 1;
+  const long long rows = (long long)ny * nz;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   double fo = 0.0, tf = 0.0;
-  if (x <= g.n[0] - 1) {
-    const long long l = lin3(g, x, y, z);
-    T s2 = T(0);
+  for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * wpb) {
+    const int y = 2 + (int)(r % ny), z = (D == 3) ? 2 + (int)(r / ny) : 1;
+    const long long l0 = lin3(g, 0, y, z);
+    for (int x = 2 + lane; x <= g.n[0] - 1; x += 32) {
+      const long long l = l0 + x;
+      double f1 = 0.0;
+      T s2 = T(0);
 #pragma unroll
-    for (int i = 0; i < D; ++i) {
-      const long long sd = (i == 0) ? 1 : ((i == 1) ? g.s1 : g.s2);
-      const T ul = u[(long long)i * g.S + l], uh = u[(long long)i * g.S + l + sd];
-      fo += fmax(0.0, (double)uh) + fmax(0.0, -(double)ul);  // `max(0.,…)` promotes in WaterLily's flux_out
-      s2 += t_max(t_abs(ul), t_abs(uh));
+      for (int i = 0; i < D; ++i) {
+        const long long sd = (i == 0) ? 1 : ((i == 1) ? g.s1 : g.s2);
+        const T ul = u[(long long)i * g.S + l], uh = u[(long long)i * g.S + l + sd];
+        f1 += fmax(0.0, (double)uh) + fmax(0.0, -(double)ul);  // `max(0.,…)` promotes in WaterLily's flux_out
+        s2 += t_max(t_abs(ul), t_abs(uh));
+      }
+      fo = fmax(fo, (double)(T)f1);  // stored into σ::T before maximum()
+      tf = fmax(tf, (double)s2);
     }
-    fo = (double)(T)fo;  // stored into σ::T before maximum()
-    tf = (double)s2;
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     fo = fmax(fo, __shfl_xor_sync(0xffffffffu, fo, off));
     tf = fmax(tf, __shfl_xor_sync(0xffffffffu, tf, off));
   }
-  if ((threadIdx.x & 31) == 0) {
+  __shared__ double w0[8], w1[8];
+  if (lane == 0) { w0[threadIdx.x >> 5] = fo; w1[threadIdx.x >> 5] = tf; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < wpb; ++w) { fo = fmax(fo, w0[w]); tf = fmax(tf, w1[w]); }
     atomicMax(red + 0, ord_key(fo));
     atomicMax(red + 1, ord_key(tf));
   }
 }
 
-template <class T, int D> __global__ void sum_inside_kernel(const T* f, const Geo g, double* out) {
-  const int x = 2 + blockIdx.x * blockDim.x + threadIdx.x, y = 2 + blockIdx.y, z = (D == 3) ? 2 + blockIdx.z : 1;
-  double s = (x <= g.n[0] - 1) ? (double)f[lin3(g, x, y, z)] : 0.0;
+template <class T, int D> __global__ void __launch_bounds__(256) sum_inside_kernel(const T* f, const Geo g, double* out) {
+  const int ny = g.n[1] - 2, nz = (D == 3) ? g.n[2] - 2 : 1;
+  const long long rows = (long long)ny * nz;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  double s = 0.0;
+  for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * wpb) {
+    const int y = 2 + (int)(r % ny), z = (D == 3) ? 2 + (int)(r / ny) : 1;
+    const long long l0 = lin3(g, 0, y, z);
+    for (int x = 2 + lane; x <= g.n[0] - 1; x += 32) s += (double)f[l0 + x];
+  }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-  __shared__ double ws[32];
-  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __shared__ double ws[8];
+  if (lane == 0) ws[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += ws[w];
+    for (int w = 0; w < wpb; ++w) t += ws[w];
     atomicAdd(out, t);
   }
 }
@@ -591,8 +610,9 @@ int ifadv_mpcfl(ifadv_ctx* c, void* stream, const void* u, double nu, double mu,
   if (!c || !u || !dt_out) return -2;
   cudaStream_t st = (cudaStream_t)stream;
   CU_CHECK(c, cudaMemsetAsync(c->misc_dev, 0, sizeof(unsigned long long) * 8, st));
-  const int bx = 128;
-  dim3 grid = row_grid(c->g, c->D, bx);
+  const int bx = 256;
+  const long long rows_ = (long long)(c->g.n[1] - 2) * (c->D == 3 ? c->g.n[2] - 2 : 1);
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((rows_ + 7) / 8, 148LL * 8));
   if (c->dtype == IFADV_F32) {
     if (c->D == 2) cfl_kernel<float, 2><<<grid, bx, 0, st>>>((const float*)u, c->g, c->misc_dev);
     else cfl_kernel<float, 3><<<grid, bx, 0, st>>>((const float*)u, c->g, c->misc_dev);
@@ -624,8 +644,9 @@ int ifadv_sum_inside(ifadv_ctx* c, void* stream, const void* f, double* out) {
   if (!c || !f || !out) return -2;
   cudaStream_t st = (cudaStream_t)stream;
   CU_CHECK(c, cudaMemsetAsync(c->misc_dev, 0, sizeof(unsigned long long) * 8, st));
-  const int bx = 128;
-  dim3 grid = row_grid(c->g, c->D, bx);
+  const int bx = 256;
+  const long long rows_ = (long long)(c->g.n[1] - 2) * (c->D == 3 ? c->g.n[2] - 2 : 1);
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((rows_ + 7) / 8, 148LL * 8));
   double* acc = reinterpret_cast<double*>(c->misc_dev);
   if (c->dtype == IFADV_F32) {
     if (c->D == 2) sum_inside_kernel<float, 2><<<grid, bx, 0, st>>>((const float*)f, c->g, acc);
