@@ -68,3 +68,18 @@ def test_perdir_mask():
     from interfaceadvection.jl_b200._lib import perdir_mask
 
     assert perdir_mask(()) == 0 and perdir_mask((1,)) == 1 and perdir_mask((2, 3)) == 6 and perdir_mask((1, 2, 3)) == 7
+
+
+def test_bench_byte_accounting_matches_survey():
+    """SURVEY §8d figures the roofline fractions in bench.py are built on: 53 / 105 B per cell and CMOM sweep, 376 / 744 B per CMOM
+    step, 52 / 100 B per pure-VOF step (3-D), 67 B for the 2-D Float64 VOF step."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert b.algorithmic_bytes_per_cell_sweep(3, 4) == 53 and b.algorithmic_bytes_per_cell_sweep(3, 8) == 105
+    assert b.algorithmic_bytes_per_cell_step(3, 4) == 376 and b.algorithmic_bytes_per_cell_step(3, 8) == 744
+    assert b.vof_bytes_per_cell_step(3, 4) == 52 and b.vof_bytes_per_cell_step(3, 8) == 100 and b.vof_bytes_per_cell_step(2, 8) == 67
+    assert set(b.WORKLOADS) >= {"C4_bubble_512_f32", "C3_dambreak_512x256x256_f32", "C2_enright_256_f32", "C1_zalesak_128_f64"}
