@@ -3,6 +3,8 @@
 //   FAM 0  dispatcher (launch_sweep_dim) + v1 tile kernel        FAM 1  plane-marching kernel (march)
 //   FAM 2  register-marching kernel (along)                      FAM 3  lean register marching (along2), y / z sweeps
 //   FAM 4  lean plane marching along x (xsweep, CMOM only)       families 1-4 exist for 3-D grids only
+#include <algorithm>
+#include <cstdlib>
 #include <limits>
 
 #include "ifadv_ctx.hpp"
@@ -164,6 +166,7 @@ static int launch_along2_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) 
   const long long tiles = (long long)((nx + 31) / 32) * ((ncc + TC - 1) / TC);
   int chunk = 128;  // a multiple of 4 (4 warm-up planes per chunk)
   while (chunk > 16 && tiles * ((na + chunk - 1) / chunk) < 148 * 8) chunk >>= 1;
+  if (const char* e = getenv("IFADV_CHUNK")) chunk = std::max(16, (atoi(e) / 4) * 4);  // measurement override
   dim3 grid((unsigned)((nx + 31) / 32), (unsigned)((ncc + TC - 1) / TC), (unsigned)((na + chunk - 1) / chunk));
   const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
   if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
@@ -196,6 +199,7 @@ static int launch_xsweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) 
   const long long tiles = (long long)((nx + 31) / 32) * ((ny + TY - 1) / TY);
   int chunk = 128;  // 3-6 warm-up planes per chunk
   while (chunk > 16 && tiles * ((nz + chunk - 1) / chunk) < 148 * 8) chunk >>= 1;
+  if (const char* e = getenv("IFADV_CHUNK")) chunk = std::max(16, (atoi(e) / 4) * 4);  // measurement override
   dim3 grid((unsigned)((nx + 31) / 32), (unsigned)((ny + TY - 1) / TY), (unsigned)((nz + chunk - 1) / chunk));
   const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
   if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
