@@ -83,6 +83,10 @@ class ClockSampler:
                                           str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            # nvidia-smi needs 0.2-1 s before its first row: the timed region only starts once the stream is flowing
+            t_end = time.time() + 5.0
+            while not self.rows and time.time() < t_end:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
@@ -96,9 +100,11 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        for t, line in self.rows:
-            if t < t0 - 0.05 or t > t1 + 0.15:
-                continue
+        inside = [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.15]
+        # a timed region shorter than the 100 ms sampling period may hold no row: take the rows next to it (the GPU has been
+        # under the same load since the warm-up steps)
+        rows = inside if inside else [r for r in self.rows if t0 - 0.5 <= r[0] <= t1 + 0.5]
+        for t, line in rows:
             p = [x.strip() for x in line.split(",")]
             try:
                 sm.append(float(p[1])); mx = float(p[2])
