@@ -465,3 +465,49 @@ def test_overlapped_step_equals_sequential(ia, T):
         res[ov] = [ia.to_numpy(x) for x in (intf.f, intf.f0, flow.u0, intf.rhou)]
     for x, y in zip(res[False], res[True]):
         assert np.array_equal(x, y)
+
+
+def test_full_size_properties_bubble_512(ia):
+    """BASELINE config 4 at full size (rising-bubble grid 512³, Float32, periodic x/y, λρ = 1e-3, full CMOM + SynDRoM; the bench
+    workload): mass conservation, boundedness, finite momentum, ghosts == BCf!(interior), and the shift invariance the periodic
+    directions offer -- the state shifted by (37, 11) cells in x, y gives the shifted result bit for bit."""
+    from interfaceadvection.jl_b200 import configs
+    N = (512, 512, 512)
+    dev = torch.device("cuda", 0)
+    case = configs.make_case("C4_bubble_512", device=dev)
+    per = (1, 2)
+
+    def run(f0, u0, steps):
+        sim = ia.TwoPhaseSimulation(N, (0, 0, 0), 512.0, T=torch.float32, lam_rho=1e-3, perdir=per, U=1.0, dt=1.0, device=dev)
+        sim.intf.f.copy_(f0); ia.BCf(sim.intf.f, per)
+        sim.flow.u.copy_(u0); ia.BC(sim.flow.u, (0, 0, 0), False, per)
+        V0 = ia.sum_inside(sim.intf.f)
+        for _ in range(steps):
+            ia.mom_advect_step(sim.flow, sim.intf, 1.0, check=True)
+            sim.flow.dt.append(1.0)
+        V1 = ia.sum_inside(sim.intf.f)
+        f, ru = sim.intf.f.clone(memory_format=torch.preserve_format), sim.intf.rhou[1:-1, 1:-1, 1:-1].clone()
+        del sim
+        torch.cuda.empty_cache()
+        return V0, V1, f, ru
+
+    base = ia.TwoPhaseSimulation(N, (0, 0, 0), 512.0, T=torch.float32, lam_rho=1e-3, InterfaceSDF=case["sdf"], perdir=per, U=1.0, dt=1.0,
+                                 device=dev)
+    f0 = base.intf.f.clone(memory_format=torch.preserve_format)
+    u0 = case["u"].clone(memory_format=torch.preserve_format)
+    del base, case
+    torch.cuda.empty_cache()
+    V0, V1, f, ru = run(f0, u0, 2)
+    assert abs(V1 - V0) <= 2e-6 * V0
+    assert float(f.min()) >= 0.0 and float(f.max()) <= 1.0
+    assert bool(torch.isfinite(ru).all())
+    g = f.clone(memory_format=torch.preserve_format); ia.BCf(g, per)
+    assert torch.equal(g, f)
+    # periodic shift invariance (interior cells; the ghost layers are rebuilt by BCf! / BC!)
+    sx, sy = 37, 11  # not a multiple of the 32 x 16 tile: every cell meets different tile / warp / halo roles
+    fs = f0.clone(memory_format=torch.preserve_format); us = u0.clone(memory_format=torch.preserve_format)
+    fs[1:-1, 1:-1, :] = torch.roll(f0[1:-1, 1:-1, :], (sx, sy), (0, 1))
+    us[1:-1, 1:-1, :, :] = torch.roll(u0[1:-1, 1:-1, :, :], (sx, sy), (0, 1))
+    _, _, f2, ru2 = run(fs, us, 2)
+    assert torch.equal(f2[1:-1, 1:-1, 1:-1], torch.roll(f[1:-1, 1:-1, 1:-1], (sx, sy), (0, 1)))
+    assert torch.equal(ru2, torch.roll(ru, (sx, sy), (0, 1)))
