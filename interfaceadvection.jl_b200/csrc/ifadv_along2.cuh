@@ -40,7 +40,9 @@ template <class T, int J, int PLH, int WX> struct A2Box {
   }
 };
 
-template <class T, int J, int CPT, bool MOM, bool FUSED, bool KOREN, int NT, int MINB>
+// SAMEU: u¹ and u² are ONE array (both advectfq! calls of MPFMomStep!: flow.jl:92, and :70 where u⁰≡u) -- the u⁰ copy stream, its
+// ring and its registers drop out; the arithmetic is unchanged (u + u, (u2-u1) + (u2-u1)), so the results are bit-identical.
+template <class T, int J, int CPT, bool MOM, bool FUSED, bool KOREN, int NT, int MINB, bool SAMEU = false>
 __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, const int chunk) {
   constexpr int TR = NT / 32;      // rows of threads
   constexpr int TCT = TR * CPT;    // tile rows: a thread owns CPT columns, rows tc, tc+TR, ...
@@ -167,11 +169,11 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
         cp_async_s(se0 + so + OU * SZ + j * (TR * WX * SZ), up + go[j]);
-        cp_async_s(se0 + so + OU0 * SZ + j * (TR * WX * SZ), u0p + go[j]);
+        if (!SAMEU) cp_async_s(se0 + so + OU0 * SZ + j * (TR * WX * SZ), u0p + go[j]);
       }
       if (MOM && hU) {
         cp_async_s(seh + so + OU * SZ, up + gh);
-        cp_async_s(seh + so + OU0 * SZ, u0p + gh);
+        if (!SAMEU) cp_async_s(seh + so + OU0 * SZ, u0p + gh);
       }
     };
     auto ld_ru = [&](int v) {
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
       f0[j] = sm[OF + e];                                  // plane ks   -> slot 0
       f1[j] = sm[OF + 1 * PLH + e];                        // plane ks+1 -> slot 1
       u1[j] = sm[OU + 1 * PLH + e];
-      u01[j] = sm[OU0 + 1 * PLH + e];
+      u01[j] = SAMEU ? u1[j] : sm[OU0 + 1 * PLH + e];
     }
   }
 
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
       for (int j = 0; j < CPT; ++j) {
         cp_async_s(se0 + dF + j * (TR * WX * SZ), P.f_in + (go[j] + oM3));
         cp_async_s(se0 + dU + j * (TR * WX * SZ), ubase + (go[j] + oA3));
-        cp_async_s(se0 + dU0 + j * (TR * WX * SZ), u0base + (go[j] + oA3));
+        if (!SAMEU) cp_async_s(se0 + dU0 + j * (TR * WX * SZ), u0base + (go[j] + oA3));
         if (MOM) {
           cp_async_s(st0 + dR + j * NT * SZ, rsrc + (go[j] + oA3));
           cp_async_s(st0 + dR + (NC + j * NT) * SZ, rsrc + (go[j] + oM3));
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
       if (hasH) cp_async_s(seh + dF, P.f_in + (gh + oM3));
       if (MOM && hU) {
         cp_async_s(seh + dU, ubase + (gh + oA3));
-        cp_async_s(seh + dU0, u0base + (gh + oA3));
+        if (!SAMEU) cp_async_s(seh + dU0, u0base + (gh + oA3));
       }
       cp_async_commit();
     }
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
       const int cnt = sCnt[rel & 3];  // block-uniform
       if (cnt > 0) {
         const T* Up = sm + OU + ((rel + 1) & 3) * PLH;
-        const T* U0p = sm + OU0 + ((rel + 1) & 3) * PLH;
+        const T* U0p = SAMEU ? Up : sm + OU0 + ((rel + 1) & 3) * PLH;
         T* Mp = sm + OM + ((rel + 1) & 1) * PLH;
         for (int i = tid; i < cnt; i += NT) {
           const int e = sList[i];
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
         us[2][j][3] = dirC[j] ? ACv : rc;
       }
       // C. VOF flux + mass flux through face k+2 (advection.jl:108-137)
-      u2[j] = sm[qU + e]; u02[j] = sm[qU0 + e];
+      u2[j] = sm[qU + e]; u02[j] = SAMEU ? u2[j] : sm[qU0 + e];
       FFn[j] = T(0); Mn[j] = T(0); mkn[j] = false;
       if (needn) {
         T dl = P.hdt * (u2[j] + u02[j]);  // δt/2*(u+u⁰)
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
     // C/D for the halo entry (mass flux and dilation that the x-1 / c-1 neighbours of the tile edge need)
     if (MOM && hU) {
       const unsigned pF = OF + sF8(1), pU = OU + s4(1) * PLH, pU0 = OU0 + s4(1) * PLH;
-      const T uh2 = sm[qU + eh], u0h2 = sm[qU0 + eh], fh1 = sm[pF + eh];
+      const T uh2 = sm[qU + eh], u0h2 = SAMEU ? uh2 : sm[qU0 + eh], fh1 = sm[pF + eh];
       T m = T(0);
       if (needn) {
         T dl = P.hdt * (uh2 + u0h2);
@@ -383,7 +385,8 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
         }
       }
       sm[wM + eh] = m;
-      const T dh = (uh2 - sm[pU + eh]) + (u0h2 - sm[pU0 + eh]);
+      const T uh1 = sm[pU + eh];
+      const T dh = (uh2 - uh1) + (u0h2 - (SAMEU ? uh1 : sm[pU0 + eh]));
       const int ch = first ? ((fh1 < T(0.5)) ? 0 : 1) : cbh1;
       sm[wD + eh] = ((ch ? lam1 : lr) * dh) / T(2);
     }

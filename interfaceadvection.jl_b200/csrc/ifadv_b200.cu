@@ -803,7 +803,7 @@ int host_step_pipelined(ifadv_ctx* c, char* fh, const char* uh, char* rh, double
     CU_CHECK(c, cudaStreamWaitEvent(hp->s_cmp, h.ev_in, 0));
     CU_CHECK(c, cudaMemcpyAsync(u0, u, 3 * Sc, cudaMemcpyDeviceToDevice, hp->s_cmp));
     int rc;
-    if ((rc = ifadv_u2rhou_advect_vof_rhouu(h.ctx, hp->s_cmp, f, f0, ff, Phi, u0, u, dt, cbar, ru, r, ruf, u, drho, lambda_rho, limiter,
+    if ((rc = ifadv_u2rhou_advect_vof_rhouu(h.ctx, hp->s_cmp, f, f0, ff, Phi, u, u, dt, cbar, ru, r, ruf, u, drho, lambda_rho, limiter,
                                             normal_scheme, uBC, perdir_mask, dirO, nullptr)) < 0) { c->err = h.ctx->err; return rc; }
     if ((rc = ifadv_axpby(h.ctx, hp->s_cmp, f0, 0.5, f0, 0.5, f))) { c->err = h.ctx->err; return rc; }
     CU_CHECK(c, cudaMemcpyAsync(f0, f, Sc, cudaMemcpyDeviceToDevice, hp->s_cmp));
@@ -909,7 +909,8 @@ int ifadv_mom_advect_step_host(ifadv_ctx* c, void* f_host, const void* u_host, v
   CU_CHECK(c, cudaMemcpyAsync(u0, u, vb, cudaMemcpyDeviceToDevice, st));
   int rc;
   // predictor: copyto!(f⁰,f); u2ρu!(ρu,u⁰,f⁰); BC!; advectfq!(f⁰; u⁰,u,uOld=u)     flow.jl:61,69-70 (fused entry)
-  if ((rc = ifadv_u2rhou_advect_vof_rhouu(c, st, f, f0, ff, Phi, u0, u, dt, cbar, ru, r, ruf, u, drho, lambda_rho, limiter, normal_scheme,
+  // (u is passed for both velocity arguments: u⁰≡u here, and one array selects the kernels without the second velocity stream)
+  if ((rc = ifadv_u2rhou_advect_vof_rhouu(c, st, f, f0, ff, Phi, u, u, dt, cbar, ru, r, ruf, u, drho, lambda_rho, limiter, normal_scheme,
                                           uBC, perdir_mask, dirO, nullptr)) < 0) return rc;
   if ((rc = ifadv_axpby(c, st, f0, 0.5, f0, 0.5, f))) return rc;  // flow.jl:74
   // corrector: copyto!(f⁰,f); u2ρu!(ρu,u⁰,f); BC!; advectfq!(f; u,u,uOld=u⁰)         flow.jl:89-92

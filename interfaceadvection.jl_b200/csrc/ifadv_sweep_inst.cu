@@ -147,7 +147,7 @@ static int launch_along_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
 
 #if IFADV_FAM == 3
 // v4: lean register-marching kernel (static ring slots, one barrier per plane) for sweeps along y / z (3-D only)
-template <class T, int J, int CPT, bool MOM, bool FUSED, bool KOREN, int MINB>
+template <class T, int J, int CPT, bool MOM, bool FUSED, bool KOREN, int MINB, bool SAMEU = false>
 static int launch_along2_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   constexpr int NT = 256, TC = (NT / 32) * CPT;
   using TL = ATile<TC>;
@@ -155,7 +155,7 @@ static int launch_along2_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) 
   fill_params<T>(c, q, J, P);
   if ((unsigned long long)c->g.S * 3ull >= 0xffffffffull) { c->err = "grid too large for 32-bit element offsets"; return -2; }
   const size_t smem = TL::template smem_bytes<T>(MOM);
-  auto kern = along2_kernel<T, J, CPT, MOM, FUSED, KOREN, NT, MINB>;
+  auto kern = along2_kernel<T, J, CPT, MOM, FUSED, KOREN, NT, MINB, SAMEU>;
   static unsigned long long attr_devs = 0ull;
   if (!((attr_devs >> (c->device & 63)) & 1ull)) {
     CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -181,7 +181,7 @@ static int launch_along2_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) 
 
 #if IFADV_FAM == 4
 // v4: lean plane-marching kernel for CMOM sweeps along x (3-D only)
-template <class T, int CPT, bool FUSED, bool KOREN, int MINB>
+template <class T, int CPT, bool FUSED, bool KOREN, int MINB, bool SAMEU = false>
 static int launch_xsweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   constexpr int NT = 256, TY = (NT / 32) * CPT;
   using TL = XTile<TY>;
@@ -189,7 +189,7 @@ static int launch_xsweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) 
   fill_params<T>(c, q, 0, P);
   if ((unsigned long long)c->g.S * 3ull >= 0xffffffffull) { c->err = "grid too large for 32-bit element offsets"; return -2; }
   const size_t smem = TL::template smem_bytes<T>();
-  auto kern = xsweep_kernel<T, CPT, FUSED, KOREN, NT, MINB>;
+  auto kern = xsweep_kernel<T, CPT, FUSED, KOREN, NT, MINB, SAMEU>;
   static unsigned long long attr_devs = 0ull;
   if (!((attr_devs >> (c->device & 63)) & 1ull)) {
     CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -281,6 +281,16 @@ template <class T, bool MOM> int launch_fam_along2(ifadv_ctx* c, cudaStream_t st
   constexpr int CP = (sizeof(T) == 4) ? IFADV_XP_A2CPT : 1;
   constexpr int MBX = (sizeof(T) == 4) ? IFADV_XP_A2MB : IFADV_XP_A2MB64;
   const bool koren = !MOM || q.lim == 2;  // the package default limiter is compiled in; the others go through limiter_other
+  if constexpr (MOM) {
+    if (koren && q.u == q.u0) {  // one velocity array for u¹ and u² (MPFMomStep!): the SAMEU instantiations
+      if (q.fused) {
+        if (q.j == 1) return launch_along2_t<T, 1, CP, MOM, MOM, true, MBX, true>(c, st, q);
+        return launch_along2_t<T, 2, CP, MOM, MOM, true, MBX, true>(c, st, q);
+      }
+      if (q.j == 1) return launch_along2_t<T, 1, CP, MOM, false, true, MBX, true>(c, st, q);
+      return launch_along2_t<T, 2, CP, MOM, false, true, MBX, true>(c, st, q);
+    }
+  }
   if (MOM && q.fused) {
     if (q.j == 1) return koren ? launch_along2_t<T, 1, CP, MOM, MOM, true, MBX>(c, st, q) : launch_along2_t<T, 1, CP, MOM, MOM, !MOM, MBX>(c, st, q);
     return koren ? launch_along2_t<T, 2, CP, MOM, MOM, true, MBX>(c, st, q) : launch_along2_t<T, 2, CP, MOM, MOM, !MOM, MBX>(c, st, q);
@@ -296,6 +306,10 @@ template <class T, bool MOM> int launch_fam_xsweep(ifadv_ctx* c, cudaStream_t st
   constexpr int CP = (sizeof(T) == 4) ? 2 : 1;
   constexpr int MB = (sizeof(T) == 4) ? 2 : 1;
   const bool koren = q.lim == 2;
+  if (koren && q.u == q.u0) {  // one velocity array for u¹ and u² (MPFMomStep!): the SAMEU instantiations
+    if (q.fused) return launch_xsweep_t<T, CP, true, true, MB, true>(c, st, q);
+    return launch_xsweep_t<T, CP, false, true, MB, true>(c, st, q);
+  }
   if (q.fused) return koren ? launch_xsweep_t<T, CP, true, true, MB>(c, st, q) : launch_xsweep_t<T, CP, true, false, MB>(c, st, q);
   return koren ? launch_xsweep_t<T, CP, false, true, MB>(c, st, q) : launch_xsweep_t<T, CP, false, false, MB>(c, st, q);
 }

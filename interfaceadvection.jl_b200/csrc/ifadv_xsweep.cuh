@@ -65,7 +65,8 @@ template <class T, int PL, int WX> struct XBox {
   IFADV_DI T operator()(int dx, int dy, int dz) const { return sF[((rel + dz) & 3) * PL + e + dx + dy * WX]; }
 };
 
-template <class T, int CPT, bool FUSED, bool KOREN, bool XB, int NT>
+// SAMEU: u¹ and u² are one array (see ifadv_along2.cuh): no u⁰ copy stream, the u⁰ values are the u values
+template <class T, int CPT, bool FUSED, bool KOREN, bool XB, int NT, bool SAMEU>
 IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
   constexpr int TR = NT / 32, TY = TR * CPT;
   using TL = XTile<TY>;
@@ -148,7 +149,7 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
       const unsigned gmv = gm[j] + pmv;
       cp_async_s(se0 + dF + j * JS, P.f_in + gmv);
       cp_async_s(se0 + dU + j * JS, P.u + (gmv + gox));
-      cp_async_s(se0 + dU0 + j * JS, P.u0 + (gmv + gox));
+      if (!SAMEU) cp_async_s(se0 + dU0 + j * JS, P.u0 + (gmv + gox));
       cp_async_s(se0 + dR + j * JS, rsrc + (gmv + gox));
       cp_async_s(se0 + dR + PL * SZ + j * JS, rsrc + (gmv + cB));
       cp_async_s(se0 + dR + 2 * PL * SZ + j * JS, rsrc + (gm[j] + cC + pov));
@@ -157,7 +158,7 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
       cp_async_s(seh + dF, P.f_in + (ghm + pmv));
       if (hM) {
         cp_async_s(seh + dU, P.u + (gho + pmv));
-        cp_async_s(seh + dU0, P.u0 + (gho + pmv));
+        if (!SAMEU) cp_async_s(seh + dU0, P.u0 + (gho + pmv));
       }
       if (hUS) {
         cp_async_s(seh + dR, rsrc + (gho + pmv));
@@ -307,7 +308,7 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
 
     // ring slots of this step
     constexpr int qF2 = OF + ((I + 2) & 3) * PL, qF1 = OF + ((I + 1) & 3) * PL;
-    constexpr int qU = OU + ((I + 2) & 1) * PL, qU0 = OU0 + ((I + 2) & 1) * PL, qR = OR + ((I + 2) & 1) * 3 * PL;
+    constexpr int qU = OU + ((I + 2) & 1) * PL, qU0 = (SAMEU ? OU : OU0) + ((I + 2) & 1) * PL, qR = OR + ((I + 2) & 1) * 3 * PL;
     constexpr int wUS = OUS + ((I + 2) & 1) * 3 * PL, wM = OM + ((I + 2) & 3) * PL, wD = ODIL + ((I + 2) & 3) * PL;
     constexpr int wFL = OFL + ((I + 1) & 1) * 4 * PL, rFL = OFL + (I & 1) * 4 * PL;
     constexpr int rD0 = ODIL + (I & 3) * PL, rDm = ODIL + ((I + 3) & 3) * PL;
@@ -513,15 +514,15 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
   }
 }
 
-template <class T, int CPT, bool FUSED, bool KOREN, int NT, int MINB>
+template <class T, int CPT, bool FUSED, bool KOREN, int NT, int MINB, bool SAMEU = false>
 __global__ void __launch_bounds__(NT, MINB) xsweep_kernel(const SweepP<T> P, const int chunk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sm = reinterpret_cast<T*>(smem_raw);
   const int ox = 2 + blockIdx.x * 32, nA = P.g.n[0];
   // tiles whose columns (incl. the halo -3..+33) reach a ghost column of a non-periodic x boundary take the body with the boundary rules
   const bool xb = !(P.g.per & 1u) && (ox - 3 < 2 || ox + 33 > nA - 1);
-  if (xb) xsweep_body<T, CPT, FUSED, KOREN, true, NT>(P, chunk, sm);
-  else xsweep_body<T, CPT, FUSED, KOREN, false, NT>(P, chunk, sm);
+  if (xb) xsweep_body<T, CPT, FUSED, KOREN, true, NT, SAMEU>(P, chunk, sm);
+  else xsweep_body<T, CPT, FUSED, KOREN, false, NT, SAMEU>(P, chunk, sm);
 }
 
 }  // namespace ifadv
