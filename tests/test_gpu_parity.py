@@ -511,3 +511,29 @@ def test_full_size_properties_bubble_512(ia):
     _, _, f2, ru2 = run(fs, us, 2)
     assert torch.equal(f2[1:-1, 1:-1, 1:-1], torch.roll(f[1:-1, 1:-1, 1:-1], (sx, sy), (0, 1)))
     assert torch.equal(ru2, torch.roll(ru, (sx, sy), (0, 1)))
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("N,perdir", [((40, 24, 20), (2,)), ((33, 17, 19), (1, 2, 3))])
+def test_single_velocity_array_kernels_equal_two_array_kernels(ia, T, N, perdir):
+    """advectVOFρuu! called with ONE array for u¹ and u² (what MPFMomStep! does, flow.jl:92) runs the instantiations without the
+    second velocity stream; handing the same values as two distinct arrays runs the general ones.  Bit-identical f, ρu, c̄."""
+    st = make_state(N, "C3", T, perdir=perdir)
+    rng = np.random.default_rng(20261017)
+    uOld = np.asfortranarray(st["u"] * T(0.9) + T(0.01) * rng.standard_normal(st["u"].shape).astype(T))
+    O.BC(uOld, st["uBC"], False, perdir)
+    rhou = O.zeros(st["u"].shape, T); O.u2rhou(rhou, uOld, st["f"], st["lam_rho"]); O.BC(rhou, st["uBC"], False, perdir)
+    outs = []
+    for alias in (True, False):
+        a = alloc_cmom(st); a["rhou"][...] = rhou
+        d = dev_arrays(ia, st, a)
+        fd, ud, uod = ia.from_numpy(st["f"]), ia.from_numpy(st["u"]), ia.from_numpy(uOld)
+        u2d = ud if alias else ud.clone(memory_format=torch.preserve_format)
+        assert (u2d.data_ptr() == ud.data_ptr()) == alias
+        for dirO in ((3, 1, 2), (1, 2, 3)):
+            stt = ia.advectVOFrhouu(fd, d["ff"], d["alpha"], d["nhat"], ud, u2d, 1.0, d["cbar"], d["rhou"], d["r"], d["Phi"], d["rhouf"],
+                                    d["nhat"], uod, d["alpha"], d["drho"], st["lam_rho"], "Koren", "WH", st["uBC"], perdir, False, dirO)
+            assert stt == 0
+        outs.append([ia.to_numpy(x) for x in (fd, d["rhou"], d["cbar"])])
+    for x, y in zip(*outs):
+        assert np.array_equal(inside(x, 3), inside(y, 3))
