@@ -13,7 +13,8 @@
  *   - every pointer named in a *_dev / plain entry point is a DEVICE pointer borrowed for the call;
  *     all work is enqueued on the caller's stream (a cudaStream_t passed as void*); no device-wide sync;
  *   - return value: 0 ok; >0 advisory (bit0 overfill, bit1 underfill; only evaluated when report != NULL);
- *     <0 fatal: -1 NaN in f, -2 invalid argument / unsupported combination, -3 CUDA error, -4 comm error.
+ *     <0 fatal: -1 NaN in f, -2 invalid argument / unsupported combination, -3 CUDA error, -4 comm error,
+ *     -5 "divergence ... is exploding" (|∇·u⁰|+|∇·u| > 10 or NaN at an over/under-filled cell, src/advection.jl:160,180).
  *
  * Preconditions shared with the reference's call sites: f, u, u0 carry valid ghost values (BCf!/BC! applied,
  * as they always are inside MPFMomStep!, flow.jl:61-92).
@@ -60,6 +61,8 @@ typedef struct {
   int64_t argmax[3], argmin[3];  /* 1-based cell index (approximate tie-breaking) */
   int dir;                       /* 1-based sweep direction the values belong to */
   int status;                    /* same bits as the return value */
+  double div_u0, div_u;          /* |∇·u⁰|, |∇·u| at the reported cell (reportFillError's diagnostics, src/advection.jl:151,170);
+                                    0 unless status > 0 */
 } ifadv_report;
 
 /* ---- context ------------------------------------------------------------------------------------------- */
@@ -139,6 +142,12 @@ int ifadv_apply_vof_samples(ifadv_ctx* ctx, void* stream, void* f, void* alpha, 
  * ifadv_advect_vof_rhouu / ifadv_u2rhou_advect_vof_rhouu call on this context then inserts cudaStreamWaitEvent(stream, event)
  * before its first write to f (one-shot).  event: cudaEvent_t. */
 int ifadv_defer_f_writes_until(ifadv_ctx* ctx, void* event);
+
+/* NaN detection without a per-call synchronisation: calls made with report == NULL never look at their reductions, so a NaN in f
+ * (error("NaN!"), src/advection.jl:148) would go unnoticed.  The NaN count of every call is folded into a sticky device flag when the
+ * next call starts; this entry point (and every call WITH a report) reads it: returns -1 if any sweep since the last check produced a
+ * NaN, else 0, and clears the flag.  Synchronises the stream -- call it every k-th step. */
+int ifadv_check_nan(ifadv_ctx* ctx, void* stream);
 
 /* ---- host-buffer convenience (what bench.py's e2e leg times) --------------------------------------------- */
 /* One CMOM advection step of MPFMomStep! on HOST arrays (flow.jl:61,69-70,74,89-92 with the forcing and

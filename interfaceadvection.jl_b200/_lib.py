@@ -20,7 +20,7 @@ class IfadvError(RuntimeError):
 
 class Report(C.Structure):
     _fields_ = [("maxf", C.c_double), ("minf", C.c_double), ("argmax", C.c_int64 * 3), ("argmin", C.c_int64 * 3),
-                ("dir", C.c_int), ("status", C.c_int)]
+                ("dir", C.c_int), ("status", C.c_int), ("div_u0", C.c_double), ("div_u", C.c_double)]
 
 
 _lib = None
@@ -61,6 +61,7 @@ def lib():
         L.ifadv_mom_advect_step_host.argtypes = [vp, vp, vp, vp, dbl, dbl, i32, i32, dblp, u32, i32p, rep]
         L.ifadv_host_step_bytes.argtypes = [vp, i64p, i64p, i32p]
         L.ifadv_defer_f_writes_until.argtypes = [vp, vp]
+        L.ifadv_check_nan.argtypes = [vp, vp]
         _lib = L
     return _lib
 
@@ -111,6 +112,8 @@ class Context:
             msg = lib().ifadv_last_error(self._h).decode()
             if rc == -1:
                 raise IfadvError("NaN!")  # error("NaN!"), src/advection.jl:148
+            if rc == -5:
+                raise IfadvError(msg)  # error("divergence, …, is exploding!"), src/advection.jl:160,180
             raise IfadvError(f"ifadv error {rc}: {msg}")
         return rc
 
@@ -188,6 +191,10 @@ class Context:
     def defer_f_writes_until(self, event):
         """One-shot: the next CMOM advect call waits for `event` (cudaEvent_t handle) before its first write to f."""
         return self._chk(lib().ifadv_defer_f_writes_until(self._h, event))
+
+    def check_nan(self, stream):
+        """Raises IfadvError("NaN!") if any sweep since the last check / reporting call produced a NaN in f (ifadv_check_nan)."""
+        return self._chk(lib().ifadv_check_nan(self._h, stream))
 
     def host_step_bytes(self):
         """(h2d_bytes, d2h_bytes, slabs) of the last mom_advect_step_host call (ifadv_host_step_bytes)."""

@@ -241,10 +241,12 @@ def _dirO(flow, D):
 
 
 def _report(status, rep: Report):
-    if status > 0:  # the reference prints and carries on (advection.jl:161-166)
+    if status > 0:  # the reference prints and carries on (advection.jl:150-166); the exploding-divergence case has already been
+        #             raised as IfadvError by the library (status -5, advection.jl:160,180)
         which = "max" if status & 1 else "min"
         val = rep.maxf - 1 if status & 1 else -rep.minf
         idx = tuple(rep.argmax) if status & 1 else tuple(rep.argmin)
+        print(f"|∇⋅u⁰| = {rep.div_u0:+13.8f}, |∇⋅u| = {rep.div_u:+13.8f}")
         print(f"ERROR: {which} VOF @ {idx} ∉ [0,1] @ direction {rep.dir}, Δf = {val}")
     return status
 

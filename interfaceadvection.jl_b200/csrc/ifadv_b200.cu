@@ -26,10 +26,13 @@ static int fail(ifadv_ctx* c, int code, const char* msg) {
 // ------------------------------------------------------------------------------------------------------------
 // small kernels
 // ------------------------------------------------------------------------------------------------------------
+// Resets the per-sweep reduction slots of a call.  Before that, a NaN count left by the PREVIOUS call (which may have run without a
+// report, i.e. without anybody looking) is folded into the sticky flag red[24]: ifadv_check_nan / the next reporting call see it.
 __global__ void red_init_kernel(unsigned long long* red, int nsets) {
   const int t = threadIdx.x;
   if (t < nsets) {
     unsigned long long* r = red + 8 * t;
+    if (r[4] != 0ull) atomicOr(red + 24, 1ull);
     r[0] = 0ull; r[1] = ~0ull; r[2] = 0ull; r[3] = ~0ull; r[4] = 0ull; r[5] = 0ull; r[6] = 0ull; r[7] = 0ull;
   }
 }
@@ -257,7 +260,7 @@ static int check_common(ifadv_ctx* c, int ns, const int* dirO) {
     if (dirO[k] < 1 || dirO[k] > c->D) return fail(c, -2, "dirO entries must be in 1..D");
     seen |= 1u << (dirO[k] - 1);
   }
-  (void)seen;
+  if (seen != (1u << c->D) - 1u) return fail(c, -2, "dirO must be a permutation of 1..D");
   return 0;
 }
 
@@ -296,6 +299,53 @@ static int decode_report(ifadv_ctx* c, const int* dirO, double filltol, ifadv_re
   return status;
 }
 
+// The reporting tail of a call (reportFillError, advection.jl:145-189): fetch the per-sweep extrema (stream sync), decode them, and for an
+// over/under-filled cell evaluate |∇·u⁰| + |∇·u| there -- the reference aborts with error("divergence, …, is exploding!") when that
+// exceeds 10 or is NaN (:160,180) and only prints otherwise.  A NaN left by an earlier call that ran without a report is fatal here too.
+template <class T>
+static int finish_report(ifadv_ctx* c, cudaStream_t st, const int* dirO, double filltol, ifadv_report* rep, const T* u, const T* u0) {
+  CU_CHECK(c, cudaMemcpyAsync(c->red_host, c->red_dev, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost, st));
+  CU_CHECK(c, cudaStreamSynchronize(st));
+  rep->div_u0 = rep->div_u = 0.0;
+  int status = decode_report(c, dirO, filltol, rep);
+  if (status >= 0 && c->red_host[24] != 0ull) {
+    CU_CHECK(c, cudaMemsetAsync(c->red_dev + 24, 0, sizeof(unsigned long long), st));
+    rep->status = -1;
+    return fail(c, -1, "NaN in f during an earlier call that ran without a report");
+  }
+  if (status < 0) return fail(c, status, "NaN in f");
+  for (int which = 0; which < 2 && status > 0; ++which) {  // the max cell (:150-167), then the min cell (:169-186)
+    if (!(status & (1 << which))) continue;
+    const int64_t* I = which == 0 ? rep->argmax : rep->argmin;
+    bool edge = false;
+    for (int a = 0; a < c->D; ++a) edge = edge || I[a] < 1 || I[a] >= c->g.n[a];
+    if (edge) continue;
+    const long long l = (long long)(I[0] - 1) + c->g.s1 * (I[1] - 1) + c->g.s2 * ((c->D == 3 ? I[2] : 1) - 1);
+    T d0 = T(0), d1 = T(0);
+    for (int a = 0; a < c->D; ++a) {
+      const long long sa = (a == 0) ? 1 : ((a == 1) ? c->g.s1 : c->g.s2);
+      T v[4];
+      CU_CHECK(c, cudaMemcpyAsync(&v[0], u0 + (long long)a * c->g.S + l, sizeof(T), cudaMemcpyDeviceToHost, st));
+      CU_CHECK(c, cudaMemcpyAsync(&v[1], u0 + (long long)a * c->g.S + l + sa, sizeof(T), cudaMemcpyDeviceToHost, st));
+      CU_CHECK(c, cudaMemcpyAsync(&v[2], u + (long long)a * c->g.S + l, sizeof(T), cudaMemcpyDeviceToHost, st));
+      CU_CHECK(c, cudaMemcpyAsync(&v[3], u + (long long)a * c->g.S + l + sa, sizeof(T), cudaMemcpyDeviceToHost, st));
+      CU_CHECK(c, cudaStreamSynchronize(st));
+      d0 += v[1] - v[0];  // div(I,u⁰) = Σ ∂(a,I,u⁰)
+      d1 += v[3] - v[2];
+    }
+    rep->div_u0 = std::fabs((double)d0);
+    rep->div_u = std::fabs((double)d1);
+    const double s = rep->div_u0 + rep->div_u;
+    if (s > 10.0 || s != s) {
+      rep->status = -5;
+      char msg[96];
+      snprintf(msg, sizeof msg, "divergence, %g, is exploding!", s);
+      return fail(c, -5, msg);
+    }
+  }
+  return status;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // typed drivers
 // ------------------------------------------------------------------------------------------------------------
@@ -320,11 +370,7 @@ static int advect_vof_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* al, const
   }
   int rc = launch_bcf<T>(c, st, f, per);  // BCf!(f;perdir), advection.jl:72 (only the final ghosts are observable)
   if (rc) return rc;
-  if (rep) {
-    CU_CHECK(c, cudaMemcpyAsync(c->red_host, c->red_dev, sizeof(unsigned long long) * 24, cudaMemcpyDeviceToHost, st));
-    CU_CHECK(c, cudaStreamSynchronize(st));
-    return decode_report(c, dirO, 10.0 * (double)std::numeric_limits<T>::epsilon(), rep);  // tol, advection.jl:69
-  }
+  if (rep) return finish_report<T>(c, st, dirO, 10.0 * (double)std::numeric_limits<T>::epsilon(), rep, u, u0);  // tol, advection.jl:69
   return 0;
 }
 
@@ -336,12 +382,10 @@ template <class T> static int bcvec_t(ifadv_ctx* c, cudaStream_t st, T* a, const
 template <class T>
 static int advect_vof_rhouu_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* Phi, const T* u, const T* u0, double dt, int8_t* cbar, T* rhou,
                               T* r, T* rhouf, const T* uOld, const T* drho, double lr, int lim, int ns, const double* uBC, unsigned per,
-                              const int* dirO, ifadv_report* rep, const T* f_src = nullptr, int fused = 0) {
+                              const int* dirO, ifadv_report* rep, cudaEvent_t wait_f, const T* f_src = nullptr, int fused = 0) {
   const int D = c->D;
   c->g.per = per;
-  // ifadv_defer_f_writes_until: one-shot event this call waits for before its first write to f
-  cudaEvent_t wait_f = c->wait_f;
-  c->wait_f = nullptr;
+  // wait_f (ifadv_defer_f_writes_until): one-shot event this call waits for before its first write to f
   if (fused && (D == 2 || c->use_march == 0)) {
     if (f_src && f_src != f) {
       if (wait_f) { CU_CHECK(c, cudaStreamWaitEvent(st, wait_f, 0)); wait_f = nullptr; }
@@ -372,11 +416,7 @@ static int advect_vof_rhouu_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* Phi
   }
   int rc = launch_bcf<T>(c, st, f, per);
   if (rc) return rc;
-  if (rep) {
-    CU_CHECK(c, cudaMemcpyAsync(c->red_host, c->red_dev, sizeof(unsigned long long) * 24, cudaMemcpyDeviceToHost, st));
-    CU_CHECK(c, cudaStreamSynchronize(st));
-    return decode_report(c, dirO, 100.0 * (double)std::numeric_limits<T>::epsilon(), rep);  // 10tol, advection.jl:85
-  }
+  if (rep) return finish_report<T>(c, st, dirO, 100.0 * (double)std::numeric_limits<T>::epsilon(), rep, u, u0);  // 10tol, advection.jl:85
   return 0;
 }
 
@@ -460,8 +500,9 @@ int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int dev
     c->use_march = (e && std::string(e) == "tile") ? 0 : ((e && std::string(e) == "march") ? 2 : 1);
     c->use_along2 = (e && std::string(e) == "along1") ? 0 : 1;  // "along1": the first register-marching kernel for y/z sweeps
   }
-  if (cudaMalloc(&c->red_dev, sizeof(unsigned long long) * 24) != cudaSuccess ||
-      cudaMallocHost(&c->red_host, sizeof(unsigned long long) * 24) != cudaSuccess ||
+  if (cudaMalloc(&c->red_dev, sizeof(unsigned long long) * 32) != cudaSuccess ||
+      cudaMemset(c->red_dev, 0, sizeof(unsigned long long) * 32) != cudaSuccess ||
+      cudaMallocHost(&c->red_host, sizeof(unsigned long long) * 32) != cudaSuccess ||
       cudaMalloc(&c->misc_dev, sizeof(unsigned long long) * 8) != cudaSuccess ||
       cudaMallocHost(&c->misc_host, sizeof(unsigned long long) * 8) != cudaSuccess) {
     delete c;
@@ -544,6 +585,8 @@ int ifadv_advect_vof_rhouu(ifadv_ctx* c, void* stream, void* f, void* ff, void* 
                            const void* drho, double lambda_rho, int limiter, int normal_scheme, const double uBC[3], unsigned perdir_mask,
                            int exitBC, const int dirO[3], ifadv_report* report) {
   (void)alpha; (void)nhat; (void)uStar; (void)dilaU;
+  cudaEvent_t wait_f = nullptr;
+  if (c) { wait_f = c->wait_f; c->wait_f = nullptr; }  // one-shot, consumed even when the call is rejected below
   int rc = check_common(c, normal_scheme, dirO);
   if (rc) return rc;
   if (limiter < 0 || limiter > 10) return fail(c, -2, "invalid limiter");
@@ -554,16 +597,18 @@ int ifadv_advect_vof_rhouu(ifadv_ctx* c, void* stream, void* f, void* ff, void* 
   if (c->dtype == IFADV_F32)
     return advect_vof_rhouu_t<float>(c, st, (float*)f, (float*)ff, (float*)Phi, (const float*)u, (const float*)u0, dt, cbar, (float*)rhou,
                                      (float*)r, (float*)rhouf, (const float*)uOld, (const float*)drho, lambda_rho, limiter, normal_scheme,
-                                     uBC, perdir_mask, dirO, report);
+                                     uBC, perdir_mask, dirO, report, wait_f);
   return advect_vof_rhouu_t<double>(c, st, (double*)f, (double*)ff, (double*)Phi, (const double*)u, (const double*)u0, dt, cbar,
                                     (double*)rhou, (double*)r, (double*)rhouf, (const double*)uOld, (const double*)drho, lambda_rho, limiter,
-                                    normal_scheme, uBC, perdir_mask, dirO, report);
+                                    normal_scheme, uBC, perdir_mask, dirO, report, wait_f);
 }
 
 int ifadv_u2rhou_advect_vof_rhouu(ifadv_ctx* c, void* stream, const void* f_src, void* f, void* ff, void* Phi, const void* u, const void* u0,
                                   double dt, int8_t* cbar, void* rhou, void* r, void* rhouf, const void* uOld, const void* drho,
                                   double lambda_rho, int limiter, int normal_scheme, const double uBC[3], unsigned perdir_mask,
                                   const int dirO[3], ifadv_report* report) {
+  cudaEvent_t wait_f = nullptr;
+  if (c) { wait_f = c->wait_f; c->wait_f = nullptr; }  // one-shot, consumed even when the call is rejected below
   int rc = check_common(c, normal_scheme, dirO);
   if (rc) return rc;
   if (limiter < 0 || limiter > 10) return fail(c, -2, "invalid limiter");
@@ -573,10 +618,10 @@ int ifadv_u2rhou_advect_vof_rhouu(ifadv_ctx* c, void* stream, const void* f_src,
   if (c->dtype == IFADV_F32)
     return advect_vof_rhouu_t<float>(c, st, (float*)f, (float*)ff, (float*)Phi, (const float*)u, (const float*)u0, dt, cbar, (float*)rhou,
                                      (float*)r, (float*)rhouf, (const float*)uOld, (const float*)drho, lambda_rho, limiter, normal_scheme,
-                                     uBC, perdir_mask, dirO, report, (const float*)f_src, 1);
+                                     uBC, perdir_mask, dirO, report, wait_f, (const float*)f_src, 1);
   return advect_vof_rhouu_t<double>(c, st, (double*)f, (double*)ff, (double*)Phi, (const double*)u, (const double*)u0, dt, cbar,
                                     (double*)rhou, (double*)r, (double*)rhouf, (const double*)uOld, (const double*)drho, lambda_rho, limiter,
-                                    normal_scheme, uBC, perdir_mask, dirO, report, (const double*)f_src, 1);
+                                    normal_scheme, uBC, perdir_mask, dirO, report, wait_f, (const double*)f_src, 1);
 }
 
 int ifadv_u2rhou(ifadv_ctx* c, void* stream, void* rhou, const void* u, const void* f, double lr) {
@@ -765,7 +810,10 @@ int host_pipe_build(ifadv_ctx* c, int cp) {
   CU_CHECK(c, cudaStreamCreateWithFlags(&hp->s_cmp, cudaStreamNonBlocking));
   CU_CHECK(c, cudaStreamCreateWithFlags(&hp->s_out, cudaStreamNonBlocking));
   for (int k = 0; k < hp->nset; ++k) {
-    for (int i = 0; i < 11; ++i) CU_CHECK(c, cudaMalloc(&hp->w[k][i], sz[i]));
+    for (int i = 0; i < 11; ++i) {
+      CU_CHECK(c, cudaMalloc(&hp->w[k][i], sz[i]));
+      CU_CHECK(c, cudaMemsetAsync(hp->w[k][i], 0, sz[i], hp->s_cmp));  // ρu ghosts (never written by the sweeps) read back as zeros
+    }
     // dρ keeps its constructor value 1 (cVOF.jl:74)
     const long long n = (long long)S * 3;
     if (c->dtype == IFADV_F32) fill_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, hp->s_cmp>>>((float*)hp->w[k][9], 1.f, n);
@@ -877,7 +925,10 @@ int ifadv_mom_advect_step_host(ifadv_ctx* c, void* f_host, const void* u_host, v
   cudaStream_t st = c->own_stream;
   if (!c->w[0]) {
     const size_t sz[11] = {sb, sb, sb, sb, vb, vb, vb, vb, vb, vb, (size_t)c->g.S};
-    for (int k = 0; k < 11; ++k) CU_CHECK(c, cudaMalloc(&c->w[k], sz[k]));
+    for (int k = 0; k < 11; ++k) {
+      CU_CHECK(c, cudaMalloc(&c->w[k], sz[k]));
+      CU_CHECK(c, cudaMemsetAsync(c->w[k], 0, sz[k], st));  // ρu ghosts (never written by the sweeps) go back to the host as zeros
+    }
     // dρ keeps its constructor value 1 (cVOF.jl:74)
     {
       const long long n = (long long)c->g.S * c->D;
@@ -931,6 +982,18 @@ int ifadv_defer_f_writes_until(ifadv_ctx* c, void* event) {
   if (!c) return -2;
   c->wait_f = (cudaEvent_t)event;
   return 0;
+}
+
+int ifadv_check_nan(ifadv_ctx* c, void* stream) {
+  if (!c) return -2;
+  cudaStream_t st = (cudaStream_t)stream;
+  CU_CHECK(c, cudaMemcpyAsync(c->red_host, c->red_dev, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost, st));
+  CU_CHECK(c, cudaStreamSynchronize(st));
+  bool nan = c->red_host[24] != 0ull;
+  for (int s = 0; s < 3; ++s) nan = nan || c->red_host[8 * s + 4] != 0ull;  // the most recent call's own sweeps
+  if (!nan) return 0;
+  CU_CHECK(c, cudaMemsetAsync(c->red_dev + 24, 0, sizeof(unsigned long long), st));
+  return fail(c, -1, "NaN in f");
 }
 
 int ifadv_host_step_bytes(const ifadv_ctx* c, int64_t* h2d, int64_t* d2h, int* slabs) {

@@ -7,14 +7,16 @@
 # plus the secondary seams u2œÅu!/œÅu2u! (src/VOFutil.jl:198-211) and MPCFL (src/flow.jl:262) for CuArray{Float32|Float64}.
 # No KernelAbstractions, no multi-backend dispatch, no CPU fallback: unsupported argument combinations raise.
 #
-# NOTE: no Julia toolchain exists in the environment this library was built in, so this file has been written
-# against the C header but never executed (INTEGRATION.md).  Install: copy to ext/, add to Project.toml
+# STATUS: UNTESTED.  No Julia toolchain exists in the environment this library was built in, so this file has been written
+# against the C header (the ccall signatures are checked against include/ifadv.h by tests/test_abi_and_host.py, which parses
+# both) but never executed (INTEGRATION.md).  Install: copy to ext/, add to Project.toml
 #     [extensions]  IntfAdvB200Ext = "CUDA"      (instead of IntfAdvCUDAExt)
 # and point ENV["IFADV_B200_LIB"] at libifadv_b200.so.
 module IntfAdvB200Ext
 
 using CUDA
 using InterfaceAdvection
+import Random
 import InterfaceAdvection: advectVOF!, advectVOFœÅuu!, u2œÅu!, œÅu2u!, MPCFL, _scalar_op, cVOF
 import InterfaceAdvection: getInterfaceNormal_WH!, getInterfaceNormal_WY!, getInterfaceNormal_Column!, getInterfaceNormal_PCD!,
                            getInterfaceNormal_SLIC!, getInterfaceNormal_MYC!, getInterfaceNormal_Y!, getInterfaceNormal_CD!,
@@ -48,7 +50,9 @@ struct IfadvReport
     maxf::Cdouble; minf::Cdouble
     argmax::NTuple{3,Int64}; argmin::NTuple{3,Int64}
     dir::Cint; status::Cint
+    div_u0::Cdouble; div_u::Cdouble
 end
+IfadvReport() = IfadvReport(0, 0, (0, 0, 0), (0, 0, 0), 0, 0, 0, 0)
 
 # ---- one context per (device, size, eltype) ----------------------------------------------------------------------------
 const CONTEXTS = Dict{Tuple{Int,NTuple{3,Int64},DataType},Ptr{Cvoid}}()
@@ -67,12 +71,14 @@ stream_ptr() = Base.unsafe_convert(Ptr{Cvoid}, CUDA.stream().handle)
 dptr(a::CuArray) = reinterpret(Ptr{Cvoid}, UInt(pointer(a)))
 function check(ctx, rc)
     rc == -1 && error("NaN!")                                   # error("NaN!"), src/advection.jl:148
+    rc == -5 && error(unsafe_string(ccall((:ifadv_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx)))  # "divergence, ‚Ä¶, is exploding!" :160,180
     rc < 0 && error("ifadv error $rc: " * unsafe_string(ccall((:ifadv_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx)))
     rc
 end
 function report(rc, rep::IfadvReport)
     rc > 0 || return
     which, Œî, idx = (rc & 1) != 0 ? ("max", rep.maxf - 1, rep.argmax) : ("min", -rep.minf, rep.argmin)
+    println("|‚àá‚ãÖu‚Å∞| = $(rep.div_u0), |‚àá‚ãÖu| = $(rep.div_u)")   # reportFillError's diagnostics (advection.jl:151,170)
     Base.printstyled("ERROR: "; color=:red, bold=true)   # printed, not thrown -- like reportFillError (advection.jl:161-166)
     println("$which VOF @ $idx ‚àâ [0,1] @ direction $(rep.dir), Œîf = $Œî")
 end
@@ -84,7 +90,7 @@ function advectVOF!(f::CuArray{T,D}, f·∂†, Œ±, nÃÇ, u, u‚Å∞, Œît, cÃÑ, œÅuf, Œªœ
     ctx = context(f)
     dO = isnothing(dirO) ? Random.shuffle(1:D) : dirO
     dirv = Cint[dO...; zeros(Cint, 3 - D)]
-    rep = Ref(IfadvReport(0, 0, (0, 0, 0), (0, 0, 0), 0, 0))
+    rep = Ref(IfadvReport())
     want = (CALLS[] += 1) % CHECK_EVERY[] == 0
     rc = ccall((:ifadv_advect_vof, LIB), Cint,
                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Ptr{Cvoid},
@@ -103,7 +109,7 @@ function advectVOFœÅuu!(f::CuArray{T,D}, f·∂†, Œ±, nÃÇ, u, u‚Å∞, Œît, cÃÑ, œÅu, 
     dO = isnothing(dirO) ? Random.shuffle(1:D) : dirO
     dirv = Cint[dO...; zeros(Cint, 3 - D)]
     A = Cdouble[uBC...; zeros(3 - D)]
-    rep = Ref(IfadvReport(0, 0, (0, 0, 0), (0, 0, 0), 0, 0))
+    rep = Ref(IfadvReport())
     want = (CALLS[] += 1) % CHECK_EVERY[] == 0
     rc = ccall((:ifadv_advect_vof_rhouu, LIB), Cint,
                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid},
@@ -137,6 +143,54 @@ function MPCFL(a::Flow{D,T}, c::cVOF; Œît_max=one(T), safetyMargin=T(0.8)) where
                      ctx, stream_ptr(), dptr(a.u), a.ŒΩ, isnothing(c.Œº) ? 0.0 : c.Œº, c.ŒªŒº, c.ŒªœÅ, isnothing(c.Œ∑) ? 0.0 : c.Œ∑, g2,
                      Œît_max, safetyMargin, out))
     T(out[])
+end
+
+# ---- MPFMomStep!  (src/flow.jl:60-109) with the transport half on the fused entry points ---------------------------------------
+# Each of the two groups `copyto!(f‚Å∞,f); u2œÅu!(œÅu,u‚Å∞,¬∑); BC!(œÅu); advectfq!(‚Ä¶)` (flow.jl:61,69-70 and :89-92) becomes ONE call of
+# ifadv_u2rhou_advect_vof_rhouu (bit-identical to the separate calls, include/ifadv.h); forcing and projection stay WaterLily's.
+function fused_group!(a::Flow{D,T}, c::cVOF, fsrc, f, u¬π, u¬≤, uOld, Œ¥t) where {D,T}
+    a.exitBC && error("IntfAdvB200Ext: exitBC=true is not supported (DESIGN.md ¬ß5)")
+    a.uBC isa Function && error("IntfAdvB200Ext: function-valued uBC is not supported (no fallback)")
+    ctx = context(f)
+    dirv = Cint[ntuple(i -> mod(length(a.Œît) + i, D) + 1, D)...; zeros(Cint, 3 - D)]   # flow.jl:163
+    A = Cdouble[a.uBC...; zeros(3 - D)]
+    rep = Ref(IfadvReport())
+    want = (CALLS[] += 1) % CHECK_EVERY[] == 0
+    rc = ccall((:ifadv_u2rhou_advect_vof_rhouu, LIB), Cint,
+               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid},
+                Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Cint, Ptr{Cdouble}, Cuint, Ptr{Cint},
+                Ptr{IfadvReport}),
+               ctx, stream_ptr(), dptr(fsrc), dptr(f), dptr(c.f·∂†), dptr(a.œÉ), dptr(u¬π), dptr(u¬≤), Œ¥t, dptr(c.cÃÑ),
+               dptr(c.œÅu), dptr(a.f), dptr(c.œÅuf), dptr(uOld), dptr(c.dœÅ), c.ŒªœÅ, limiter_enum(a.Œª), normal_enum(c.normalScheme),
+               A, perdir_mask(a.perdir), dirv, want ? rep : C_NULL)
+    report(check(ctx, rc), rep[])
+    nothing
+end
+function InterfaceAdvection.MPFMomStep!(a::Flow{D,T}, b::WaterLily.AbstractPoisson, c::cVOF{D,T,<:CuArray}, d::WaterLily.AbstractBody;
+                                        Œ¥t=last(a.Œît), udf=nothing, kwargs...) where {D,T<:Union{Float32,Float64}}
+    t‚ÇÅ = sum(a.Œît); t‚ÇÄ = t‚ÇÅ - Œ¥t; t‚Çò = t‚ÇÅ - Œ¥t / 2
+    stage!(fNow, tNow, tUdf, w, dtUdf) = begin   # forcing + projection of one RK stage (flow.jl:73-82 / :94-106), WaterLily side
+        fill!(a.Œº‚ÇÄ, 1)
+        InterfaceAdvection.viscSurfTenœÅu!(a.f, a.u, a.œÉ, fNow, c.Œ±, c.nÃÇ, c.f·∂†, c.ŒªŒº, c.Œº, c.ŒªœÅ, c.Œ∑; perdir=a.perdir)
+        u2œÅu!(c.nÃÇ, a.u‚Å∞, c.f, c.ŒªœÅ)
+        w == 1 && (a.u‚Å∞ .= a.u)
+        w == 1 ? InterfaceAdvection.updateU!(a.u, c.œÅu, c.nÃÇ, a.f, Œ¥t, fNow, c.ŒªœÅ, tNow, a.g, a.uBC) :
+                 InterfaceAdvection.updateU!(a.u, c.œÅu, c.nÃÇ, a.f, Œ¥t, fNow, c.ŒªœÅ, tNow, a.g, a.uBC, w)
+        WaterLily.udf!(a, udf, a.u‚Å∞, tUdf; dt=dtUdf, kwargs...)
+        WaterLily.BC!(a.u, a.uBC, a.exitBC, a.perdir)
+        InterfaceAdvection.updateL!(a.Œº‚ÇÄ, fNow, c.ŒªœÅ; perdir=a.perdir)
+        WaterLily.update!(b)
+        w == 1 ? InterfaceAdvection.myproject!(a, b) : InterfaceAdvection.myproject!(a, b, w)
+        WaterLily.BC!(a.u, a.uBC, a.exitBC, a.perdir)
+    end
+    copyto!(a.u‚Å∞, a.u)                                         # :61
+    fused_group!(a, c, c.f, c.f‚Å∞, a.u‚Å∞, a.u, a.u, Œ¥t)          # :61 (f‚Å∞‚Üêf), :69, :70
+    @. c.f‚Å∞ = (c.f‚Å∞ + c.f) / 2                                 # :74
+    stage!(c.f‚Å∞, t‚Çò, t‚ÇÄ, T(1 / 2), T(1 / 2) * Œ¥t)              # :73-82
+    copyto!(c.f‚Å∞, c.f)                                         # :89
+    fused_group!(a, c, c.f, c.f, a.u, a.u, a.u‚Å∞, Œ¥t)           # :91, :92
+    stage!(c.f, t‚ÇÅ, t‚ÇÅ, 1, Œ¥t)                                 # :94-106
+    push!(a.Œît, min(MPCFL(a, c), 1.2Œ¥t))                      # :108
 end
 
 end # module

@@ -347,9 +347,11 @@ struct FillReport {
   double maxf, minf;
   int64_t argmax[3], argmin[3];
   int dir;
-  int status;  // bit0 overfill, bit1 underfill, <0 NaN
+  int status;  // bit0 overfill, bit1 underfill, -1 NaN, -5 "divergence ... is exploding!"
+  double div_u0, div_u;  // |∇·u⁰|, |∇·u| at the reported cell (advection.jl:151,170)
 };
-template <class T> int reportFillError(const Grid& g, const SF<T>& f, int d, T tol, FillReport* rep) {  // advection.jl:145-189 (diagnostic prints dropped)
+// advection.jl:145-189: the diagnostic prints are dropped, the two throws are kept as negative statuses
+template <class T> int reportFillError(const Grid& g, const SF<T>& f, const VF<T>& u, const VF<T>& u0, int d, T tol, FillReport* rep) {
   // findmax/findmin over ALL of f (ghosts included), first occurrence wins
   T mx = -std::numeric_limits<T>::infinity(), mn = std::numeric_limits<T>::infinity();
   int64_t imx = 0, imn = 0;
@@ -390,6 +392,25 @@ template <class T> int reportFillError(const Grid& g, const SF<T>& f, int d, T t
     rep->argmax[0] = imx % g.n[0] + 1; rep->argmax[1] = (imx / g.n[0]) % g.n[1] + 1; rep->argmax[2] = imx / (g.n[0] * g.n[1]) + 1;
     rep->argmin[0] = imn % g.n[0] + 1; rep->argmin[1] = (imn / g.n[0]) % g.n[1] + 1; rep->argmin[2] = imn / (g.n[0] * g.n[1]) + 1;
     rep->dir = d + 1;
+    rep->div_u0 = rep->div_u = 0;
+  }
+  if (st > 0) {
+    // ((du⁰+du > 10) || isnan(du⁰+du)) && error("divergence, …, is exploding!")   (:160 for the max cell, :180 for the min cell)
+    auto check = [&](int64_t l) -> bool {
+      I3 I{{l % g.n[0] + 1, (l / g.n[0]) % g.n[1] + 1, l / (g.n[0] * g.n[1]) + 1}};
+      bool edge = false;
+      for (int a = 0; a < g.D; ++a) edge = edge || I.i[a] >= g.n[a];  // div needs I+δ inside the array
+      if (edge) return false;
+      T d0 = 0, d1 = 0;
+      for (int a = 0; a < g.D; ++a) { d0 += d_vec(a, I, u0); d1 += d_vec(a, I, u); }
+      const double a0 = std::fabs((double)d0), a1 = std::fabs((double)d1);
+      if (rep) { rep->div_u0 = a0; rep->div_u = a1; }
+      return (a0 + a1 > 10) || (a0 + a1 != a0 + a1);
+    };
+    if (((st & 1) && check(imx)) || ((st & 2) && check(imn))) {
+      if (rep) rep->status = -5;
+      return -5;
+    }
   }
   return st;
 }
@@ -403,7 +424,7 @@ int advectVOF1d(const Grid& g, const SF<T>& f, const SF<T>& ff, const SF<T>& al,
   loop(r_inside(g), [&](I3 I) {
     f(I) = f(I) + ((ff(I) - ff(sh(I, d, +1))) + (T(cbar[lin(g, I)]) * (d_vec(d, I, u) + d_vec(d, I, u0))) * dt / 2);
   });
-  int st = reportFillError(g, f, d, filltol, rep);
+  int st = reportFillError(g, f, u, u0, d, filltol, rep);
   cleanWisp(g, f, tol);
   BCf(g, f, perdir);
   return st;

@@ -21,7 +21,7 @@ LIMITERS = {"upwind": 0, "minmod": 1, "Koren": 2, "vanAlbada1": 3, "Sweby": 4, "
 
 class FillReport(C.Structure):
     _fields_ = [("maxf", C.c_double), ("minf", C.c_double), ("argmax", C.c_int64 * 3), ("argmin", C.c_int64 * 3),
-                ("dir", C.c_int), ("status", C.c_int)]
+                ("dir", C.c_int), ("status", C.c_int), ("div_u0", C.c_double), ("div_u", C.c_double)]
 
 
 def build(force: bool = False) -> None:

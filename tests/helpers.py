@@ -70,3 +70,39 @@ def inside(a, D):
 def dirO_for(nsteps_done, D):
     n = 1 + nsteps_done  # length(Δt)
     return tuple((n + i) % D + 1 for i in range(1, D + 1))
+
+
+def second_velocity(st, seed, scale, amp):
+    """A velocity field that differs from st["u"] in VALUE: scale·u + a smooth, non-solenoidal perturbation (so the dilation
+    terms see ∂u¹ ≠ ∂u²), periodic with the box, with the case's BC! applied."""
+    T, D, Ng = st["dtype"], st["D"], st["Ng"]
+    idx = np.indices(Ng).astype(np.float64)
+    ph = [2 * np.pi * idx[k] / (Ng[k] - 2) for k in range(D)]
+    v = np.empty(Ng + (D,), dtype=T, order="F")
+    for i in range(D):
+        w = np.sin(ph[0] + 0.37 * seed + 0.9 * i) * np.cos(ph[1] - 0.21 * seed + 0.4 * i)
+        if D == 3:
+            w = w * np.cos(ph[2] + 0.3 * seed - 0.7 * i)
+        v[..., i] = (T(scale) * st["u"][..., i].astype(np.float64) + amp * w).astype(T)
+    O.BC(v, st["uBC"], False, st["perdir"])
+    return v
+
+
+def oracle_mom_step_hook(st, f, u, dt, dirO, hook, lam="Koren", scheme="WH"):
+    """Transport part of MPFMomStep! (flow.jl:61,69-70,74,89-92) on the oracle with a `hook(u, rhou, f, stage)` standing in for
+    the forcing + projection blocks (flow.jl:75-82, 95-106): it may change u in place.  Mirrors api.mom_advect_step(project=...).
+    f and u are advanced in place; returns ρu after the corrector."""
+    T = st["dtype"]
+    a = alloc_cmom(st)
+    u0 = u.copy(order="F"); f0 = f.copy(order="F")                                                     # :61
+    O.u2rhou(a["rhou"], u0, f0, st["lam_rho"]); O.BC(a["rhou"], st["uBC"], False, st["perdir"])       # :69
+    O.advectVOFrhouu(f0, a["ff"], a["alpha"], a["nhat"], u0, u, dt, a["cbar"], a["rhou"], a["r"], a["Phi"], a["rhouf"], a["nhat"], u,
+                     a["alpha"], a["drho"], st["lam_rho"], lam, scheme, st["uBC"], st["perdir"], False, dirO)  # :70
+    f0[...] = (f0 + f) * T(0.5)                                                                        # :74
+    hook(u, a["rhou"], f0, "predictor")                                                                # :75-82
+    f0[...] = f                                                                                        # :89
+    O.u2rhou(a["rhou"], u0, f, st["lam_rho"]); O.BC(a["rhou"], st["uBC"], False, st["perdir"])        # :91
+    O.advectVOFrhouu(f, a["ff"], a["alpha"], a["nhat"], u, u, dt, a["cbar"], a["rhou"], a["r"], a["Phi"], a["rhouf"], a["nhat"], u0,
+                     a["alpha"], a["drho"], st["lam_rho"], lam, scheme, st["uBC"], st["perdir"], False, dirO)  # :92
+    hook(u, a["rhou"], f, "corrector")                                                                 # :95-106
+    return a["rhou"]

@@ -83,3 +83,69 @@ def test_bench_byte_accounting_matches_survey():
     assert b.algorithmic_bytes_per_cell_step(3, 4) == 376 and b.algorithmic_bytes_per_cell_step(3, 8) == 744
     assert b.vof_bytes_per_cell_step(3, 4) == 52 and b.vof_bytes_per_cell_step(3, 8) == 100 and b.vof_bytes_per_cell_step(2, 8) == 67
     assert set(b.WORKLOADS) >= {"C4_bubble_512_f32", "C3_dambreak_512x256x256_f32", "C2_enright_256_f32", "C1_zalesak_128_f64"}
+
+
+def _c_kind(arg: str) -> str:
+    arg = arg.strip()
+    if "*" in arg or "[" in arg:
+        return "ptr"
+    if arg.startswith("double"):
+        return "double"
+    if arg.startswith("unsigned"):
+        return "uint"
+    if arg.startswith("int64_t"):
+        return "int64"
+    if arg.startswith("int"):
+        return "int"
+    raise AssertionError(arg)
+
+
+def _jl_kind(t: str) -> str:
+    t = t.strip()
+    if t.startswith(("Ptr{", "Ref{")) or t == "Cstring":
+        return "ptr"
+    return {"Cdouble": "double", "Cuint": "uint", "Cint": "int", "Int64": "int64"}[t]
+
+
+def test_julia_ccall_signatures_match_header():
+    """The Julia glue cannot be executed here (no Julia in the image): at least hold every `ccall` in it against the prototype in
+    include/ifadv.h -- same symbol, same number of arguments, same C kind (pointer / double / int / unsigned) position by position,
+    and the report struct field for field."""
+    hdr = open(os.path.join(ROOT, "include", "ifadv.h")).read()
+    hdr_nc = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|int64_t|const char\*)\s+(ifadv_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", hdr_nc, flags=re.S):
+        args = [a for a in re.split(r",", m.group(2).replace("\n", " ")) if a.strip() and a.strip() != "void"]
+        protos[m.group(1)] = [_c_kind(a) for a in args]
+    jl = open(os.path.join(ROOT, "interfaceadvection.jl_b200", "julia", "IntfAdvB200Ext.jl")).read()
+    calls = re.findall(r"ccall\(\(:(ifadv_[a-z0-9_]+), LIB\),\s*\w+,\s*\((.*?)\),\s*\n?\s*ctx", jl, flags=re.S)
+    seen = set()
+    for name, types in calls:
+        # split the Julia type tuple at top-level commas
+        parts, depth, cur = [], 0, ""
+        for ch in types.replace("\n", " "):
+            if ch == "{":
+                depth += 1
+            elif ch == "}":
+                depth -= 1
+            if ch == "," and depth == 0:
+                parts.append(cur); cur = ""
+            else:
+                cur += ch
+        if cur.strip():
+            parts.append(cur)
+        kinds = [_jl_kind(p) for p in parts]
+        assert name in protos, name
+        assert kinds == protos[name], (name, kinds, protos[name])
+        seen.add(name)
+    assert {"ifadv_create", "ifadv_advect_vof", "ifadv_advect_vof_rhouu", "ifadv_u2rhou_advect_vof_rhouu", "ifadv_u2rhou", "ifadv_rhou2u",
+            "ifadv_mpcfl", "ifadv_last_error"} <= seen
+    # report struct: field order and C types
+    c_fields = re.search(r"typedef struct \{(.*?)\} ifadv_report;", hdr_nc, flags=re.S).group(1)
+    c_names = re.findall(r"\b(maxf|minf|argmax|argmin|dir|status|div_u0|div_u)\b", c_fields)
+    j_fields = re.search(r"struct IfadvReport\n(.*?)\nend", jl, flags=re.S).group(1)
+    j_names = re.findall(r"\b(maxf|minf|argmax|argmin|dir|status|div_u0|div_u)::", j_fields)
+    assert c_names == j_names == ["maxf", "minf", "argmax", "argmin", "dir", "status", "div_u0", "div_u"]
+    import ctypes as C
+    from interfaceadvection.jl_b200._lib import Report
+    assert [f[0] for f in Report._fields_] == c_names and C.sizeof(Report) == 8 * 2 + 8 * 6 + 4 * 2 + 8 * 2
