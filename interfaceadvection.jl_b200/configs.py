@@ -200,10 +200,12 @@ CONFIGS = {
 }
 
 
-def make_case(name_or_N, dtype=None, device=None, kind=None, Nl=None, origin=None):
+def make_case(name_or_N, dtype=None, device=None, kind=None, Nl=None, origin=None, vel=None):
     """Return dict(N, sdf, u, perdir, lam_rho, cmom) for a named config, or for an explicit (N, kind) at reduced size.
     Nl / origin: sample the velocity on a sub-box of Nl cells whose first interior cell has global index origin+1
-    (slab decomposition); N always describes the GLOBAL box the analytic fields are scaled to."""
+    (slab decomposition); N always describes the GLOBAL box the analytic fields are scaled to.
+    vel: None = the config's own generator; "enright" = the three-component discrete-curl LeVeque field (every sweep direction
+    carries a non-zero flux; compatible with walls and with periodic boxes); "tgv" = Taylor-Green (w ≡ 0 in 3-D)."""
     if isinstance(name_or_N, str):
         cfg = dict(CONFIGS[name_or_N])
         kind = name_or_N.split("_")[0]
@@ -236,5 +238,9 @@ def make_case(name_or_N, dtype=None, device=None, kind=None, Nl=None, origin=Non
         sdf, u = sdf_sloshing(N), tgv(N, T, **kw)
     else:
         raise KeyError(kind)
+    if vel == "enright" and len(N) == 3 and kind != "C2":
+        u = enright(N, T, **kw)
+    elif vel == "tgv" and kind in ("C2",):
+        u = tgv(N, T, **kw)
     cfg.update(sdf=sdf, u=u, dtype=dtype, kind=kind)
     return cfg

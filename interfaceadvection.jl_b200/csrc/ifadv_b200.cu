@@ -499,6 +499,7 @@ int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int dev
     // default: register-marching (y,z sweeps) + plane-marching (x sweep); "march": plane-marching for all; "tile": v1
     c->use_march = (e && std::string(e) == "tile") ? 0 : ((e && std::string(e) == "march") ? 2 : 1);
     c->use_along2 = (e && std::string(e) == "along1") ? 0 : 1;  // "along1": the first register-marching kernel for y/z sweeps
+    c->use_xrow = (e && std::string(e) == "xsweep") ? 0 : 1;    // "xsweep": the plane-marching kernel for CMOM x sweeps
   }
   if (cudaMalloc(&c->red_dev, sizeof(unsigned long long) * 32) != cudaSuccess ||
       cudaMemset(c->red_dev, 0, sizeof(unsigned long long) * 32) != cudaSuccess ||
@@ -799,7 +800,7 @@ int host_pipe_build(ifadv_ctx* c, int cp) {
     CU_CHECK(c, cudaEventCreateWithFlags(&h.ev_out, cudaEventDisableTiming));
     hp->ch.push_back(h);
     if (ifadv_create(&hp->ch.back().ctx, 3, ng, c->dtype, c->device) != 0) { c->err = "child context creation failed"; return -3; }
-    hp->ch.back().ctx->use_march = c->use_march; hp->ch.back().ctx->use_along2 = c->use_along2;
+    hp->ch.back().ctx->use_march = c->use_march; hp->ch.back().ctx->use_along2 = c->use_along2; hp->ch.back().ctx->use_xrow = c->use_xrow;
     maxpl = std::max(maxpl, (size_t)(h.hi - h.lo));
   }
   hp->nset = (int)std::min<size_t>(3, hp->ch.size());
@@ -992,7 +993,9 @@ int ifadv_check_nan(ifadv_ctx* c, void* stream) {
   bool nan = c->red_host[24] != 0ull;
   for (int s = 0; s < 3; ++s) nan = nan || c->red_host[8 * s + 4] != 0ull;  // the most recent call's own sweeps
   if (!nan) return 0;
+  // consumed: clear the sticky flag and the counts it was derived from
   CU_CHECK(c, cudaMemsetAsync(c->red_dev + 24, 0, sizeof(unsigned long long), st));
+  for (int s = 0; s < 3; ++s) CU_CHECK(c, cudaMemsetAsync(c->red_dev + 8 * s + 4, 0, sizeof(unsigned long long), st));
   return fail(c, -1, "NaN in f");
 }
 

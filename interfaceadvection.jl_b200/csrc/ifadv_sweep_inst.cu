@@ -1,15 +1,16 @@
 // ifadv_sweep_inst.cu -- instantiates the fused sweep kernels for ONE (T, D, MOM, family) combination, chosen with
-// -DIFADV_T=float|double -DIFADV_D=2|3 -DIFADV_MOM=0|1 -DIFADV_FAM=0..4, so that the instantiations compile in parallel:
+// -DIFADV_T=float|double -DIFADV_D=2|3 -DIFADV_MOM=0|1 -DIFADV_FAM=0..5, so that the instantiations compile in parallel:
 //   FAM 0  dispatcher (launch_sweep_dim) + v1 tile kernel        FAM 1  plane-marching kernel (march)
 //   FAM 2  register-marching kernel (along)                      FAM 3  lean register marching (along2), y / z sweeps
-//   FAM 4  lean plane marching along x (xsweep, CMOM only)       families 1-4 exist for 3-D grids only
+//   FAM 4  lean plane marching along x (xsweep, CMOM only)       FAM 5  warp-autonomous rows along x (xrow, CMOM only)
+//   families 1-5 exist for 3-D grids only
 #include <algorithm>
 #include <cstdlib>
 #include <limits>
 
 #include "ifadv_ctx.hpp"
 #ifndef IFADV_FAM
-#error "compile with -DIFADV_FAM=0..4"
+#error "compile with -DIFADV_FAM=0..5"
 #endif
 #if IFADV_FAM == 0
 #include "ifadv_sweep.cuh"
@@ -19,8 +20,10 @@
 #include "ifadv_along.cuh"
 #elif IFADV_FAM == 3
 #include "ifadv_along2.cuh"
-#else
+#elif IFADV_FAM == 4
 #include "ifadv_xsweep.cuh"
+#else
+#include "ifadv_xrow.cuh"
 #endif
 
 namespace ifadv {
@@ -212,18 +215,67 @@ static int launch_xsweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) 
 
 #endif
 
+#if IFADV_FAM == 5
+#ifndef IFADV_XP_XROW_R
+#define IFADV_XP_XROW_R 2
+#endif
+#ifndef IFADV_XP_XROW_MB
+#define IFADV_XP_XROW_MB 2
+#endif
+// v5: warp-autonomous row kernel for CMOM sweeps along x (3-D only, even row pitch, vector-aligned arrays)
+template <class T, int R, bool FUSED, bool KOREN, int MINB, bool SAMEU>
+static int launch_xrow_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  using TL = XRTile<R>;
+  SweepP<T> P;
+  fill_params<T>(c, q, 0, P);
+  if ((unsigned long long)c->g.S * 3ull >= 0xffffffffull) { c->err = "grid too large for 32-bit element offsets"; return -2; }
+  const size_t smem = TL::template Bytes<T>::cta;
+  auto kern = xrow_kernel<T, R, FUSED, KOREN, MINB, SAMEU>;
+  static unsigned long long attr_devs = 0ull;
+  if (!((attr_devs >> (c->device & 63)) & 1ull)) {
+    CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_devs |= 1ull << (c->device & 63);
+  }
+  const int nx = c->g.n[0] - 2, ny = c->g.n[1] - 2, nz = c->g.n[2] - 2;
+  const unsigned gx = (unsigned)((nx + TL::TX) / TL::TX), gy = (unsigned)((ny + TL::TY - 1) / TL::TY);  // elements 1..nx in tiles [60b, 60b+59]
+  int chunk = 128;  // one warm-up plane per chunk
+  while (chunk > 16 && (long long)gx * gy * ((nz + chunk - 1) / chunk) < 148 * 8) chunk >>= 1;
+  if (const char* e = getenv("IFADV_CHUNK")) chunk = std::max(4, atoi(e));  // measurement override
+  dim3 grid(gx, gy, (unsigned)((nz + chunk - 1) / chunk));
+  const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
+  if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
+  kern<<<grid, 256, smem, st>>>(P, chunk);
+  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_tag[c->prof_n] = (unsigned char)((q.fused ? 1 : 0) | ((2 * q.j + (q.fused ? 1 : 0)) << 1)); c->prof_n++; }
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+#endif
+
 // per-family entry points (3-D only), each defined and explicitly instantiated in its own translation unit
 template <class T, bool MOM> int launch_fam_march(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 template <class T, bool MOM> int launch_fam_along(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 template <class T, bool MOM> int launch_fam_along2(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 template <class T, bool MOM> int launch_fam_xsweep(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
+template <class T, bool MOM> int launch_fam_xrow(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
+// the row kernel moves two cells per access: rows must start vector-aligned (even row pitch) and so must every array
+template <class T> static bool xrow_ok(const ifadv_ctx* c, const SweepCfg<T>& q) {
+  if (c->g.n[0] & 1) return false;
+  const uintptr_t m = 2 * sizeof(T) - 1;
+  const uintptr_t a = (uintptr_t)q.f_in | (uintptr_t)q.f_out | (uintptr_t)q.u | (uintptr_t)q.u0 | (uintptr_t)q.rhou_in | (uintptr_t)q.rhou_out |
+                      (uintptr_t)q.uOld;
+  return (a & m) == 0 && ((uintptr_t)q.cbar & 1) == 0;
+}
 
 #if IFADV_FAM == 0
 template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   if constexpr (D == 3) {
     if (c->use_march == 1 && c->use_along2) {
       if (q.j != 0) return launch_fam_along2<T, MOM>(c, st, q);
-      if constexpr (MOM) return launch_fam_xsweep<T, MOM>(c, st, q);
+      if constexpr (MOM) {
+        if (c->use_xrow && xrow_ok<T>(c, q)) return launch_fam_xrow<T, MOM>(c, st, q);
+        return launch_fam_xsweep<T, MOM>(c, st, q);
+      }
     }
     if (c->use_march == 1 && q.j != 0) return launch_fam_along<T, MOM>(c, st, q);
     if (c->use_march) return launch_fam_march<T, MOM>(c, st, q);
@@ -300,7 +352,7 @@ template <class T, bool MOM> int launch_fam_along2(ifadv_ctx* c, cudaStream_t st
 }
 template int launch_fam_along2<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
 
-#else
+#elif IFADV_FAM == 4
 template <class T, bool MOM> int launch_fam_xsweep(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   static_assert(MOM, "the pure-VOF x-sweep runs the march kernel");
   constexpr int CP = (sizeof(T) == 4) ? 2 : 1;
@@ -314,6 +366,24 @@ template <class T, bool MOM> int launch_fam_xsweep(ifadv_ctx* c, cudaStream_t st
   return koren ? launch_xsweep_t<T, CP, false, true, MB>(c, st, q) : launch_xsweep_t<T, CP, false, false, MB>(c, st, q);
 }
 template int launch_fam_xsweep<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
+
+#else
+template <class T, bool MOM> int launch_fam_xrow(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  static_assert(MOM, "the pure-VOF x-sweep runs the march kernel");
+  constexpr int RR = IFADV_XP_XROW_R, MB = IFADV_XP_XROW_MB;
+  const bool koren = q.lim == 2;
+  if (koren && q.u == q.u0) {  // one velocity array for u¹ and u² (MPFMomStep!): the SAMEU instantiations
+    if (q.fused) return launch_xrow_t<T, RR, true, true, MB, true>(c, st, q);
+    return launch_xrow_t<T, RR, false, true, MB, true>(c, st, q);
+  }
+#ifdef IFADV_XROW_DEV  // development builds: only the two hot instantiations, everything else runs the plane-marching kernel
+  return launch_fam_xsweep<T, MOM>(c, st, q);
+#else
+  if (q.fused) return koren ? launch_xrow_t<T, RR, true, true, MB, false>(c, st, q) : launch_xrow_t<T, RR, true, false, MB, false>(c, st, q);
+  return koren ? launch_xrow_t<T, RR, false, true, MB, false>(c, st, q) : launch_xrow_t<T, RR, false, false, MB, false>(c, st, q);
+#endif
+}
+template int launch_fam_xrow<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
 #endif
 
 }  // namespace ifadv

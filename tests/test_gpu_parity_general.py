@@ -364,7 +364,11 @@ def test_sticky_nan_without_report(ia):
     fd, ud = ia.from_numpy(bad), ia.from_numpy(st["u"])
     ctx = ia.context_for(fd)
     s = torch.cuda.current_stream().cuda_stream
-    ctx.check_nan(s)  # clean slate
+    try:
+        ctx.check_nan(s)  # clean slate: the context is shared (cached by shape) with other tests that leave a NaN behind
+    except ia.IfadvError:
+        pass
+    ctx.check_nan(s)      # reading the flags consumed them
     assert ia.advectVOF(fd, d["ff"], d["alpha"], d["nhat"], ud, ud, 1.0, d["cbar"], d["rhouf"], st["lam_rho"], "WH", (), (1, 2), check=False) == 0
     # a later, healthy call WITH a report still reports the earlier NaN
     gd = ia.from_numpy(st["f"])
