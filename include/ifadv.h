@@ -143,6 +143,30 @@ int ifadv_apply_vof_samples(ifadv_ctx* ctx, void* stream, void* f, void* alpha, 
  * before its first write to f (one-shot).  event: cudaEvent_t. */
 int ifadv_defer_f_writes_until(ifadv_ctx* ctx, void* event);
 
+/* ---- z-slab decomposition across the GPUs of one box (one process per GPU) ------------------------------------------------
+ * New functionality (the reference is single-device); its oracle is the single-GPU run: owned cells come out
+ * BIT-IDENTICAL.  The global grid N1 x N2 x (nz·nranks) is cut into z-slabs; a rank's arrays hold, along z,
+ *     [array ghost | G ghost planes (if a lower neighbour exists) | nz owned planes | G ghost planes (upper neighbour) | array ghost]
+ * i.e. Ng_local[2] = nz + 2 + (#neighbour sides)·G, with the reference's layout otherwise.  G >= 3 covers the reach of one
+ * directional sweep (3 planes below / 2 above).  On a slab context the CMOM entry points update the owned planes only and, after
+ * every directional sweep, exchange the G boundary planes of what the sweep produced (f, ρu and once c̄) with both neighbours --
+ * ncclSend/ncclRecv in one group on the caller's stream -- so the next sweep reads them like any interior plane; f leaves the
+ * call with valid ghost planes.  The caller keeps the ghost planes of u, u⁰/uOld valid (ifadv_exchange_planes after every change)
+ * and passes a perdir_mask without the z bit when nranks > 1 (the periodic wrap goes through the exchange).  ifadv_sum_inside and
+ * ifadv_mpcfl reduce over the owned planes and all-reduce, so every rank gets the global value.  Communication failures return -4.
+ * comm: an ncclComm_t (from NCCL.jl / the host framework; or ifadv_nccl_comm_init below), borrowed for the context's lifetime. */
+int ifadv_create_slab(ifadv_ctx** ctx, const int64_t Ng_local[3], int dtype, int device, void* nccl_comm, int rank, int nranks,
+                      int ghost_planes, int periodic_z);
+/* owned plane range [kz0, kz1) (1-based), neighbour ranks (-1 = physical boundary), bytes sent by this context's exchanges */
+int ifadv_slab_info(const ifadv_ctx* ctx, int* kz0, int* kz1, int* lower, int* upper, int64_t* bytes_sent);
+/* exchange the ghost planes of `ncomp` fields (component stride = one scalar field) of `elem_bytes`-byte elements; no-op on a
+ * single-GPU context */
+int ifadv_exchange_planes(ifadv_ctx* ctx, void* stream, void* field, int ncomp, int elem_bytes);
+/* convenience for hosts without an NCCL binding of their own: rank 0 creates the id, every rank initialises with it */
+int ifadv_nccl_unique_id(char id[128]);
+int ifadv_nccl_comm_init(void** comm, int nranks, const char id[128], int rank, int device);
+int ifadv_nccl_comm_destroy(void* comm);
+
 /* NaN detection without a per-call synchronisation: calls made with report == NULL never look at their reductions, so a NaN in f
  * (error("NaN!"), src/advection.jl:148) would go unnoticed.  The NaN count of every call is folded into a sticky device flag when the
  * next call starts; this entry point (and every call WITH a report) reads it: returns -1 if any sweep since the last check produced a

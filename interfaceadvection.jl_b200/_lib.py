@@ -62,6 +62,12 @@ def lib():
         L.ifadv_host_step_bytes.argtypes = [vp, i64p, i64p, i32p]
         L.ifadv_defer_f_writes_until.argtypes = [vp, vp]
         L.ifadv_check_nan.argtypes = [vp, vp]
+        L.ifadv_create_slab.argtypes = [C.POINTER(vp), i64p, i32, i32, vp, i32, i32, i32, i32]
+        L.ifadv_slab_info.argtypes = [vp, i32p, i32p, i32p, i32p, i64p]
+        L.ifadv_exchange_planes.argtypes = [vp, vp, vp, i32, i32]
+        L.ifadv_nccl_unique_id.argtypes = [C.c_char_p]
+        L.ifadv_nccl_comm_init.argtypes = [C.POINTER(vp), i32, C.c_char_p, i32, i32]
+        L.ifadv_nccl_comm_destroy.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -86,15 +92,29 @@ def _i3(v, D):
 class Context:
     """ifadv_ctx: one per (device, grid, dtype).  Ng = array extents including ghosts (N .+ 2)."""
 
-    def __init__(self, Ng, dtype: str, device: int = 0):
+    def __init__(self, Ng, dtype: str, device: int = 0, slab=None):
+        """slab: None, or dict(comm=<ncclComm_t as int>, rank, nranks, G, per_z) -> ifadv_create_slab (Ng = LOCAL extents)."""
         self.D = len(Ng)
         self.Ng = tuple(int(n) for n in Ng)
         self.dtype = {"float32": 0, "float64": 1}[dtype]
         self._h = C.c_void_p()
         ng = (C.c_int64 * 3)(*(list(self.Ng) + [1] * (3 - self.D)))
-        rc = lib().ifadv_create(C.byref(self._h), self.D, ng, self.dtype, int(device))
+        if slab is None:
+            rc = lib().ifadv_create(C.byref(self._h), self.D, ng, self.dtype, int(device))
+        else:
+            rc = lib().ifadv_create_slab(C.byref(self._h), ng, self.dtype, int(device), C.c_void_p(slab["comm"]), int(slab["rank"]),
+                                         int(slab["nranks"]), int(slab["G"]), int(bool(slab["per_z"])))
         if rc != 0:
-            raise IfadvError(f"ifadv_create failed ({rc}): a CUDA device is required, there is no CPU fallback")
+            raise IfadvError(f"ifadv_create{'_slab' if slab else ''} failed ({rc}): a CUDA device is required, there is no CPU fallback")
+
+    def slab_info(self):
+        """-> dict(kz0, kz1, lower, upper, bytes_sent): owned planes [kz0, kz1) (1-based), neighbour ranks, exchange volume"""
+        a, b, lo, up, n = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0), C.c_int64(0)
+        self._chk(lib().ifadv_slab_info(self._h, C.byref(a), C.byref(b), C.byref(lo), C.byref(up), C.byref(n)))
+        return dict(kz0=a.value, kz1=b.value, lower=lo.value, upper=up.value, bytes_sent=int(n.value))
+
+    def exchange_planes(self, stream, field, ncomp, elem_bytes):
+        return self._chk(lib().ifadv_exchange_planes(self._h, stream, field, int(ncomp), int(elem_bytes)))
 
     def close(self):
         if self._h:
@@ -206,3 +226,23 @@ class Context:
         r = C.byref(report) if report is not None else None
         return self._chk(lib().ifadv_mom_advect_step_host(self._h, f_host, u_host, rhou_host, float(dt), float(lam_rho), int(limiter),
                                                           int(scheme), _d3(uBC, self.D), perdir_mask(perdir), _i3(dirO, self.D), r))
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = lib().ifadv_nccl_unique_id(buf)
+    if rc != 0:
+        raise IfadvError(f"ifadv_nccl_unique_id failed ({rc})")
+    return buf.raw
+
+
+def nccl_comm_init(nranks: int, uid: bytes, rank: int, device: int) -> int:
+    comm = C.c_void_p()
+    rc = lib().ifadv_nccl_comm_init(C.byref(comm), int(nranks), C.create_string_buffer(uid, 128), int(rank), int(device))
+    if rc != 0:
+        raise IfadvError(f"ifadv_nccl_comm_init failed ({rc})")
+    return comm.value
+
+
+def nccl_comm_destroy(comm: int):
+    lib().ifadv_nccl_comm_destroy(C.c_void_p(comm))

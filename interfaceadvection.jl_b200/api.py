@@ -88,6 +88,11 @@ def context_for(f: torch.Tensor) -> Context:
     return _contexts[key]
 
 
+def register_context(shape, dtype, device_index, ctx: Context):
+    """Bind a pre-built context (e.g. a z-slab context, Context(..., slab=...)) to every field of this local shape / dtype / device."""
+    _contexts[(tuple(shape), dtype, device_index)] = ctx
+
+
 def _stream(t: torch.Tensor) -> int:
     if not t.is_cuda:
         raise IfadvError("the B200 path needs CUDA tensors; there is no CPU fallback")
@@ -371,6 +376,7 @@ def mom_advect_step(a: Flow, c: cVOF, dt=None, project: Optional[Callable] = Non
     ctx.axpby(s, _p(c.f0), 0.5, _p(c.f0), 0.5, _p(c.f))               # :74
     if project is not None:
         project(a, c, "predictor")                                    # :75-82 (WaterLily side)
+        ctx.exchange_planes(s, _p(a.u), a.D, a.u.element_size())      # z-slab: the changed u needs its ghost planes (no-op on one GPU)
     _copy(c.f0, c.f)                                                  # :89
     if fused:
         u2rhou_advectfq(a, c, c.f, c.f, a.u, a.u, a.u0, dt, check=check)    # :91, :92
@@ -380,6 +386,7 @@ def mom_advect_step(a: Flow, c: cVOF, dt=None, project: Optional[Callable] = Non
         advectfq(a, c, c.f, a.u, a.u, a.u0, dt, check=check)          # :92
     if project is not None:
         project(a, c, "corrector")                                    # :95-106 (WaterLily side)
+        ctx.exchange_planes(s, _p(a.u), a.D, a.u.element_size())
 
 
 def MPFMomStep(a: Flow, b, c: cVOF, d=None, dt=None, project: Optional[Callable] = None, check=False):

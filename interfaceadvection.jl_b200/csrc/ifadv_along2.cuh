@@ -73,8 +73,10 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
   const int nA = g.n[J], nX = g.n[0], nCc = g.n[DCC];
   const unsigned sA = (unsigned)((J == 1) ? g.s1 : g.s2), sCc = (unsigned)((DCC == 1) ? g.s1 : g.s2);
   const bool perA = (g.per >> J) & 1u, perX = g.per & 1u, perC = (g.per >> DCC) & 1u;
-  const int ox = 2 + blockIdx.x * 32, oc = 2 + blockIdx.y * TCT;
-  const int k0 = 2 + blockIdx.z * chunk, k1 = min(k0 + chunk, nA);
+  // dimension 3 is restricted to the planes [kz0, kz1) (z-slabs): the march range for J == 2, the tile rows for J == 1
+  const int ox = 2 + blockIdx.x * 32, oc = ((J == 1) ? P.kz0 : 2) + blockIdx.y * TCT;
+  const int chi = (J == 1) ? P.kz1 : nCc;  // first cross index not updated
+  const int k0 = ((J == 2) ? P.kz0 : 2) + blockIdx.z * chunk, k1 = min(k0 + chunk, (J == 2) ? P.kz1 : nA);
   const int ks = k0 - 4;
   const T lr = P.lr, omlr = P.omlr, dt = P.dt;
   const T lam1 = lin_interp(T(1), lr, omlr);
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
   for (int j = 0; j < CPT; ++j) {
     const int vcc = oc + tc + j * TR;
     go[j] = (unsigned)(mapc(vx, nX, perX) - 1) + (unsigned)(mapc(vcc, nCc, perC) - 1) * sCc;
-    valid[j] = vx <= nX - 1 && vcc <= nCc - 1;
+    valid[j] = vx <= nX - 1 && vcc < chi;
     dirC[j] = !perC && (vcc == 2 || vcc == nCc);
   }
   int eh = 0;

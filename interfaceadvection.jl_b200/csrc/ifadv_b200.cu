@@ -2,6 +2,8 @@
 // Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -shared
 // There is no CPU fallback: every entry point needs a CUDA device and fails with -3 otherwise.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <cmath>
 #include <cstdio>
@@ -145,13 +147,13 @@ template <class T, bool VEC> __global__ void __launch_bounds__(256) axpby_kernel
 
 // Field reductions over inside(f): persistent grid, a warp walks whole x-rows (coalesced), per-lane partials, one atomic per CTA.
 // MPCFL's two reductions (flow.jl:267-271): max flux_out and max maxTotalFlux over inside(σ)
-template <class T, int D> __global__ void __launch_bounds__(256) cfl_kernel(const T* u, const Geo g, unsigned long long* red) {
-  const int ny = g.n[1] - 2, nz = (D == 3) ? g.n[2] - 2 : 1;
+template <class T, int D> __global__ void __launch_bounds__(256) cfl_kernel(const T* u, const Geo g, unsigned long long* red, int kz0, int kz1) {
+  const int ny = g.n[1] - 2, nz = (D == 3) ? kz1 - kz0 : 1;
   const long long rows = (long long)ny * nz;
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   double fo = 0.0, tf = 0.0;
   for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * wpb) {
-    const int y = 2 + (int)(r % ny), z = (D == 3) ? 2 + (int)(r / ny) : 1;
+    const int y = 2 + (int)(r % ny), z = (D == 3) ? kz0 + (int)(r / ny) : 1;
     const long long l0 = lin3(g, 0, y, z);
     for (int x = 2 + lane; x <= g.n[0] - 1; x += 32) {
       const long long l = l0 + x;
@@ -183,13 +185,13 @@ template <class T, int D> __global__ void __launch_bounds__(256) cfl_kernel(cons
   }
 }
 
-template <class T, int D> __global__ void __launch_bounds__(256) sum_inside_kernel(const T* f, const Geo g, double* out) {
-  const int ny = g.n[1] - 2, nz = (D == 3) ? g.n[2] - 2 : 1;
+template <class T, int D> __global__ void __launch_bounds__(256) sum_inside_kernel(const T* f, const Geo g, double* out, int kz0, int kz1) {
+  const int ny = g.n[1] - 2, nz = (D == 3) ? kz1 - kz0 : 1;
   const long long rows = (long long)ny * nz;
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   double s = 0.0;
   for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * wpb) {
-    const int y = 2 + (int)(r % ny), z = (D == 3) ? 2 + (int)(r / ny) : 1;
+    const int y = 2 + (int)(r % ny), z = (D == 3) ? kz0 + (int)(r / ny) : 1;
     const long long l0 = lin3(g, 0, y, z);
     for (int x = 2 + lane; x <= g.n[0] - 1; x += 32) s += (double)f[l0 + x];
   }
@@ -349,6 +351,80 @@ static int finish_report(ifadv_ctx* c, cudaStream_t st, const int* dirO, double 
 // ------------------------------------------------------------------------------------------------------------
 // typed drivers
 // ------------------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------------------
+// z-slab decomposition: NCCL ghost-plane exchange (new functionality, no reference counterpart: SURVEY.md §8e)
+// ------------------------------------------------------------------------------------------------------------
+// NCCL is resolved at run time (the copy the process has already loaded -- e.g. the one bundled with PyTorch or NCCL.jl -- else the
+// system libnccl.so.2), so the single-GPU product has no link-time dependency on it.
+namespace {
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  const char* (*GetErrorString)(ncclResult_t);
+  bool ok;
+};
+NcclApi* nccl_api() {
+  static NcclApi api = [] {
+    NcclApi a{};
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return a;
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
+    a.GroupStart = (decltype(a.GroupStart))dlsym(h, "ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))dlsym(h, "ncclGroupEnd");
+    a.Send = (decltype(a.Send))dlsym(h, "ncclSend");
+    a.Recv = (decltype(a.Recv))dlsym(h, "ncclRecv");
+    a.AllReduce = (decltype(a.AllReduce))dlsym(h, "ncclAllReduce");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.GroupStart && a.GroupEnd && a.Send && a.Recv && a.AllReduce;
+    return a;
+  }();
+  return &api;
+}
+#define NCCL_CHECK(ctx, call)                                                                                  \
+  do {                                                                                                         \
+    ncclResult_t r_ = (call);                                                                                  \
+    if (r_ != ncclSuccess) {                                                                                   \
+      if (ctx) (ctx)->err = std::string(#call) + ": " + (nccl_api()->GetErrorString ? nccl_api()->GetErrorString(r_) : "NCCL error"); \
+      return -4;                                                                                               \
+    }                                                                                                          \
+  } while (0)
+
+// Ghost planes of `ncomp` fields of `esz`-byte elements (component stride S elements): my top G owned planes -> the upper neighbour's
+// lower ghost planes, my bottom G owned planes -> the lower neighbour's upper ghost planes; ONE NCCL group on the caller's stream.
+// Posting order (sends: up, down; receives: from below, from above) lets NCCL match the pairs when both neighbours are one peer.
+int slab_exchange(ifadv_ctx* c, cudaStream_t st, void* base, size_t esz, int ncomp) {
+  const ifadv_slab& sl = c->slab;
+  if (sl.nranks <= 1) return 0;
+  NcclApi* A = nccl_api();
+  if (!A->ok) return fail(c, -4, "NCCL is not available");
+  const size_t pl = esz * (size_t)c->g.s2, comp = esz * (size_t)c->g.S;
+  const size_t G = (size_t)sl.G;
+  ncclComm_t comm = (ncclComm_t)sl.comm;
+  NCCL_CHECK(c, A->GroupStart());
+  for (int i = 0; i < ncomp; ++i) {
+    char* b = (char*)base + comp * i;
+    // 0-based storage plane p holds 1-based plane p+1
+    if (sl.upper >= 0) NCCL_CHECK(c, A->Send(b + pl * (size_t)(c->kz1 - 1 - sl.G), pl * G, ncclInt8, sl.upper, comm, st));
+    if (sl.lower >= 0) NCCL_CHECK(c, A->Send(b + pl * (size_t)(c->kz0 - 1), pl * G, ncclInt8, sl.lower, comm, st));
+    if (sl.lower >= 0) NCCL_CHECK(c, A->Recv(b + pl * (size_t)(c->kz0 - 1 - sl.G), pl * G, ncclInt8, sl.lower, comm, st));
+    if (sl.upper >= 0) NCCL_CHECK(c, A->Recv(b + pl * (size_t)(c->kz1 - 1), pl * G, ncclInt8, sl.upper, comm, st));
+    c->slab.bytes_sent += (long long)(pl * G) * ((sl.upper >= 0) + (sl.lower >= 0));
+  }
+  NCCL_CHECK(c, A->GroupEnd());
+  return 0;
+}
+}  // namespace
+
 template <class T>
 static int advect_vof_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* al, const T* u, const T* u0, double dt, int8_t* cbar, T* rhouf,
                         double lr, int ns, unsigned per, const int* dirO, int flags, ifadv_report* rep) {
@@ -413,9 +489,16 @@ static int advect_vof_rhouu_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* Phi
     if (s == D - 1 && wait_f) CU_CHECK(c, cudaStreamWaitEvent(st, wait_f, 0));  // the last sweep is the first to write f
     int rc = launch_sweep<T, true>(c, st, q);
     if (rc) return rc;
+    if (c->slab.nranks > 1 && s < D - 1) {
+      // z-slab: the next sweep reads the neighbours' planes of what this sweep produced (stencil reach 3 below / 2 above)
+      if ((rc = slab_exchange(c, st, fb[s + 1], sizeof(T), 1))) return rc;
+      if ((rc = slab_exchange(c, st, rb[s + 1], sizeof(T), D))) return rc;
+      if (s == 0 && (rc = slab_exchange(c, st, cbar, 1, 1))) return rc;  // c̄ of the call (written by sweep 1 on owned planes)
+    }
   }
   int rc = launch_bcf<T>(c, st, f, per);
   if (rc) return rc;
+  if (c->slab.nranks > 1 && (rc = slab_exchange(c, st, f, sizeof(T), 1))) return rc;  // the caller's f leaves with valid ghost planes
   if (rep) return finish_report<T>(c, st, dirO, 100.0 * (double)std::numeric_limits<T>::epsilon(), rep, u, u0);  // 10tol, advection.jl:85
   return 0;
 }
@@ -481,11 +564,13 @@ int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int dev
   if (cudaSetDevice(device) != cudaSuccess) return -3;
   ifadv_ctx* c = new ifadv_ctx();
   c->D = D; c->dtype = dtype; c->device = device; c->launches = 0;
+  c->slab = ifadv_slab{nullptr, 0, 1, 0, 0, 0, -1, -1, 0};
   c->g.n[0] = (int)Ng[0]; c->g.n[1] = (int)Ng[1]; c->g.n[2] = (D == 3) ? (int)Ng[2] : 1;
   c->g.s1 = c->g.n[0]; c->g.s2 = (long long)c->g.n[0] * c->g.n[1];
   c->g.S = c->g.s2 * c->g.n[2];
   c->g.per = 0;
   for (int k = 0; k < 3; ++k) c->Ng[k] = c->g.n[k];
+  c->kz0 = 2; c->kz1 = c->g.n[2];
   for (auto& p : c->w) p = nullptr;
   c->pin_f = c->pin_u = c->pin_ru = nullptr;
   c->own_stream = nullptr;
@@ -572,6 +657,7 @@ int ifadv_advect_vof(ifadv_ctx* c, void* stream, void* f, void* ff, void* alpha,
   (void)nhat;
   int rc = check_common(c, normal_scheme, dirO);
   if (rc) return rc;
+  if (c->slab.nranks > 1) return fail(c, -2, "z-slab contexts run the CMOM path (ifadv_advect_vof_rhouu / ifadv_u2rhou_advect_vof_rhouu)");
   if (!f || !ff || !u || !u0 || !cbar || (c->D == 3 && !alpha)) return fail(c, -2, "null array");
   cudaStream_t st = (cudaStream_t)stream;
   if (c->dtype == IFADV_F32)
@@ -657,17 +743,21 @@ int ifadv_mpcfl(ifadv_ctx* c, void* stream, const void* u, double nu, double mu,
   cudaStream_t st = (cudaStream_t)stream;
   CU_CHECK(c, cudaMemsetAsync(c->misc_dev, 0, sizeof(unsigned long long) * 8, st));
   const int bx = 256;
-  const long long rows_ = (long long)(c->g.n[1] - 2) * (c->D == 3 ? c->g.n[2] - 2 : 1);
+  const long long rows_ = (long long)(c->g.n[1] - 2) * (c->D == 3 ? c->kz1 - c->kz0 : 1);
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((rows_ + 7) / 8, 148LL * 8));
   if (c->dtype == IFADV_F32) {
-    if (c->D == 2) cfl_kernel<float, 2><<<grid, bx, 0, st>>>((const float*)u, c->g, c->misc_dev);
-    else cfl_kernel<float, 3><<<grid, bx, 0, st>>>((const float*)u, c->g, c->misc_dev);
+    if (c->D == 2) cfl_kernel<float, 2><<<grid, bx, 0, st>>>((const float*)u, c->g, c->misc_dev, c->kz0, c->kz1);
+    else cfl_kernel<float, 3><<<grid, bx, 0, st>>>((const float*)u, c->g, c->misc_dev, c->kz0, c->kz1);
   } else {
-    if (c->D == 2) cfl_kernel<double, 2><<<grid, bx, 0, st>>>((const double*)u, c->g, c->misc_dev);
-    else cfl_kernel<double, 3><<<grid, bx, 0, st>>>((const double*)u, c->g, c->misc_dev);
+    if (c->D == 2) cfl_kernel<double, 2><<<grid, bx, 0, st>>>((const double*)u, c->g, c->misc_dev, c->kz0, c->kz1);
+    else cfl_kernel<double, 3><<<grid, bx, 0, st>>>((const double*)u, c->g, c->misc_dev, c->kz0, c->kz1);
   }
   c->launches++;
   CU_CHECK(c, cudaGetLastError());
+  if (c->slab.nranks > 1) {  // order-preserving keys of non-negative maxima: the global maximum is the maximum of the keys
+    if (!nccl_api()->ok) return fail(c, -4, "NCCL is not available");
+    NCCL_CHECK(c, nccl_api()->AllReduce(c->misc_dev, c->misc_dev, 2, ncclUint64, ncclMax, (ncclComm_t)c->slab.comm, st));
+  }
   CU_CHECK(c, cudaMemcpyAsync(c->misc_host, c->misc_dev, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
   CU_CHECK(c, cudaStreamSynchronize(st));
   // ghosts of σ are 0 after fill!(a.σ,0) (flow.jl:264), so the maxima are at least 0 -- the keys start at 0.0's floor
@@ -691,18 +781,22 @@ int ifadv_sum_inside(ifadv_ctx* c, void* stream, const void* f, double* out) {
   cudaStream_t st = (cudaStream_t)stream;
   CU_CHECK(c, cudaMemsetAsync(c->misc_dev, 0, sizeof(unsigned long long) * 8, st));
   const int bx = 256;
-  const long long rows_ = (long long)(c->g.n[1] - 2) * (c->D == 3 ? c->g.n[2] - 2 : 1);
+  const long long rows_ = (long long)(c->g.n[1] - 2) * (c->D == 3 ? c->kz1 - c->kz0 : 1);
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((rows_ + 7) / 8, 148LL * 8));
   double* acc = reinterpret_cast<double*>(c->misc_dev);
   if (c->dtype == IFADV_F32) {
-    if (c->D == 2) sum_inside_kernel<float, 2><<<grid, bx, 0, st>>>((const float*)f, c->g, acc);
-    else sum_inside_kernel<float, 3><<<grid, bx, 0, st>>>((const float*)f, c->g, acc);
+    if (c->D == 2) sum_inside_kernel<float, 2><<<grid, bx, 0, st>>>((const float*)f, c->g, acc, c->kz0, c->kz1);
+    else sum_inside_kernel<float, 3><<<grid, bx, 0, st>>>((const float*)f, c->g, acc, c->kz0, c->kz1);
   } else {
-    if (c->D == 2) sum_inside_kernel<double, 2><<<grid, bx, 0, st>>>((const double*)f, c->g, acc);
-    else sum_inside_kernel<double, 3><<<grid, bx, 0, st>>>((const double*)f, c->g, acc);
+    if (c->D == 2) sum_inside_kernel<double, 2><<<grid, bx, 0, st>>>((const double*)f, c->g, acc, c->kz0, c->kz1);
+    else sum_inside_kernel<double, 3><<<grid, bx, 0, st>>>((const double*)f, c->g, acc, c->kz0, c->kz1);
   }
   c->launches++;
   CU_CHECK(c, cudaGetLastError());
+  if (c->slab.nranks > 1) {  // a slab sums its owned planes; the result is the global mass on every rank
+    if (!nccl_api()->ok) return fail(c, -4, "NCCL is not available");
+    NCCL_CHECK(c, nccl_api()->AllReduce(c->misc_dev, c->misc_dev, 1, ncclDouble, ncclSum, (ncclComm_t)c->slab.comm, st));
+  }
   CU_CHECK(c, cudaMemcpyAsync(c->misc_host, c->misc_dev, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
   CU_CHECK(c, cudaStreamSynchronize(st));
   memcpy(out, c->misc_host, sizeof(double));
@@ -983,6 +1077,69 @@ int ifadv_defer_f_writes_until(ifadv_ctx* c, void* event) {
   if (!c) return -2;
   c->wait_f = (cudaEvent_t)event;
   return 0;
+}
+
+// ---- z-slab decomposition ------------------------------------------------------------------------------------------------
+int ifadv_nccl_unique_id(char id[128]) {
+  if (!id) return -2;
+  NcclApi* A = nccl_api();
+  if (!A->ok) return -4;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId u;
+  if (A->GetUniqueId(&u) != ncclSuccess) return -4;
+  memcpy(id, &u, 128);
+  return 0;
+}
+int ifadv_nccl_comm_init(void** comm, int nranks, const char id[128], int rank, int device) {
+  if (!comm || !id || nranks < 1 || rank < 0 || rank >= nranks) return -2;
+  NcclApi* A = nccl_api();
+  if (!A->ok) return -4;
+  if (cudaSetDevice(device) != cudaSuccess) return -3;
+  ncclUniqueId u;
+  memcpy(&u, id, 128);
+  ncclComm_t c;
+  if (A->CommInitRank(&c, nranks, u, rank) != ncclSuccess) return -4;
+  *comm = (void*)c;
+  return 0;
+}
+int ifadv_nccl_comm_destroy(void* comm) {
+  if (!comm) return 0;
+  NcclApi* A = nccl_api();
+  if (!A->ok) return -4;
+  return A->CommDestroy((ncclComm_t)comm) == ncclSuccess ? 0 : -4;
+}
+
+int ifadv_create_slab(ifadv_ctx** out, const int64_t Ng_local[3], int dtype, int device, void* nccl_comm, int rank, int nranks,
+                      int ghost_planes, int periodic_z) {
+  if (!out || !Ng_local || nranks < 1 || rank < 0 || rank >= nranks || ghost_planes < 3) return -2;
+  const int G = ghost_planes;
+  const bool lo = nranks > 1 && (rank > 0 || periodic_z), hi = nranks > 1 && (rank < nranks - 1 || periodic_z);
+  const int glo = lo ? G : 0, ghi = hi ? G : 0;
+  if (Ng_local[2] - 2 - glo - ghi < G) return -2;  // a slab sends G owned planes to each neighbour
+  if (nranks > 1 && !nccl_comm) return -2;
+  int rc = ifadv_create(out, 3, Ng_local, dtype, device);
+  if (rc) return rc;
+  ifadv_ctx* c = *out;
+  c->slab.comm = nccl_comm; c->slab.rank = rank; c->slab.nranks = nranks; c->slab.G = G; c->slab.glo = glo; c->slab.ghi = ghi;
+  c->slab.lower = lo ? (rank + nranks - 1) % nranks : -1;
+  c->slab.upper = hi ? (rank + 1) % nranks : -1;
+  c->slab.bytes_sent = 0;
+  c->kz0 = 2 + glo;
+  c->kz1 = (int)Ng_local[2] - ghi;
+  return 0;
+}
+int ifadv_slab_info(const ifadv_ctx* c, int* kz0, int* kz1, int* lower, int* upper, int64_t* bytes_sent) {
+  if (!c) return -2;
+  if (kz0) *kz0 = c->kz0;
+  if (kz1) *kz1 = c->kz1;
+  if (lower) *lower = c->slab.lower;
+  if (upper) *upper = c->slab.upper;
+  if (bytes_sent) *bytes_sent = c->slab.bytes_sent;
+  return 0;
+}
+int ifadv_exchange_planes(ifadv_ctx* c, void* stream, void* field, int ncomp, int elem_bytes) {
+  if (!c || !field || ncomp < 1 || elem_bytes < 1) return -2;
+  return slab_exchange(c, (cudaStream_t)stream, field, (size_t)elem_bytes, ncomp);
 }
 
 int ifadv_check_nan(ifadv_ctx* c, void* stream) {

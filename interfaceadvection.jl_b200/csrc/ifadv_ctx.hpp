@@ -10,8 +10,18 @@
 // ------------------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------------------
+// z-slab decomposition (ifadv_create_slab): the local arrays hold the owned planes plus G ghost planes per neighbour side
+struct ifadv_slab {
+  void* comm;           // ncclComm_t (borrowed)
+  int rank, nranks;     // nranks <= 1: not a slab
+  int G, glo, ghi;      // ghost planes per side with a neighbour; present below / above
+  int lower, upper;     // neighbour ranks (-1: physical boundary)
+  long long bytes_sent; // by the exchanges of this context
+};
 struct ifadv_ctx {
   int D, dtype, device;
+  int kz0, kz1;  // planes [kz0, kz1) of dimension 3 the sweeps update: 2 .. n[2], or the owned planes of a z-slab
+  ifadv_slab slab;
   ifadv::Geo g;
   int64_t Ng[3];
   unsigned long long* red_dev;   // 3 sweeps x 8 slots

@@ -54,6 +54,8 @@ template <class T> struct SweepP {
   int scheme, lim, first;
   int fused;  // sweep 1 of the fused entry: ρu_in = BC!(uOld*ρ(f̄)) is formed on the fly (u2ρu! + BC! folded in)
   unsigned long long* red;  // [0] max key, [1] min key, [2] argmax pack, [3] argmin pack, [4] nan count
+  int kz0, kz1;  // planes [kz0, kz1) of dimension 3 this launch updates (1-based): 2..n[2] on one GPU; the owned planes of a z-slab,
+                 // whose ghost planes (filled by the exchange) are read like any other interior plane   [3-D lean kernels only]
 };
 
 // order-preserving map double -> uint64 (for atomicMax/atomicMin)

@@ -77,6 +77,7 @@ template <class T> static void fill_params(ifadv_ctx* c, const SweepCfg<T>& q, i
   for (int i = 0; i < 3; ++i) P.A[i] = (T)q.A[i];
   P.g = c->g; P.scheme = q.scheme; P.lim = q.lim; P.first = q.first; P.red = q.red; P.fused = q.fused;
   for (int i = 0; i < 3; ++i) P.coff[i] = (long long)i * c->g.S;
+  P.kz0 = c->kz0; P.kz1 = c->kz1;
 }
 
 #if IFADV_FAM == 1
@@ -165,7 +166,8 @@ static int launch_along2_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) 
     attr_devs |= 1ull << (c->device & 63);
   }
   constexpr int DCC = (J == 1) ? 2 : 1;
-  const int nx = c->g.n[0] - 2, ncc = c->g.n[DCC] - 2, na = c->g.n[J] - 2;
+  const int nzo = c->kz1 - c->kz0;  // planes of dimension 3 to update (all of them on one GPU, the owned ones of a z-slab)
+  const int nx = c->g.n[0] - 2, ncc = (DCC == 2) ? nzo : c->g.n[DCC] - 2, na = (J == 2) ? nzo : c->g.n[J] - 2;
   const long long tiles = (long long)((nx + 31) / 32) * ((ncc + TC - 1) / TC);
   int chunk = 128;  // a multiple of 4 (4 warm-up planes per chunk)
   while (chunk > 16 && tiles * ((na + chunk - 1) / chunk) < 148 * 8) chunk >>= 1;
@@ -198,7 +200,7 @@ static int launch_xsweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) 
     CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_devs |= 1ull << (c->device & 63);
   }
-  const int nx = c->g.n[0] - 2, ny = c->g.n[1] - 2, nz = c->g.n[2] - 2;
+  const int nx = c->g.n[0] - 2, ny = c->g.n[1] - 2, nz = c->kz1 - c->kz0;
   const long long tiles = (long long)((nx + 31) / 32) * ((ny + TY - 1) / TY);
   int chunk = 128;  // 3-6 warm-up planes per chunk
   while (chunk > 16 && tiles * ((nz + chunk - 1) / chunk) < 148 * 8) chunk >>= 1;
@@ -236,7 +238,7 @@ static int launch_xrow_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
     CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_devs |= 1ull << (c->device & 63);
   }
-  const int nx = c->g.n[0] - 2, ny = c->g.n[1] - 2, nz = c->g.n[2] - 2;
+  const int nx = c->g.n[0] - 2, ny = c->g.n[1] - 2, nz = c->kz1 - c->kz0;
   const unsigned gx = (unsigned)((nx + TL::TX) / TL::TX), gy = (unsigned)((ny + TL::TY - 1) / TL::TY);  // elements 1..nx in tiles [60b, 60b+59]
   int chunk = 128;  // one warm-up plane per chunk
   while (chunk > 16 && (long long)gx * gy * ((nz + chunk - 1) / chunk) < 148 * 8) chunk >>= 1;
@@ -269,6 +271,10 @@ template <class T> static bool xrow_ok(const ifadv_ctx* c, const SweepCfg<T>& q)
 
 #if IFADV_FAM == 0
 template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  if (c->slab.nranks > 1 && !(D == 3 && MOM && c->use_march == 1 && c->use_along2)) {
+    c->err = "z-slab contexts run the 3-D CMOM path on the lean kernels only";
+    return -2;
+  }
   if constexpr (D == 3) {
     if (c->use_march == 1 && c->use_along2) {
       if (q.j != 0) return launch_fam_along2<T, MOM>(c, st, q);

@@ -81,7 +81,7 @@ IFADV_DI void xrow_body(const SweepP<T>& P, const int chunk, unsigned char* smem
   const int va = ea0 + 2 * lane + 1;             // 1-based x index of cell a; cell b = va + 1
   const int vy0 = 2 + (int)blockIdx.y * TL::TY + wq * R;  // the warp's first row
   if (vy0 > nB - 1) return;                      // ragged tile: nothing to own (no CTA barrier exists in this kernel)
-  const int k0 = 2 + (int)blockIdx.z * chunk, k1 = min(k0 + chunk, nC);  // planes [k0, k1)
+  const int k0 = P.kz0 + (int)blockIdx.z * chunk, k1 = min(k0 + chunk, P.kz1);  // planes [k0, k1) of this CTA
   const T lr = P.lr, omlr = P.omlr, dt = P.dt;
   const T lam1 = lin_interp(T(1), lr, omlr);
   const T AA = P.A[0], AB = P.A[1], AC = P.A[2];

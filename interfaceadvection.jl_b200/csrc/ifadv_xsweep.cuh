@@ -84,7 +84,7 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
   const bool perA = g.per & 1u, perB = (g.per >> 1) & 1u, perC = (g.per >> 2) & 1u;
   const unsigned cB = (unsigned)P.coff[1], cC = (unsigned)P.coff[2];
   const int ox = 2 + blockIdx.x * 32, oy = 2 + blockIdx.y * TY;
-  const int k0 = 2 + blockIdx.z * chunk, k1 = min(k0 + chunk, nC);
+  const int k0 = P.kz0 + blockIdx.z * chunk, k1 = min(k0 + chunk, P.kz1);
   const int ks = k1 - 4 * ((k1 - k0 + 3 + 3) / 4);  // >= 3 warm-up steps, a multiple of four steps in total
   const T lr = P.lr, omlr = P.omlr, dt = P.dt;
   const T lam1 = lin_interp(T(1), lr, omlr);

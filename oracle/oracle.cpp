@@ -160,6 +160,19 @@ int orc_advect_vof_rhouu(int dtype, int D, const int64_t* Ng, void* f, void* ff,
   });
   return 0;
 }
+// one directional sweep (number iop of the call) of advectVOFρuu! -- see advectVOFrhouu's only_op
+int orc_advect_vof_rhouu_sweep(int dtype, int D, const int64_t* Ng, void* f, void* ff, void* alpha, void* nhat, void* u, void* u0, double dt,
+                               int8_t* cbar, void* rhou, void* r, void* Phi, void* rhouf, void* uStar, void* uOld, void* dilaU, void* drho,
+                               double lr, int limiter_id, int scheme, const double* uBC, unsigned perdir, int exitBC, const int* dirO,
+                               FillReport* rep, int iop) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, {
+    T A[3] = {(T)uBC[0], (T)uBC[1], D == 3 ? (T)uBC[2] : T(0)};
+    return advectVOFrhouu<T>(g, (T*)f, (T*)ff, (T*)alpha, (T*)nhat, (T*)u, (T*)u0, (T)dt, cbar, (T*)rhou, (T*)r, (T*)Phi, (T*)rhouf,
+                             (T*)uStar, (T*)uOld, (T*)dilaU, (T*)drho, (T)lr, limiter_id, scheme, A, perdir, exitBC != 0, dirO, rep, iop);
+  });
+  return 0;
+}
 // MPCFL (src/flow.jl:262).  mu<=0 / eta<=0 / gnorm<=0 disable the corresponding limit.
 int orc_mpcfl(int dtype, int D, const int64_t* Ng, void* u, void* sigma, double nu, double mu, double lam_mu, double lam_rho, double eta,
               double gnorm, double dt_max, double safety, double* out) {

@@ -95,16 +95,19 @@ void advectrhouu1D(const Grid& g, const VF<T>& rhou, const VF<T>& r, const SF<T>
 template <class T>
 int advectVOFrhouu(const Grid& g, T* f_, T* ff_, T* al_, T* nh_, T* u_, T* u0_, T Dt, int8_t* cbar, T* rhou_, T* r_, T* Phi_, T* rhouf_,
                    T* uStar_, T* uOld_, T* dilaU_, T* drho_, T lr, int lam, int ns, const T* uBC, unsigned perdir, bool exitBC,
-                   const int* dirO, FillReport* rep) {
+                   const int* dirO, FillReport* rep, int only_op = -1) {
+  // only_op >= 0: run just the directional sweep number only_op of the call (c̄ is computed with sweep 0) -- lets a slab-decomposed
+  // test driver exchange ghost planes between the sweeps exactly like the multi-GPU path does
   const int D = g.D;
   SF<T> f{f_, &g}, ff{ff_, &g}, al{al_, &g}, Phi{Phi_, &g}, dil{dilaU_, &g};
   VF<T> nh{nh_, &g}, u{u_, &g}, u0{u0_, &g}, rhou{rhou_, &g}, r{r_, &g}, rhouf{rhouf_, &g}, uStar{uStar_, &g}, uOld{uOld_, &g},
       drho{drho_, &g};
   const T tol = 10 * std::numeric_limits<T>::epsilon();
-  compute_cbar(g, f, cbar);
+  if (only_op <= 0) compute_cbar(g, f, cbar);
   int status = 0;
   if (rep) { rep->status = 0; rep->dir = -1; }
   for (int iOp = 0; iOp < D; ++iOp) {
+    if (only_op >= 0 && iOp != only_op) continue;
     const int d = dirO[iOp] - 1;
     const T dt = T(1) * Dt;
     rhou2u(g, r, rhou, f, lr);                 // :197

@@ -223,6 +223,20 @@ def advectVOFrhouu(f, ff, alpha, nhat, u, u0, dt, cbar, rhou, r, Phi, rhouf, uSt
     return st, rep
 
 
+def advectVOFrhouu_sweep(iop, f, ff, alpha, nhat, u, u0, dt, cbar, rhou, r, Phi, rhouf, uStar, uOld, dilaU, drho, lr, limiter="Koren",
+                         scheme="WH", uBC=(0, 0, 0), perdir=(), exitBC=False, dirO=None):
+    """Directional sweep number `iop` (0-based) of advectVOFρuu! on its own (c̄ is computed with sweep 0)."""
+    D, ng = _ng(f)
+    rep = FillReport()
+    A = (C.c_double * 3)(*(list(map(float, uBC))[:D] + [0.0] * (3 - D)))
+    st = lib().orc_advect_vof_rhouu_sweep(_dt(f), D, ng, _p(f), _p(ff), _p(alpha), _p(nhat), _p(u), _p(u0), C.c_double(dt),
+                                          C.c_void_p(cbar.ctypes.data), _p(rhou), _p(r), _p(Phi), _p(rhouf), _p(uStar), _p(uOld),
+                                          _p(dilaU), _p(drho), C.c_double(lr), LIMITERS[limiter], NORMAL_SCHEMES[scheme], A,
+                                          mask(perdir), int(bool(exitBC)), (C.c_int * 3)(*(list(dirO) + [0] * (3 - D))), C.byref(rep),
+                                          int(iop))
+    return st, rep
+
+
 def MPCFL(u, sigma, nu=0.0, mu=0.0, lam_mu=1e-2, lam_rho=1e-3, eta=0.0, gnorm=0.0, dt_max=1.0, safety=0.8) -> float:
     D, ng = _ng(sigma)
     out = C.c_double()

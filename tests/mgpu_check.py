@@ -1,7 +1,8 @@
 """Multi-GPU parity check (run under torchrun on a GPU box, NOT collected by pytest):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
-Every rank advances its z-slab with the CUDA path; rank 0 also advances the whole grid on one GPU.  Owned cells of
-f and ρu must be BIT-IDENTICAL ("N-GPU result == 1-GPU result")."""
+Every rank advances its z-slab with the CUDA path (ifadv_create_slab: per-sweep NCCL ghost-plane exchange inside the library) and
+also advances the whole grid on its own GPU.  Owned cells of f and ρu must be BIT-IDENTICAL ("N-GPU result == 1-GPU
+result") -- with prescribed velocities, and with a `project` hook that changes u between predictor and corrector."""
 import os
 import sys
 
@@ -20,17 +21,18 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok_all = True
-    for dtype, per_z, N in [("float64", False, (64, 48, 40)), ("float32", True, (64, 64, 32)), ("float32", False, (96, 64, 64))]:
+    for dtype, per_z, N, hook in [("float64", False, (64, 48, 40), False), ("float32", True, (64, 64, 32), False),
+                                  ("float32", False, (96, 64, 64), True), ("float64", True, (60, 40, 12), True)]:
         perdir = (1, 2, 3) if per_z else (1, 2)
         T = getattr(torch, dtype)
         N1, N2, nz = N
         Ng = (N1, N2, nz * world)
         # global state, built identically on every rank
-        case = configs.make_case(Ng, dtype=dtype, device=dev, kind="C4")
+        case = configs.make_case(Ng, dtype=dtype, device=dev, kind="C4", vel="enright")  # w != 0: fluxes cross the slab ends
         sim = ia.TwoPhaseSimulation(Ng, (0, 0, 0), float(N1), T=T, lam_rho=1e-3, InterfaceSDF=case["sdf"], perdir=perdir, U=1.0, dt=1.0,
                                     device=dev)
         sim.flow.u.copy_(case["u"]); ia.BC(sim.flow.u, (0, 0, 0), False, perdir)
-        g = slab.SlabGeom(rank, world, nz, slab.W_DEFAULT, per_z)
+        g = slab.SlabGeom(rank, world, nz, slab.G_DEFAULT, per_z)
         nzg = nz * world
         zidx = torch.tensor([((g.z_origin + l - 1) % nzg) + 1 if per_z else min(max(g.z_origin + l, 0), nzg + 1)
                              for l in range(g.nz_local + 2)], device=dev)
@@ -38,9 +40,16 @@ def main():
         u_loc = sim.flow.u.index_select(2, zidx)
         run = slab.SlabRunner(N, dtype, perdir, "C4", rank, world, dev, fields=(f_loc, u_loc))
         nsteps = 3
+
+        def project(a, c, stage):  # stand-in for forcing + projection: u changes between predictor and corrector
+            v = torch.empty_like(a.u)
+            ia.rhou2u(v, c.rhou, c.f0 if stage == "predictor" else c.f, c.lam_rho)
+            a.u[1:-1, 1:-1, 1:-1] = a.u[1:-1, 1:-1, 1:-1] * 0.9 + v[1:-1, 1:-1, 1:-1] * 0.1
+            ia.BC(a.u, a.uBC, False, a.perdir)
+
         for _ in range(nsteps):
-            run.step()
-            ia.mom_advect_step(sim.flow, sim.intf, 1.0); sim.flow.dt.append(1.0)
+            run.step(project=project if hook else None)
+            ia.mom_advect_step(sim.flow, sim.intf, 1.0, project=project if hook else None); sim.flow.dt.append(1.0)
         torch.cuda.synchronize()
         ref_f = sim.intf.f[1:-1, 1:-1, 1 + rank * nz: 1 + (rank + 1) * nz]
         ref_ru = sim.intf.rhou[1:-1, 1:-1, 1 + rank * nz: 1 + (rank + 1) * nz, :]
@@ -50,7 +59,7 @@ def main():
         flag = torch.tensor([1 if ok else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
-            print(f"[mgpu_check] world={world} {dtype} per_z={per_z} N/gpu={N}: bitwise={'OK' if flag.item() else 'MISMATCH'} "
+            print(f"[mgpu_check] world={world} {dtype} per_z={per_z} hook={hook} N/gpu={N}: bitwise={'OK' if flag.item() else 'MISMATCH'} "
                   f"max|Δf|(rank0)={err:.3e} mass={m:.6f} single-GPU mass={ia.sum_inside(sim.intf.f):.6f} bytes_sent/rank={run.bytes_sent}")
         ok_all = ok_all and bool(flag.item())
     dist.destroy_process_group()

@@ -1,6 +1,8 @@
 """N>1 host logic on CPU: world_size-2 (and 3) gloo processes run the slab decomposition with the ORACLE as the
-per-rank step function and must reproduce the single-domain oracle result bit for bit on every owned cell.
-This pins the overlap width W, the exchange routine and the slab geometry without a GPU."""
+per-rank sweep function and must reproduce the single-domain oracle result bit for bit on every owned cell.
+The scheme is the multi-GPU path's (include/ifadv.h): G = 3 ghost planes per neighbour side, exchange of f, ρu and c̄ after every
+directional sweep.  This pins the ghost width (reach of one sweep), the plane ranges and posting order of the exchange and the
+slab geometry without a GPU."""
 import os
 import socket
 
@@ -33,6 +35,35 @@ def _oracle_step(f, u, lam_rho, perdir, dirO):
     oracle_mom_advect_step(st, f, u, 1.0, dirO)
 
 
+def _slab_step(ia, slab, g, f_t, u, lam_rho, lperdir, dirO):
+    """Transport half of MPFMomStep! on one slab, sweep by sweep, with the ghost-plane exchanges of the multi-GPU path."""
+    from tests.helpers import alloc_cmom
+
+    f = _np_view(f_t)
+    T = f.dtype.type
+    st = dict(D=3, Ng=f.shape, dtype=T, perdir=lperdir, uBC=(0.0, 0.0, 0.0), lam_rho=lam_rho)
+    a = alloc_cmom(st)
+    # exchanged arrays live in column-major torch tensors; numpy views share their memory
+    ru_t = ia.jl_zeros(f.shape + (3,), f_t.dtype, "cpu"); ru = _np_view(ru_t)
+    cb_t = ia.jl_zeros(f.shape, torch.int8, "cpu"); cb = _np_view(cb_t)
+    f0_t = ia.jl_zeros(f.shape, f_t.dtype, "cpu"); f0 = _np_view(f0_t)
+    u0 = u.copy(order="F")
+
+    def group(ft, fa, u1, u2, uOld):
+        O.u2rhou(ru, u0, fa, lam_rho); O.BC(ru, (0, 0, 0), False, lperdir)
+        for iop in range(3):
+            O.advectVOFrhouu_sweep(iop, fa, a["ff"], a["alpha"], a["nhat"], u1, u2, 1.0, cb, ru, a["r"], a["Phi"], a["rhouf"], a["nhat"],
+                                   uOld, a["alpha"], a["drho"], lam_rho, "Koren", "WH", (0, 0, 0), lperdir, False, dirO)
+            if iop < 2:
+                slab.exchange_overlap([ft, ru_t] + ([cb_t] if iop == 0 else []), g)
+            else:
+                slab.exchange_overlap([ft], g)
+
+    f0[...] = f
+    group(f0_t, f0, u0, u, u)          # flow.jl:69-70
+    f0[...] = (f0 + f) * T(0.5)        # :74
+    f0[...] = f                        # :89
+    group(f_t, f, u, u, u0)            # :91-92
 def _worker(rank, world, port, N, per_z, nsteps, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -43,7 +74,7 @@ def _worker(rank, world, port, N, per_z, nsteps, out):
 
         perdir = (1, 2, 3) if per_z else (1, 2)
         N1, N2, nz = N
-        g = slab.SlabGeom(rank, world, nz, slab.W_DEFAULT, per_z)
+        g = slab.SlabGeom(rank, world, nz, slab.G_DEFAULT, per_z)
         Ng_glob = (N1, N2, nz * world)
         Nl = (N1, N2, g.nz_local)
         lperdir = g.local_perdir(perdir)
@@ -53,7 +84,7 @@ def _worker(rank, world, port, N, per_z, nsteps, out):
         fg0 = O.zeros(tuple(n + 2 for n in Ng_glob), T); ag = O.zeros(fg0.shape, T); ng = O.zeros(fg0.shape + (3,), T)
         sdf = configs.sdf_sphere([N1 / 2, N2 / 2, nz * world / 2], min(N1, N2) / 3.2)
         O.applyVOF(fg0, ag, ng, sdf); O.BCf(fg0, perdir)
-        ug0 = np.asfortranarray(configs.tgv(Ng_glob, T, U=0.3)); O.BC(ug0, (0, 0, 0), False, perdir)
+        ug0 = np.asfortranarray(configs.enright(Ng_glob, T, amp=0.3)); O.BC(ug0, (0, 0, 0), False, perdir)  # w != 0: z fluxes cross the slab ends
         # local array plane l (0-based, ghost at 0) <-> global array plane z_origin + l, wrapped on a periodic box
         nzg = nz * world
         zidx = [((g.z_origin + l - 1) % nzg) + 1 if per_z else min(max(g.z_origin + l, 0), nzg + 1) for l in range(g.nz_local + 2)]
@@ -64,10 +95,13 @@ def _worker(rank, world, port, N, per_z, nsteps, out):
         f[...] = fg0[:, :, zidx]
         O.BCf(f, lperdir)
         slab.exchange_overlap([f_t], g)
+        u_t = ia.jl_zeros(u.shape, torch.float64, "cpu")
+        _np_view(u_t)[...] = u
+        slab.exchange_overlap([u_t], g)  # BC! treated the slab ends as walls: the neighbours' planes replace that
+        u = _np_view(u_t)
         for n in range(nsteps):
             dirO = tuple((1 + n + i) % 3 + 1 for i in range(1, 4))
-            _oracle_step(f, u, 1e-3, lperdir, dirO)
-            slab.exchange_overlap([f_t], g)
+            _slab_step(ia, slab, g, f_t, u, 1e-3, lperdir, dirO)
         owned = f[1:-1, 1:-1, g.owned].copy()
         # rank 0 gathers and compares with the single-domain run
         gathered = [None] * world
@@ -89,7 +123,7 @@ def test_slab_oracle_bitwise(world, per_z):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    N = (12, 10, 18)  # per rank: 18 owned planes (> 2W)
+    N = (12, 10, 9)  # per rank: 9 owned planes (>= G)
     procs = [ctx.Process(target=_worker, args=(r, world, port, N, per_z, 2, out)) for r in range(world)]
     for p in procs:
         p.start()
@@ -103,7 +137,7 @@ def test_slab_oracle_bitwise(world, per_z):
 def test_slab_geometry():
     from interfaceadvection.jl_b200.slab import SlabGeom
 
-    g = SlabGeom(0, 4, 128, 8, False)
+    g = SlabGeom(0, 4, 128, 8, False)  # any ghost width
     assert (g.wlo, g.whi, g.nz_local, g.z_origin, g.lower, g.upper) == (0, 8, 136, 0, None, 1)
     g = SlabGeom(3, 4, 128, 8, False)
     assert (g.wlo, g.whi, g.nz_local, g.z_origin, g.lower, g.upper) == (8, 0, 136, 376, 2, None)
