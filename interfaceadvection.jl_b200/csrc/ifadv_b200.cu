@@ -487,14 +487,48 @@ static int advect_vof_rhouu_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* Phi
     for (int i = 0; i < 3; ++i) q.A[i] = (i < D) ? uBC[i] : 0.0;
     q.red = c->red_dev + 8 * s;
     if (s == D - 1 && wait_f) CU_CHECK(c, cudaStreamWaitEvent(st, wait_f, 0));  // the last sweep is the first to write f
-    int rc = launch_sweep<T, true>(c, st, q);
-    if (rc) return rc;
-    if (c->slab.nranks > 1 && s < D - 1) {
-      // z-slab: the next sweep reads the neighbours' planes of what this sweep produced (stencil reach 3 below / 2 above)
-      if ((rc = slab_exchange(c, st, fb[s + 1], sizeof(T), 1))) return rc;
-      if ((rc = slab_exchange(c, st, rb[s + 1], sizeof(T), D))) return rc;
-      if (s == 0 && (rc = slab_exchange(c, st, cbar, 1, 1))) return rc;  // c̄ of the call (written by sweep 1 on owned planes)
+    int rc;
+    if (c->slab.nranks <= 1) {
+      if ((rc = launch_sweep<T, true>(c, st, q))) return rc;
+      continue;
     }
+    // z-slab: the next sweep reads the neighbours' planes of what this sweep produced (stencil reach 3 below / 2 above).
+    // Overlap: the G boundary planes of each slab end are swept FIRST (they need the ghost planes the previous exchange delivers and
+    // produce the planes this sweep's exchange sends); the exchange then runs on the context's second stream underneath the sweep
+    // of the interior planes, which reads owned planes only.
+    const int G = c->slab.G, z0 = c->kz0, z1 = c->kz1;
+    const bool split = c->slab.overlap && (z1 - z0) >= 2 * G + 4;
+    auto sweep_planes = [&](int a, int b, bool timed) -> int {
+      if (b <= a) return 0;
+      const int p0 = c->prof_on;
+      c->kz0 = a; c->kz1 = b;
+      if (!timed) c->prof_on = 0;
+      const int r = launch_sweep<T, true>(c, st, q);
+      c->kz0 = z0; c->kz1 = z1; c->prof_on = p0;
+      return r;
+    };
+    auto exchange_outputs = [&](cudaStream_t xs) -> int {
+      int r;
+      if ((r = slab_exchange(c, xs, fb[s + 1], sizeof(T), 1))) return r;
+      if ((r = slab_exchange(c, xs, rb[s + 1], sizeof(T), D))) return r;
+      if (s == 0 && (r = slab_exchange(c, xs, cbar, 1, 1))) return r;  // c̄ of the call (written by sweep 1 on owned planes)
+      return 0;
+    };
+    if (!split) {
+      if ((rc = sweep_planes(z0, z1, true))) return rc;
+      if (s < D - 1 && (rc = exchange_outputs(st))) return rc;
+      continue;
+    }
+    if (s > 0) CU_CHECK(c, cudaStreamWaitEvent(st, c->slab_ev[1], 0));  // ghost planes of this sweep's inputs have arrived
+    if ((rc = sweep_planes(z0, z0 + G, false))) return rc;
+    if ((rc = sweep_planes(z1 - G, z1, false))) return rc;
+    if (s < D - 1) {
+      CU_CHECK(c, cudaEventRecord(c->slab_ev[0], st));
+      CU_CHECK(c, cudaStreamWaitEvent(c->slab_stream, c->slab_ev[0], 0));
+      if ((rc = exchange_outputs(c->slab_stream))) return rc;
+      CU_CHECK(c, cudaEventRecord(c->slab_ev[1], c->slab_stream));
+    }
+    if ((rc = sweep_planes(z0 + G, z1 - G, true))) return rc;
   }
   int rc = launch_bcf<T>(c, st, f, per);
   if (rc) return rc;
@@ -564,7 +598,8 @@ int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int dev
   if (cudaSetDevice(device) != cudaSuccess) return -3;
   ifadv_ctx* c = new ifadv_ctx();
   c->D = D; c->dtype = dtype; c->device = device; c->launches = 0;
-  c->slab = ifadv_slab{nullptr, 0, 1, 0, 0, 0, -1, -1, 0};
+  c->slab = ifadv_slab{nullptr, 0, 1, 0, 0, 0, -1, -1, 0, 0};
+  c->slab_stream = nullptr; c->slab_ev[0] = c->slab_ev[1] = nullptr;
   c->g.n[0] = (int)Ng[0]; c->g.n[1] = (int)Ng[1]; c->g.n[2] = (D == 3) ? (int)Ng[2] : 1;
   c->g.s1 = c->g.n[0]; c->g.s2 = (long long)c->g.n[0] * c->g.n[1];
   c->g.S = c->g.s2 * c->g.n[2];
@@ -607,6 +642,7 @@ int ifadv_destroy(ifadv_ctx* c) {
   if (c->pin_u) cudaFreeHost(c->pin_u);
   if (c->pin_ru) cudaFreeHost(c->pin_ru);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->slab_stream) { cudaStreamDestroy(c->slab_stream); cudaEventDestroy(c->slab_ev[0]); cudaEventDestroy(c->slab_ev[1]); }
   host_pipe_free(c);
   if (c->prof_ev) { for (int k = 0; k < 2 * IFADV_PROF_MAX; ++k) cudaEventDestroy(c->prof_ev[k]); delete[] c->prof_ev; delete[] c->prof_tag; }
   delete c;
@@ -1126,6 +1162,15 @@ int ifadv_create_slab(ifadv_ctx** out, const int64_t Ng_local[3], int dtype, int
   c->slab.bytes_sent = 0;
   c->kz0 = 2 + glo;
   c->kz1 = (int)Ng_local[2] - ghi;
+  {
+    const char* e = getenv("IFADV_SLAB_OVERLAP");  // 0: exchanges on the caller's stream, one launch per sweep (measurement aid)
+    c->slab.overlap = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (nranks > 1) {
+    CU_CHECK(c, cudaStreamCreateWithFlags(&c->slab_stream, cudaStreamNonBlocking));
+    CU_CHECK(c, cudaEventCreateWithFlags(&c->slab_ev[0], cudaEventDisableTiming));
+    CU_CHECK(c, cudaEventCreateWithFlags(&c->slab_ev[1], cudaEventDisableTiming));
+  }
   return 0;
 }
 int ifadv_slab_info(const ifadv_ctx* c, int* kz0, int* kz1, int* lower, int* upper, int64_t* bytes_sent) {

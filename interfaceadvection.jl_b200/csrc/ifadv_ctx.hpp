@@ -17,11 +17,14 @@ struct ifadv_slab {
   int G, glo, ghi;      // ghost planes per side with a neighbour; present below / above
   int lower, upper;     // neighbour ranks (-1: physical boundary)
   long long bytes_sent; // by the exchanges of this context
+  int overlap;          // 1: boundary planes first, exchange on slab_stream underneath the interior planes
 };
 struct ifadv_ctx {
   int D, dtype, device;
   int kz0, kz1;  // planes [kz0, kz1) of dimension 3 the sweeps update: 2 .. n[2], or the owned planes of a z-slab
   ifadv_slab slab;
+  cudaStream_t slab_stream;  // second stream of the overlapped exchange
+  cudaEvent_t slab_ev[2];    // [0] boundary planes swept (main -> slab_stream), [1] exchange done (slab_stream -> main)
   ifadv::Geo g;
   int64_t Ng[3];
   unsigned long long* red_dev;   // 3 sweeps x 8 slots

@@ -225,14 +225,14 @@ static int launch_xsweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) 
 #define IFADV_XP_XROW_MB 2
 #endif
 // v5: warp-autonomous row kernel for CMOM sweeps along x (3-D only, even row pitch, vector-aligned arrays)
-template <class T, int R, bool FUSED, bool KOREN, int MINB, bool SAMEU>
+template <class T, int R, bool MOM, bool FUSED, bool KOREN, int MINB, bool SAMEU>
 static int launch_xrow_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   using TL = XRTile<R>;
   SweepP<T> P;
   fill_params<T>(c, q, 0, P);
   if ((unsigned long long)c->g.S * 3ull >= 0xffffffffull) { c->err = "grid too large for 32-bit element offsets"; return -2; }
   const size_t smem = TL::template Bytes<T>::cta;
-  auto kern = xrow_kernel<T, R, FUSED, KOREN, MINB, SAMEU>;
+  auto kern = xrow_kernel<T, R, MOM, FUSED, KOREN, MINB, SAMEU>;
   static unsigned long long attr_devs = 0ull;
   if (!((attr_devs >> (c->device & 63)) & 1ull)) {
     CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -265,7 +265,7 @@ template <class T> static bool xrow_ok(const ifadv_ctx* c, const SweepCfg<T>& q)
   if (c->g.n[0] & 1) return false;
   const uintptr_t m = 2 * sizeof(T) - 1;
   const uintptr_t a = (uintptr_t)q.f_in | (uintptr_t)q.f_out | (uintptr_t)q.u | (uintptr_t)q.u0 | (uintptr_t)q.rhou_in | (uintptr_t)q.rhou_out |
-                      (uintptr_t)q.uOld;
+                      (uintptr_t)q.uOld | (uintptr_t)q.rhouf;
   return (a & m) == 0 && ((uintptr_t)q.cbar & 1) == 0;
 }
 
@@ -278,10 +278,8 @@ template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStrea
   if constexpr (D == 3) {
     if (c->use_march == 1 && c->use_along2) {
       if (q.j != 0) return launch_fam_along2<T, MOM>(c, st, q);
-      if constexpr (MOM) {
-        if (c->use_xrow && xrow_ok<T>(c, q)) return launch_fam_xrow<T, MOM>(c, st, q);
-        return launch_fam_xsweep<T, MOM>(c, st, q);
-      }
+      if (c->use_xrow && xrow_ok<T>(c, q)) return launch_fam_xrow<T, MOM>(c, st, q);
+      if constexpr (MOM) return launch_fam_xsweep<T, MOM>(c, st, q);
     }
     if (c->use_march == 1 && q.j != 0) return launch_fam_along<T, MOM>(c, st, q);
     if (c->use_march) return launch_fam_march<T, MOM>(c, st, q);
@@ -375,19 +373,23 @@ template int launch_fam_xsweep<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream
 
 #else
 template <class T, bool MOM> int launch_fam_xrow(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
-  static_assert(MOM, "the pure-VOF x-sweep runs the march kernel");
   constexpr int RR = IFADV_XP_XROW_R, MB = IFADV_XP_XROW_MB;
-  const bool koren = q.lim == 2;
-  if (koren && q.u == q.u0) {  // one velocity array for u¹ and u² (MPFMomStep!): the SAMEU instantiations
-    if (q.fused) return launch_xrow_t<T, RR, true, true, MB, true>(c, st, q);
-    return launch_xrow_t<T, RR, false, true, MB, true>(c, st, q);
-  }
+  if constexpr (!MOM) {  // pure VOF (advect!): no limiter, no momentum streams
+    if (q.u == q.u0) return launch_xrow_t<T, RR, false, false, true, MB, true>(c, st, q);
+    return launch_xrow_t<T, RR, false, false, true, MB, false>(c, st, q);
+  } else {
+    const bool koren = q.lim == 2;
+    if (koren && q.u == q.u0) {  // one velocity array for u¹ and u² (MPFMomStep!): the SAMEU instantiations
+      if (q.fused) return launch_xrow_t<T, RR, true, true, true, MB, true>(c, st, q);
+      return launch_xrow_t<T, RR, true, false, true, MB, true>(c, st, q);
+    }
 #ifdef IFADV_XROW_DEV  // development builds: only the two hot instantiations, everything else runs the plane-marching kernel
-  return launch_fam_xsweep<T, MOM>(c, st, q);
+    return launch_fam_xsweep<T, MOM>(c, st, q);
 #else
-  if (q.fused) return koren ? launch_xrow_t<T, RR, true, true, MB, false>(c, st, q) : launch_xrow_t<T, RR, true, false, MB, false>(c, st, q);
-  return koren ? launch_xrow_t<T, RR, false, true, MB, false>(c, st, q) : launch_xrow_t<T, RR, false, false, MB, false>(c, st, q);
+    if (q.fused) return koren ? launch_xrow_t<T, RR, true, true, true, MB, false>(c, st, q) : launch_xrow_t<T, RR, true, true, false, MB, false>(c, st, q);
+    return koren ? launch_xrow_t<T, RR, true, false, true, MB, false>(c, st, q) : launch_xrow_t<T, RR, true, false, false, MB, false>(c, st, q);
 #endif
+  }
 }
 template int launch_fam_xrow<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
 #endif

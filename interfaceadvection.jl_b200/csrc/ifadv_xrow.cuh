@@ -57,7 +57,7 @@ template <class T> IFADV_DI void cp_async_pair(unsigned saddr, const T* gsrc) {
 template <class T> IFADV_DI typename V2<T>::type ldg2(const T* p) { return __ldg(reinterpret_cast<const typename V2<T>::type*>(p)); }
 template <class T> IFADV_DI typename V2<T>::type lds2(const T* p) { return *reinterpret_cast<const typename V2<T>::type*>(p); }
 
-template <class T, int R, bool FUSED, bool KOREN, bool SAMEU, bool EDGE>
+template <class T, int R, bool MOM, bool FUSED, bool KOREN, bool SAMEU, bool EDGE>
 IFADV_DI void xrow_body(const SweepP<T>& P, const int chunk, unsigned char* smem_raw) {
   using TL = XRTile<R>;
   using T2 = typename V2<T>::type;
@@ -87,6 +87,7 @@ IFADV_DI void xrow_body(const SweepP<T>& P, const int chunk, unsigned char* smem
   const T AA = P.A[0], AB = P.A[1], AC = P.A[2];
   const bool first = FUSED ? true : (P.first != 0);  // the fused sweep is always sweep 1
   const T* const rsrc = FUSED ? P.uOld : P.rhou_in;  // fused sweep 1: ρu = BC!(uOld*ρ(f̄)) is formed on the fly
+  constexpr int R0 = MOM ? 0 : 1;                    // first S1 row: the row y-1 only feeds the momentum fluxes
 
   // ---- per-thread constants ------------------------------------------------------------------------------------------------
   // x offsets of the two cells: mapped (f, c̄, ρu_y, ρu_z, uOld: ghost -> interior-equivalent cell) and as stored (u_x faces, ρu_x)
@@ -171,7 +172,7 @@ IFADV_DI void xrow_body(const SweepP<T>& P, const int chunk, unsigned char* smem
     const T* Fk = sF + (k & 3) * PLF;
 #pragma unroll
     for (int r = 0; r <= R; ++r) {
-      if (warm && r == 0) {  // the warm-up plane only feeds the z-1 terms of the warp's own rows
+      if ((warm || !MOM) && r == 0) {  // the warm-up plane only feeds the z-1 terms of the warp's own rows; pure VOF needs no row y-1
         FF[0][0] = FF[0][1] = M[0][0] = M[0][1] = dil[0][0] = dil[0][1] = dv[0][0] = dv[0][1] = T(0);
         continue;
       }
@@ -197,7 +198,8 @@ IFADV_DI void xrow_body(const SweepP<T>& P, const int chunk, unsigned char* smem
             FFo = dl;                       // parked here until then
           } else {
             FFo = fc * dl;                            // advection.jl:125-126
-            Mo = (dl * lr + omlr * FFo) * P.idt;      // fᶠ2ρuf (VOFutil.jl:218), rmul!(ρuf, inv(δt)) (flow.jl:207)
+            Mo = dl * lr + omlr * FFo;                // fᶠ2ρuf (VOFutil.jl:218)
+            if (MOM) Mo = Mo * P.idt;                 // rmul!(ρuf, inv(δt)) (flow.jl:207)
           }
         }
         FF[r][c] = FFo; M[r][c] = Mo;
@@ -234,7 +236,9 @@ IFADV_DI void xrow_body(const SweepP<T>& P, const int chunk, unsigned char* smem
         RBox<T, PLF, FP> B{sF, eu, k};
         const T ff = plic_face_flux_inl<T, 3>(P.scheme, B, Fk[eu], 0, dl);
         sFX[e] = ff;
-        sMX[e] = (dl * lr + omlr * ff) * P.idt;
+        T m = dl * lr + omlr * ff;
+        if (MOM) m = m * P.idt;
+        sMX[e] = m;
       }
       __syncwarp();
 #pragma unroll
@@ -252,18 +256,20 @@ IFADV_DI void xrow_body(const SweepP<T>& P, const int chunk, unsigned char* smem
   int cbn[R + 1];
 #pragma unroll
   for (int r = 0; r <= R; ++r) cbn[r] = 0;
-  ld_f(k0 - 2); ld_f(k0 - 1); ld_f(k0);
-  ld_u(k0 - 1, un, u0n, cbn);
+  if (MOM) { ld_f(k0 - 2); ld_f(k0 - 1); ld_f(k0); }
+  else { ld_f(k0 - 1); ld_f(k0); ld_f(k0 + 1); }
+  ld_u(MOM ? k0 - 1 : k0, un, u0n, cbn);
   cp_async_wait_all();
   __syncwarp();
 
   // The march starts one plane early: step k0-1 only evaluates S1 (it feeds the z-1 terms -- f, mass flux, dilation -- of plane k0).
-  unsigned pk = (unsigned)(k0 - 2) * s2;  // offset of plane k (owned planes are interior: no map)
-  for (int k = k0 - 1; k < k1; ++k, pk += s2) {
+  const int kstart = MOM ? k0 - 1 : k0;          // pure VOF has no z-1 terms: no warm-up plane
+  unsigned pk = (unsigned)(kstart - 1) * s2;  // offset of plane k (owned planes are interior: no map)
+  for (int k = kstart; k < k1; ++k, pk += s2) {
     const bool warm = k < k0;
     // ---- loads of this step: f(k+2) -> ring, ρu / uOld of plane k and u_x / c̄ of plane k+1 -> registers -------------------
     T2 q[R][3], o[R][3];
-    if (!warm) {
+    if (MOM && !warm) {
 #pragma unroll
       for (int j = 0; j < R; ++j) {
         const unsigned ob = pk + rowm[j + 2];
@@ -311,6 +317,53 @@ IFADV_DI void xrow_body(const SweepP<T>& P, const int chunk, unsigned char* smem
         fz[j][0] = fo.x; fz[j][1] = fo.y;
         Mz[j][0] = M[r][0]; Mz[j][1] = M[r][1];
         dilz[j][0] = dil[r][0]; dilz[j][1] = dil[r][1];
+        continue;
+      }
+      if (!MOM) {  // pure VOF (advectVOF!, advection.jl:34-78): the f update and the optional ρuf[·,x] output -- nothing else
+        const T FFRa = __shfl_down_sync(FULL, FF[r][0], 1);
+        const T MRa = __shfl_down_sync(FULL, M[r][0], 1);
+        T fn[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const T f0 = c ? fo.y : fo.x;
+          T v = f0 + ((FF[r][c] - (c ? FFRa : FF[r][1])) + dv[r][c]);  // advection.jl:67
+          if (okc[c] && rv[j]) {
+            rmax = max_nan(rmax, v);
+            rmin = t_min(rmin, v);
+            if (v > T(1) || v < T(0)) {
+              const unsigned lk = pk + rowm[r + 1] + xm[c];
+              if (v >= rmax) amax = lk;
+              if (v <= rmin) amin = lk;
+            }
+          }
+          fn[c] = (v < P.tol) ? T(0) : ((v > P.onemtol) ? T(1) : v);  // cleanWisp!
+        }
+        if (rv[j]) {
+          const unsigned lk = pk + rowm[r + 1];
+          if (!EDGE) {
+            if (okc[0]) {
+              const unsigned l0 = lk + xm[0];
+              T2 w;
+              w.x = fn[0]; w.y = fn[1];
+              *reinterpret_cast<T2*>(P.f_out + l0) = w;
+              if (first) *reinterpret_cast<unsigned short*>(P.cbar + l0) = (unsigned short)(((fo.x < T(0.5)) ? 0 : 1) | (((fo.y < T(0.5)) ? 0 : 1) << 8));
+              if (P.rhouf_j != nullptr) { w.x = M[r][0]; w.y = M[r][1]; *reinterpret_cast<T2*>(P.rhouf_j + l0) = w; }
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              if (okc[c]) {
+                const unsigned l0 = lk + xm[c];
+                P.f_out[l0] = fn[c];
+                if (first) P.cbar[l0] = (int8_t)(((c ? fo.y : fo.x) < T(0.5)) ? 0 : 1);
+                if (P.rhouf_j != nullptr) {
+                  P.rhouf_j[l0] = M[r][c];
+                  if (va + c == nA - 1) P.rhouf_j[l0 + 1] = c ? MRa : M[r][1];  // inside_uWB includes the upper boundary face
+                }
+              }
+            }
+          }
+        }
         continue;
       }
       const T fxm = Frow[1 + 2 * lane];
@@ -493,15 +546,15 @@ IFADV_DI void xrow_body(const SweepP<T>& P, const int chunk, unsigned char* smem
   }
 }
 
-template <class T, int R, bool FUSED, bool KOREN, int MINB, bool SAMEU>
+template <class T, int R, bool MOM, bool FUSED, bool KOREN, int MINB, bool SAMEU>
 __global__ void __launch_bounds__(256, MINB) xrow_kernel(const SweepP<T> P, const int chunk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nA = P.g.n[0];
   const int ea0 = (int)blockIdx.x * XRTile<R>::TX - 2;
   // a tile is interior when every cell its lanes touch (elements ea0-1 .. ea0+63) is an interior cell: no index map, no boundary rule
   const bool edge = ea0 - 1 < 1 || ea0 + 63 > nA - 2;
-  if (!edge) xrow_body<T, R, FUSED, KOREN, SAMEU, false>(P, chunk, smem_raw);
-  else xrow_body<T, R, FUSED, KOREN, SAMEU, true>(P, chunk, smem_raw);
+  if (!edge) xrow_body<T, R, MOM, FUSED, KOREN, SAMEU, false>(P, chunk, smem_raw);
+  else xrow_body<T, R, MOM, FUSED, KOREN, SAMEU, true>(P, chunk, smem_raw);
 }
 
 }  // namespace ifadv

@@ -35,6 +35,17 @@ int orc_num_threads() {
 #endif
 }
 
+// the timing build ignores an inherited OMP_NUM_THREADS=1 (torchrun exports it): the CPU legs state their thread count explicitly
+int orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
+
 int orc_get_intercept(int dtype, int D, const double* n, double g, double* out) {
   DISPATCH(dtype, {
     T nn[3] = {(T)n[0], (T)n[1], D == 3 ? (T)n[2] : T(0)};

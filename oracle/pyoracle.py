@@ -254,3 +254,8 @@ def sum_inside(f) -> float:
 
 def num_threads(omp=True) -> int:
     return lib(omp).orc_num_threads()
+
+
+def set_num_threads(n: int, omp=True) -> int:
+    """omp_set_num_threads on the timing build (an inherited OMP_NUM_THREADS=1, as torchrun exports, would otherwise pin it)."""
+    return lib(omp).orc_set_num_threads(int(n))
