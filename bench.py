@@ -401,31 +401,43 @@ def roofline_of(w, wl, N_gpu, r, steps):
 
 def slab_bitwise_check(ia, torch, dist, rank, world, dev):
     """Before timing at N > 1: a small global grid advanced by the N-rank slab decomposition and, on every rank, by the single-GPU
-    path; the owned cells of f and ρu must be BIT-IDENTICAL (the oracle of the multi-GPU path)."""
+    path (the oracle of the multi-GPU path).  Float64 (IEEE-exact arithmetic): the owned cells of f and ρu must be
+    BIT-IDENTICAL.  Float32 is built with FMA contraction, and the boundary / interior instantiations of a kernel contract
+    differently, so a plane that is "interior" on one GPU and "next to a slab end" on N GPUs may differ in the last bit: reported as
+    the largest absolute difference (a few 1e-8 on O(1) fields), required to stay below 1e-6."""
     from interfaceadvection.jl_b200 import configs, slab
 
     N = (96, 64, 24)
     perdir = (1, 2)
-    dtype, T = "float32", torch.float32
     Ng = (N[0], N[1], N[2] * world)
-    case = configs.make_case(Ng, dtype=dtype, device=dev, kind="C4", vel="enright")
-    sim = ia.TwoPhaseSimulation(Ng, (0, 0, 0), float(N[0]), T=T, lam_rho=1e-3, InterfaceSDF=case["sdf"], perdir=perdir, U=1.0, dt=1.0,
-                                device=dev)
-    sim.flow.u.copy_(case["u"]); ia.BC(sim.flow.u, (0, 0, 0), False, perdir)
-    g = slab.SlabGeom(rank, world, N[2], slab.G_DEFAULT, False)
-    nzg = N[2] * world
-    zidx = torch.tensor([min(max(g.z_origin + l, 0), nzg + 1) for l in range(g.nz_local + 2)], device=dev)
-    run = slab.SlabRunner(N, dtype, perdir, "C4", rank, world, dev, fields=(sim.intf.f.index_select(2, zidx), sim.flow.u.index_select(2, zidx)))
-    for _ in range(2):
-        run.step()
-        ia.mom_advect_step(sim.flow, sim.intf, 1.0); sim.flow.dt.append(1.0)
-    torch.cuda.synchronize()
-    sl = slice(1 + rank * N[2], 1 + (rank + 1) * N[2])
-    ok = torch.equal(sim.intf.f[1:-1, 1:-1, sl], run.owned_f()) and torch.equal(sim.intf.rhou[1:-1, 1:-1, sl, :], run.owned_rhou())
-    flag = torch.tensor([1 if ok else 0], device=dev)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    return {"grid_per_gpu": list(N), "dtype": "f32", "steps": 2, "velocity": "enright (three components)",
-            "owned_cells_bit_identical_to_1gpu": bool(flag.item())}
+    out = {"grid_per_gpu": list(N), "steps": 2, "velocity": "enright (three components)", "interface": "sphere across the rank 0 / rank 1 slab boundary"}
+    for dtype in ("float64", "float32"):
+        T = getattr(torch, dtype)
+        case = configs.make_case(Ng, dtype=dtype, device=dev, kind="C4", vel="enright")
+        sdf = configs.sdf_sphere([N[0] / 2, N[1] / 2, N[2] * 1.0], N[2] * 0.6, inside_dark=False)
+        sim = ia.TwoPhaseSimulation(Ng, (0, 0, 0), float(N[0]), T=T, lam_rho=1e-3, InterfaceSDF=sdf, perdir=perdir, U=1.0, dt=1.0, device=dev)
+        sim.flow.u.copy_(case["u"]); ia.BC(sim.flow.u, (0, 0, 0), False, perdir)
+        g = slab.SlabGeom(rank, world, N[2], slab.G_DEFAULT, False)
+        nzg = N[2] * world
+        zidx = torch.tensor([min(max(g.z_origin + l, 0), nzg + 1) for l in range(g.nz_local + 2)], device=dev)
+        run = slab.SlabRunner(N, dtype, perdir, "C4", rank, world, dev, fields=(sim.intf.f.index_select(2, zidx), sim.flow.u.index_select(2, zidx)))
+        for _ in range(2):
+            run.step()
+            ia.mom_advect_step(sim.flow, sim.intf, 1.0); sim.flow.dt.append(1.0)
+        torch.cuda.synchronize()
+        sl = slice(1 + rank * N[2], 1 + (rank + 1) * N[2])
+        df = (sim.intf.f[1:-1, 1:-1, sl] - run.owned_f()).abs().max()
+        dr = (sim.intf.rhou[1:-1, 1:-1, sl, :] - run.owned_rhou()).abs().max()
+        ok = torch.equal(sim.intf.f[1:-1, 1:-1, sl], run.owned_f()) and torch.equal(sim.intf.rhou[1:-1, 1:-1, sl, :], run.owned_rhou())
+        v = torch.tensor([1.0 if ok else 0.0, -float(df), -float(dr)], device=dev, dtype=torch.float64)
+        dist.all_reduce(v, op=dist.ReduceOp.MIN)
+        key = "f64" if dtype == "float64" else "f32"
+        out[key + "_owned_cells_bit_identical_to_1gpu"] = bool(v[0].item() == 1.0)
+        out[key + "_max_abs_diff"] = {"f": -float(v[1].item()), "rhou": -float(v[2].item())}
+        del run, sim
+        ia.api._contexts.clear()
+    out["pass"] = bool(out["f64_owned_cells_bit_identical_to_1gpu"] and max(out["f32_max_abs_diff"].values()) <= 1e-6)
+    return out
 
 
 def measure_workload(ia, torch, dist, wl, rank, world, dev, local, steps, warmup, clocks):

@@ -402,23 +402,26 @@ NcclApi* nccl_api() {
 // Ghost planes of `ncomp` fields of `esz`-byte elements (component stride S elements): my top G owned planes -> the upper neighbour's
 // lower ghost planes, my bottom G owned planes -> the lower neighbour's upper ghost planes; ONE NCCL group on the caller's stream.
 // Posting order (sends: up, down; receives: from below, from above) lets NCCL match the pairs when both neighbours are one peer.
-int slab_exchange(ifadv_ctx* c, cudaStream_t st, void* base, size_t esz, int ncomp) {
+// nup: planes sent UP (my top owned planes -> the upper neighbour's lower ghost planes), ndn: planes sent DOWN.  A sweep reaches 3
+// planes below / 2 above a cell for f and 2 / 2 for ρu, so the inner calls send fewer than G planes where that suffices.
+int slab_exchange(ifadv_ctx* c, cudaStream_t st, void* base, size_t esz, int ncomp, int nup = -1, int ndn = -1) {
   const ifadv_slab& sl = c->slab;
   if (sl.nranks <= 1) return 0;
   NcclApi* A = nccl_api();
   if (!A->ok) return fail(c, -4, "NCCL is not available");
+  if (nup < 0 || nup > sl.G) nup = sl.G;
+  if (ndn < 0 || ndn > sl.G) ndn = sl.G;
   const size_t pl = esz * (size_t)c->g.s2, comp = esz * (size_t)c->g.S;
-  const size_t G = (size_t)sl.G;
   ncclComm_t comm = (ncclComm_t)sl.comm;
   NCCL_CHECK(c, A->GroupStart());
   for (int i = 0; i < ncomp; ++i) {
     char* b = (char*)base + comp * i;
     // 0-based storage plane p holds 1-based plane p+1
-    if (sl.upper >= 0) NCCL_CHECK(c, A->Send(b + pl * (size_t)(c->kz1 - 1 - sl.G), pl * G, ncclInt8, sl.upper, comm, st));
-    if (sl.lower >= 0) NCCL_CHECK(c, A->Send(b + pl * (size_t)(c->kz0 - 1), pl * G, ncclInt8, sl.lower, comm, st));
-    if (sl.lower >= 0) NCCL_CHECK(c, A->Recv(b + pl * (size_t)(c->kz0 - 1 - sl.G), pl * G, ncclInt8, sl.lower, comm, st));
-    if (sl.upper >= 0) NCCL_CHECK(c, A->Recv(b + pl * (size_t)(c->kz1 - 1), pl * G, ncclInt8, sl.upper, comm, st));
-    c->slab.bytes_sent += (long long)(pl * G) * ((sl.upper >= 0) + (sl.lower >= 0));
+    if (sl.upper >= 0) NCCL_CHECK(c, A->Send(b + pl * (size_t)(c->kz1 - 1 - nup), pl * (size_t)nup, ncclInt8, sl.upper, comm, st));
+    if (sl.lower >= 0) NCCL_CHECK(c, A->Send(b + pl * (size_t)(c->kz0 - 1), pl * (size_t)ndn, ncclInt8, sl.lower, comm, st));
+    if (sl.lower >= 0) NCCL_CHECK(c, A->Recv(b + pl * (size_t)(c->kz0 - 1 - nup), pl * (size_t)nup, ncclInt8, sl.lower, comm, st));
+    if (sl.upper >= 0) NCCL_CHECK(c, A->Recv(b + pl * (size_t)(c->kz1 - 1), pl * (size_t)ndn, ncclInt8, sl.upper, comm, st));
+    c->slab.bytes_sent += (long long)pl * ((sl.upper >= 0 ? nup : 0) + (sl.lower >= 0 ? ndn : 0));
   }
   NCCL_CHECK(c, A->GroupEnd());
   return 0;
@@ -508,10 +511,13 @@ static int advect_vof_rhouu_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* Phi
       return r;
     };
     auto exchange_outputs = [&](cudaStream_t xs) -> int {
+      // one NCCL group for everything the next sweep needs from the neighbours: f 3 planes up / 2 down, ρu 2 / 2, c̄ 3 / 2
       int r;
-      if ((r = slab_exchange(c, xs, fb[s + 1], sizeof(T), 1))) return r;
-      if ((r = slab_exchange(c, xs, rb[s + 1], sizeof(T), D))) return r;
-      if (s == 0 && (r = slab_exchange(c, xs, cbar, 1, 1))) return r;  // c̄ of the call (written by sweep 1 on owned planes)
+      NCCL_CHECK(c, nccl_api()->GroupStart());
+      if ((r = slab_exchange(c, xs, fb[s + 1], sizeof(T), 1, 3, 2))) return r;
+      if ((r = slab_exchange(c, xs, rb[s + 1], sizeof(T), D, 2, 2))) return r;
+      if (s == 0 && (r = slab_exchange(c, xs, cbar, 1, 1, 3, 2))) return r;  // c̄ of the call (written by sweep 1 on owned planes)
+      NCCL_CHECK(c, nccl_api()->GroupEnd());
       return 0;
     };
     if (!split) {
@@ -620,6 +626,7 @@ int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int dev
     c->use_march = (e && std::string(e) == "tile") ? 0 : ((e && std::string(e) == "march") ? 2 : 1);
     c->use_along2 = (e && std::string(e) == "along1") ? 0 : 1;  // "along1": the first register-marching kernel for y/z sweeps
     c->use_xrow = (e && std::string(e) == "xsweep") ? 0 : 1;    // "xsweep": the plane-marching kernel for CMOM x sweeps
+    c->use_arow = (e && std::string(e) == "along2") ? 0 : 1;    // "along2": the CTA-cooperative register-marching kernel for y/z sweeps
   }
   if (cudaMalloc(&c->red_dev, sizeof(unsigned long long) * 32) != cudaSuccess ||
       cudaMemset(c->red_dev, 0, sizeof(unsigned long long) * 32) != cudaSuccess ||
@@ -930,7 +937,7 @@ int host_pipe_build(ifadv_ctx* c, int cp) {
     CU_CHECK(c, cudaEventCreateWithFlags(&h.ev_out, cudaEventDisableTiming));
     hp->ch.push_back(h);
     if (ifadv_create(&hp->ch.back().ctx, 3, ng, c->dtype, c->device) != 0) { c->err = "child context creation failed"; return -3; }
-    hp->ch.back().ctx->use_march = c->use_march; hp->ch.back().ctx->use_along2 = c->use_along2; hp->ch.back().ctx->use_xrow = c->use_xrow;
+    hp->ch.back().ctx->use_march = c->use_march; hp->ch.back().ctx->use_along2 = c->use_along2; hp->ch.back().ctx->use_xrow = c->use_xrow; hp->ch.back().ctx->use_arow = c->use_arow;
     maxpl = std::max(maxpl, (size_t)(h.hi - h.lo));
   }
   hp->nset = (int)std::min<size_t>(3, hp->ch.size());
@@ -1163,11 +1170,16 @@ int ifadv_create_slab(ifadv_ctx** out, const int64_t Ng_local[3], int dtype, int
   c->kz0 = 2 + glo;
   c->kz1 = (int)Ng_local[2] - ghi;
   {
-    const char* e = getenv("IFADV_SLAB_OVERLAP");  // 0: exchanges on the caller's stream, one launch per sweep (measurement aid)
-    c->slab.overlap = (e && atoi(e) == 0) ? 0 : 1;
+    // IFADV_SLAB_OVERLAP=1: boundary planes first, exchange on a second (high-priority) stream underneath the interior planes.
+    // Measured on 4 / 8 B200 (profiles/r02_multigpu.md): with NCCL send/recv the split does not pay -- the three launches per sweep
+    // and the exchange kernel competing for SMs cost more than the exchange they hide -- so the default is the in-line exchange.
+    const char* e = getenv("IFADV_SLAB_OVERLAP");
+    c->slab.overlap = (e && atoi(e) != 0) ? 1 : 0;
   }
   if (nranks > 1) {
-    CU_CHECK(c, cudaStreamCreateWithFlags(&c->slab_stream, cudaStreamNonBlocking));
+    int plo = 0, phi = 0;  // the exchange must not queue behind the CTAs of the interior sweep: highest priority
+    CU_CHECK(c, cudaDeviceGetStreamPriorityRange(&plo, &phi));
+    CU_CHECK(c, cudaStreamCreateWithPriority(&c->slab_stream, cudaStreamNonBlocking, phi));
     CU_CHECK(c, cudaEventCreateWithFlags(&c->slab_ev[0], cudaEventDisableTiming));
     CU_CHECK(c, cudaEventCreateWithFlags(&c->slab_ev[1], cudaEventDisableTiming));
   }

@@ -47,6 +47,7 @@ struct ifadv_ctx {
   int use_march;  // 1: register-marching (y,z) + plane-marching (x) kernels (default); 2: plane-marching only; 0: v1 tile kernel
   int use_along2;  // 1 (default): lean register-marching kernel ifadv_along2.cuh for y/z sweeps; 0: ifadv_along.cuh
   int use_xrow;    // 1 (default): warp-autonomous row kernel ifadv_xrow.cuh for CMOM x sweeps; 0: ifadv_xsweep.cuh
+  int use_arow;    // 1: warp-autonomous column kernel ifadv_arow.cuh for Float32 y/z sweeps; 0: ifadv_along2.cuh
   int prof_on, prof_n;
   cudaEvent_t* prof_ev;  // 2 * IFADV_PROF_MAX events
   unsigned char* prof_tag;  // per launch: bit 0 = fused first sweep (10s+1 B/cell) / standard sweep (13s+1 B/cell); bits 1.. = 2*j + fused

@@ -10,7 +10,7 @@
 
 #include "ifadv_ctx.hpp"
 #ifndef IFADV_FAM
-#error "compile with -DIFADV_FAM=0..5"
+#error "compile with -DIFADV_FAM=0..6"
 #endif
 #if IFADV_FAM == 0
 #include "ifadv_sweep.cuh"
@@ -22,8 +22,10 @@
 #include "ifadv_along2.cuh"
 #elif IFADV_FAM == 4
 #include "ifadv_xsweep.cuh"
-#else
+#elif IFADV_FAM == 5
 #include "ifadv_xrow.cuh"
+#else
+#include "ifadv_arow.cuh"
 #endif
 
 namespace ifadv {
@@ -254,12 +256,49 @@ static int launch_xrow_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
 }
 #endif
 
+#if IFADV_FAM == 6
+#ifndef IFADV_XP_AROW_MB
+#define IFADV_XP_AROW_MB 2
+#endif
+// v6: warp-autonomous column kernel for sweeps along y / z (3-D only, even row pitch, vector-aligned arrays)
+template <class T, int J, bool MOM, bool FUSED, bool KOREN, int MINB, bool SAMEU>
+static int launch_arow_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  using TL = ARTile;
+  SweepP<T> P;
+  fill_params<T>(c, q, J, P);
+  if ((unsigned long long)c->g.S * 3ull >= 0xffffffffull) { c->err = "grid too large for 32-bit element offsets"; return -2; }
+  const size_t smem = TL::template Bytes<T>::cta;
+  auto kern = arow_kernel<T, J, MOM, FUSED, KOREN, MINB, SAMEU>;
+  static unsigned long long attr_devs = 0ull;
+  if (!((attr_devs >> (c->device & 63)) & 1ull)) {
+    CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_devs |= 1ull << (c->device & 63);
+  }
+  constexpr int DCC = (J == 1) ? 2 : 1;
+  const int nzo = c->kz1 - c->kz0;  // planes of dimension 3 to update (all of them on one GPU, the owned ones of a z-slab)
+  const int nx = c->g.n[0] - 2, ncc = (DCC == 2) ? nzo : c->g.n[DCC] - 2, na = (J == 2) ? nzo : c->g.n[J] - 2;
+  const unsigned gx = (unsigned)((nx + TL::TX) / TL::TX), gy = (unsigned)((ncc + TL::NW - 1) / TL::NW);  // elements 1..nx in tiles [62b, 62b+61]
+  int chunk = 128;  // four warm-up planes per chunk
+  while (chunk > 32 && (long long)gx * gy * ((na + chunk - 1) / chunk) < 148 * 8) chunk >>= 1;
+  if (const char* e = getenv("IFADV_CHUNK")) chunk = std::max(8, atoi(e));  // measurement override
+  dim3 grid(gx, gy, (unsigned)((na + chunk - 1) / chunk));
+  const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
+  if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
+  kern<<<grid, 256, smem, st>>>(P, chunk);
+  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_tag[c->prof_n] = (unsigned char)((q.fused ? 1 : 0) | ((2 * q.j + (q.fused ? 1 : 0)) << 1)); c->prof_n++; }
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+#endif
+
 // per-family entry points (3-D only), each defined and explicitly instantiated in its own translation unit
 template <class T, bool MOM> int launch_fam_march(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 template <class T, bool MOM> int launch_fam_along(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 template <class T, bool MOM> int launch_fam_along2(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 template <class T, bool MOM> int launch_fam_xsweep(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 template <class T, bool MOM> int launch_fam_xrow(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
+template <class T, bool MOM> int launch_fam_arow(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 // the row kernel moves two cells per access: rows must start vector-aligned (even row pitch) and so must every array
 template <class T> static bool xrow_ok(const ifadv_ctx* c, const SweepCfg<T>& q) {
   if (c->g.n[0] & 1) return false;
@@ -277,7 +316,10 @@ template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStrea
   }
   if constexpr (D == 3) {
     if (c->use_march == 1 && c->use_along2) {
-      if (q.j != 0) return launch_fam_along2<T, MOM>(c, st, q);
+      if (q.j != 0) {
+        if (c->use_arow && sizeof(T) == 4 && xrow_ok<T>(c, q)) return launch_fam_arow<T, MOM>(c, st, q);
+        return launch_fam_along2<T, MOM>(c, st, q);
+      }
       if (c->use_xrow && xrow_ok<T>(c, q)) return launch_fam_xrow<T, MOM>(c, st, q);
       if constexpr (MOM) return launch_fam_xsweep<T, MOM>(c, st, q);
     }
@@ -371,9 +413,11 @@ template <class T, bool MOM> int launch_fam_xsweep(ifadv_ctx* c, cudaStream_t st
 }
 template int launch_fam_xsweep<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
 
-#else
+#elif IFADV_FAM == 5
 template <class T, bool MOM> int launch_fam_xrow(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
-  constexpr int RR = IFADV_XP_XROW_R, MB = IFADV_XP_XROW_MB;
+  // Float32: two rows per warp at 128 registers (2 CTAs/SM); Float64: one row per warp at 222 registers without spills (1 CTA/SM) --
+  // two rows spill at 128 registers (x-sweep 2.01 ms at 256^3) and need 254 at 1 CTA/SM (1.44 ms); one row: 1.28 ms
+  constexpr int RR = (sizeof(T) == 4) ? IFADV_XP_XROW_R : 1, MB = (sizeof(T) == 4) ? IFADV_XP_XROW_MB : 1;
   if constexpr (!MOM) {  // pure VOF (advect!): no limiter, no momentum streams
     if (q.u == q.u0) return launch_xrow_t<T, RR, false, false, true, MB, true>(c, st, q);
     return launch_xrow_t<T, RR, false, false, true, MB, false>(c, st, q);
@@ -392,6 +436,23 @@ template <class T, bool MOM> int launch_fam_xrow(ifadv_ctx* c, cudaStream_t st, 
   }
 }
 template int launch_fam_xrow<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
+
+#elif IFADV_FAM == 6
+template <class T, bool MOM> int launch_fam_arow(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  constexpr int MB = IFADV_XP_AROW_MB;
+  if constexpr (!MOM) {
+    if (q.u == q.u0) return q.j == 1 ? launch_arow_t<T, 1, false, false, true, MB, true>(c, st, q) : launch_arow_t<T, 2, false, false, true, MB, true>(c, st, q);
+    return q.j == 1 ? launch_arow_t<T, 1, false, false, true, MB, false>(c, st, q) : launch_arow_t<T, 2, false, false, true, MB, false>(c, st, q);
+  } else {
+    const bool koren = q.lim == 2;
+    if (koren && q.u == q.u0) {
+      if (q.fused) return q.j == 1 ? launch_arow_t<T, 1, true, true, true, MB, true>(c, st, q) : launch_arow_t<T, 2, true, true, true, MB, true>(c, st, q);
+      return q.j == 1 ? launch_arow_t<T, 1, true, false, true, MB, true>(c, st, q) : launch_arow_t<T, 2, true, false, true, MB, true>(c, st, q);
+    }
+    return launch_fam_along2<T, MOM>(c, st, q);  // general instantiations: the CTA-cooperative kernel
+  }
+}
+template int launch_fam_arow<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
 #endif
 
 }  // namespace ifadv
