@@ -278,7 +278,8 @@ class _Single:
 
     def step(self):
         if self.vof:
-            self.ia.advect(self.sim.flow, self.sim.intf, check=False)  # advect!(a,c): pure VOF with u⁰, u (advection.jl:17-23)
+            # advect!(a,c): pure VOF with u⁰, u (advection.jl:17-23); without the optional ρuf output, as the 4s+1 B/cell accounting assumes
+            self.ia.advect(self.sim.flow, self.sim.intf, check=False, want_rhouf=False)
         else:
             self.ia.mom_advect_step(self.sim.flow, self.sim.intf, 1.0)
         self.sim.flow.dt.append(1.0)  # fixed Δt; advances the sweep-order rotation like push!(Δt) would
@@ -448,7 +449,10 @@ def measure_workload(ia, torch, dist, wl, rank, world, dev, local, steps, warmup
     value = cells * steps / (r["ms"] * 1e-3) / 1e9
     roof = roofline_of(w, wl, N_gpu, r, steps)
     sent = getattr(runner, "bytes_sent", 0)
+    w = dict(w, _transport=getattr(runner, "transport", "none"))
     del runner
+    if dist is not None:
+        dist.barrier()  # every rank has dropped its mappings of the neighbours' buffers before anybody frees them
     torch.cuda.synchronize(); torch.cuda.empty_cache()
     ia.api._contexts.clear()
     return w, N_gpu, r, value, roof, sent
@@ -535,8 +539,8 @@ def run_b200(args):
                                                "solenoidal", None: "config default (Taylor-Green, u_z ≡ 0 in 3-D; C1: rigid rotation; C2: Enright)"}[w["vel"]],
                        "step": "pure-VOF advection step = advect! = D fused sweeps" if vof else "CMOM advection step = 2 x (u2rhou + BC + advectfq) + midpoint f0 = 6 fused sweeps (u2rhou+BC folded into the first sweep of each group); the u0<-u / f0<-f copies and the midpoint run on a second stream underneath the sweeps",
                        "l2": "working set >> 126 MB L2 (inputs larger than L2, no flush needed)",
-                       "parallelism": (f"z-slab x{world}: 3 ghost planes per neighbour side, NCCL send/recv of f, rho-u, c-bar after every directional "
-                                       "sweep, overlapped with the sweep of the interior planes") if world > 1 else "single GPU",
+                       "parallelism": (f"z-slab x{world}: 3 ghost planes per neighbour side, exchange of f (3 planes up / 2 down), rho-u (2 / 2) and "
+                                       f"c-bar after every directional sweep; transport: {w.get('_transport')}") if world > 1 else "single GPU",
                        "nccl_bytes_sent_per_rank_per_step": int(sent / (args.steps + args.warmup)) if world > 1 else 0,
                        "mass_drift_rel": r["mass_drift_rel"]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": r["launches"], "clocks": r["clocks"],

@@ -157,6 +157,12 @@ int ifadv_defer_f_writes_until(ifadv_ctx* ctx, void* event);
  * comm: an ncclComm_t (from NCCL.jl / the host framework; or ifadv_nccl_comm_init below), borrowed for the context's lifetime. */
 int ifadv_create_slab(ifadv_ctx** ctx, const int64_t Ng_local[3], int dtype, int device, void* nccl_comm, int rank, int nranks,
                       int ghost_planes, int periodic_z);
+/* Transport of the exchanges.  Default: peer-to-peer -- every rank maps a staging buffer and a flag block of its two neighbours
+ * through CUDA IPC when the context is created; an exchange is then copy-engine pushes over NVLink (cudaMemcpyAsync into the
+ * neighbour's staging buffer) ordered by flags in the receiver's memory, without a host synchronisation and without an SM-resident
+ * communication kernel.  The NCCL communicator carries the handles at creation and the scalar all-reduces.  When IPC is not
+ * available on some rank (or IFADV_SLAB_P2P=0) all ranks use ncclSend/ncclRecv instead.  1 = peer-to-peer in use. */
+int ifadv_slab_p2p(const ifadv_ctx* ctx);
 /* owned plane range [kz0, kz1) (1-based), neighbour ranks (-1 = physical boundary), bytes sent by this context's exchanges */
 int ifadv_slab_info(const ifadv_ctx* ctx, int* kz0, int* kz1, int* lower, int* upper, int64_t* bytes_sent);
 /* exchange the ghost planes of `ncomp` fields (component stride = one scalar field) of `elem_bytes`-byte elements; no-op on a

@@ -65,6 +65,7 @@ def lib():
         L.ifadv_create_slab.argtypes = [C.POINTER(vp), i64p, i32, i32, vp, i32, i32, i32, i32]
         L.ifadv_slab_info.argtypes = [vp, i32p, i32p, i32p, i32p, i64p]
         L.ifadv_exchange_planes.argtypes = [vp, vp, vp, i32, i32]
+        L.ifadv_slab_p2p.argtypes = [vp]
         L.ifadv_nccl_unique_id.argtypes = [C.c_char_p]
         L.ifadv_nccl_comm_init.argtypes = [C.POINTER(vp), i32, C.c_char_p, i32, i32]
         L.ifadv_nccl_comm_destroy.argtypes = [vp]
@@ -111,7 +112,8 @@ class Context:
         """-> dict(kz0, kz1, lower, upper, bytes_sent): owned planes [kz0, kz1) (1-based), neighbour ranks, exchange volume"""
         a, b, lo, up, n = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0), C.c_int64(0)
         self._chk(lib().ifadv_slab_info(self._h, C.byref(a), C.byref(b), C.byref(lo), C.byref(up), C.byref(n)))
-        return dict(kz0=a.value, kz1=b.value, lower=lo.value, upper=up.value, bytes_sent=int(n.value))
+        return dict(kz0=a.value, kz1=b.value, lower=lo.value, upper=up.value, bytes_sent=int(n.value),
+                    transport="cuda-ipc peer-to-peer (copy engines)" if lib().ifadv_slab_p2p(self._h) else "nccl send/recv")
 
     def exchange_planes(self, stream, field, ncomp, elem_bytes):
         return self._chk(lib().ifadv_exchange_planes(self._h, stream, field, int(ncomp), int(elem_bytes)))

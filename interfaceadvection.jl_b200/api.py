@@ -268,14 +268,15 @@ def advectVOF(f, ff, alpha, nhat, u, u0, dt, cbar, rhouf, lam_rho, normalScheme=
     return _report(st, rep) if check else st
 
 
-def advect(a: Flow, c: cVOF, f=None, u1=None, u2=None, dt=None, check=True):
-    """advect!(a,c,f,u¹,u²,dt)  (src/advection.jl:17-23)"""
+def advect(a: Flow, c: cVOF, f=None, u1=None, u2=None, dt=None, check=True, want_rhouf=True):
+    """advect!(a,c,f,u¹,u²,dt)  (src/advection.jl:17-23).  want_rhouf=False skips the un-normalised mass flux ρuf that advect! leaves
+    behind for its callers (IFADV_NO_RHOUF: D·s bytes per cell and step less, plus the fill!(ρuf,0) pass)."""
     f = c.f if f is None else f
     u1 = a.u0 if u1 is None else u1
     u2 = a.u if u2 is None else u2
     dt = a.dt[-1] if dt is None else dt
     return advectVOF(f, c.ff, c.alpha, c.nhat, u1, u2, dt, c.cbar, c.rhouf, c.lam_rho, c.normalScheme, perdir=a.perdir,
-                     dirO=_dirO(a, a.D), check=check)
+                     dirO=_dirO(a, a.D), check=check, want_rhouf=want_rhouf)
 
 
 def advectVOFrhouu(f, ff, alpha, nhat, u, u0, dt, cbar, rhou, r, Phi, rhouf, uStar, uOld, dilaU, drho, lam_rho, lam="Koren",

@@ -399,32 +399,193 @@ NcclApi* nccl_api() {
     }                                                                                                          \
   } while (0)
 
-// Ghost planes of `ncomp` fields of `esz`-byte elements (component stride S elements): my top G owned planes -> the upper neighbour's
-// lower ghost planes, my bottom G owned planes -> the lower neighbour's upper ghost planes; ONE NCCL group on the caller's stream.
-// Posting order (sends: up, down; receives: from below, from above) lets NCCL match the pairs when both neighbours are one peer.
-// nup: planes sent UP (my top owned planes -> the upper neighbour's lower ghost planes), ndn: planes sent DOWN.  A sweep reaches 3
-// planes below / 2 above a cell for f and 2 / 2 for ρu, so the inner calls send fewer than G planes where that suffices.
-int slab_exchange(ifadv_ctx* c, cudaStream_t st, void* base, size_t esz, int ncomp, int nup = -1, int ndn = -1) {
+// ---- flag kernels of the peer-to-peer path -------------------------------------------------------------------------------------
+__global__ void p2p_write_kernel(unsigned* a, unsigned* b, unsigned v) {
+  __threadfence_system();
+  if (a) *reinterpret_cast<volatile unsigned*>(a) = v;
+  if (b) *reinterpret_cast<volatile unsigned*>(b) = v;
+  __threadfence_system();
+}
+__global__ void p2p_wait_kernel(const unsigned* a, const unsigned* b, unsigned v, unsigned* err) {
+  // bounded spin (about 4 s): a mismatch between the ranks must surface as an error, never as a hung GPU
+  const long long t0 = clock64();
+  const volatile unsigned* va = a;
+  const volatile unsigned* vb = b;
+  while ((va && (int)(*va - v) < 0) || (vb && (int)(*vb - v) < 0)) {
+    if (clock64() - t0 > 8000000000ll) { atomicExch(err, 1u); break; }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+
+struct XItem {
+  void* base;
+  size_t esz;
+  int ncomp, nup, ndn;
+};
+
+// Ghost planes of a batch of fields (component stride S elements): my top `nup` owned planes -> the upper neighbour's lower ghost
+// planes, my bottom `ndn` owned planes -> the lower neighbour's upper ghost planes.  A sweep reaches 3 planes below / 2 above a
+// cell for f and 2 / 2 for ρu, so the inner calls send fewer than G planes where that suffices.
+// Peer-to-peer path (default): copy engines push over NVLink into the receiver's staging buffer, flags in the receiver's memory
+// order sender and receiver on the streams (no host synchronisation, no SM-resident communication kernel):
+//   ready(seq) -> neighbours;  wait ready(seq) from neighbours;  push;  done(seq) -> neighbours;  wait done(seq);  unpack.
+// NCCL path (IFADV_SLAB_P2P=0, or when IPC is not available): ncclSend/ncclRecv in ONE group; sends go [up, down] and receives
+// [from below, from above] per component, so the pairs match when both neighbours are one peer.
+int slab_exchange_batch(ifadv_ctx* c, cudaStream_t st, const XItem* items, int n) {
   const ifadv_slab& sl = c->slab;
   if (sl.nranks <= 1) return 0;
+  const size_t s2 = (size_t)c->g.s2, S = (size_t)c->g.S;
+  auto clampn = [&](int v) { return (v < 0 || v > sl.G) ? sl.G : v; };
+  if (c->p2p.on) {
+    size_t need_up = 0, need_dn = 0;
+    for (int i = 0; i < n; ++i) {
+      need_up += items[i].esz * s2 * (size_t)clampn(items[i].nup) * items[i].ncomp;
+      need_dn += items[i].esz * s2 * (size_t)clampn(items[i].ndn) * items[i].ncomp;
+    }
+    if (need_up <= c->p2p.cap && need_dn <= c->p2p.cap) {
+      ifadv_p2p& p = c->p2p;
+      const unsigned seq = ++p.seq;
+      unsigned* err = p.flags + 8;
+      const bool lo = sl.lower >= 0, up = sl.upper >= 0;
+      // I am the lower neighbour's UPPER neighbour (its flags [1], [3]) and the upper neighbour's LOWER neighbour (its [0], [2])
+      p2p_write_kernel<<<1, 1, 0, st>>>(lo ? p.peer_flags[0] + 1 : nullptr, up ? p.peer_flags[1] + 0 : nullptr, seq);
+      p2p_wait_kernel<<<1, 1, 0, st>>>(lo ? p.flags + 0 : nullptr, up ? p.flags + 1 : nullptr, seq, err);
+      size_t offU = 0, offD = 0;
+      for (int i = 0; i < n; ++i) {
+        const size_t esz = items[i].esz, pl = esz * s2, comp = esz * S;
+        const int nup = clampn(items[i].nup), ndn = clampn(items[i].ndn);
+        for (int k = 0; k < items[i].ncomp; ++k) {
+          const char* b = (const char*)items[i].base + comp * k;  // 0-based storage plane q holds 1-based plane q+1
+          if (up) { CU_CHECK(c, cudaMemcpyAsync(p.peer_stage[1] + offU, b + pl * (size_t)(c->kz1 - 1 - nup), pl * nup, cudaMemcpyDeviceToDevice, st)); offU += pl * nup; }
+          if (lo) { CU_CHECK(c, cudaMemcpyAsync(p.peer_stage[0] + offD, b + pl * (size_t)(c->kz0 - 1), pl * ndn, cudaMemcpyDeviceToDevice, st)); offD += pl * ndn; }
+          c->slab.bytes_sent += (long long)pl * ((up ? nup : 0) + (lo ? ndn : 0));
+        }
+      }
+      p2p_write_kernel<<<1, 1, 0, st>>>(lo ? p.peer_flags[0] + 3 : nullptr, up ? p.peer_flags[1] + 2 : nullptr, seq);
+      p2p_wait_kernel<<<1, 1, 0, st>>>(lo ? p.flags + 2 : nullptr, up ? p.flags + 3 : nullptr, seq, err);
+      size_t offL = 0, offH = 0;  // my stage[0] holds the lower neighbour's up-push (nup planes), stage[1] the upper's down-push (ndn)
+      for (int i = 0; i < n; ++i) {
+        const size_t esz = items[i].esz, pl = esz * s2, comp = esz * S;
+        const int nup = clampn(items[i].nup), ndn = clampn(items[i].ndn);
+        for (int k = 0; k < items[i].ncomp; ++k) {
+          char* b = (char*)items[i].base + comp * k;
+          if (lo) { CU_CHECK(c, cudaMemcpyAsync(b + pl * (size_t)(c->kz0 - 1 - nup), p.stage[0] + offL, pl * nup, cudaMemcpyDeviceToDevice, st)); offL += pl * nup; }
+          if (up) { CU_CHECK(c, cudaMemcpyAsync(b + pl * (size_t)(c->kz1 - 1), p.stage[1] + offH, pl * ndn, cudaMemcpyDeviceToDevice, st)); offH += pl * ndn; }
+        }
+      }
+      c->launches += 4;
+      CU_CHECK(c, cudaGetLastError());
+      return 0;
+    }
+  }
   NcclApi* A = nccl_api();
   if (!A->ok) return fail(c, -4, "NCCL is not available");
-  if (nup < 0 || nup > sl.G) nup = sl.G;
-  if (ndn < 0 || ndn > sl.G) ndn = sl.G;
-  const size_t pl = esz * (size_t)c->g.s2, comp = esz * (size_t)c->g.S;
   ncclComm_t comm = (ncclComm_t)sl.comm;
   NCCL_CHECK(c, A->GroupStart());
-  for (int i = 0; i < ncomp; ++i) {
-    char* b = (char*)base + comp * i;
-    // 0-based storage plane p holds 1-based plane p+1
-    if (sl.upper >= 0) NCCL_CHECK(c, A->Send(b + pl * (size_t)(c->kz1 - 1 - nup), pl * (size_t)nup, ncclInt8, sl.upper, comm, st));
-    if (sl.lower >= 0) NCCL_CHECK(c, A->Send(b + pl * (size_t)(c->kz0 - 1), pl * (size_t)ndn, ncclInt8, sl.lower, comm, st));
-    if (sl.lower >= 0) NCCL_CHECK(c, A->Recv(b + pl * (size_t)(c->kz0 - 1 - nup), pl * (size_t)nup, ncclInt8, sl.lower, comm, st));
-    if (sl.upper >= 0) NCCL_CHECK(c, A->Recv(b + pl * (size_t)(c->kz1 - 1), pl * (size_t)ndn, ncclInt8, sl.upper, comm, st));
-    c->slab.bytes_sent += (long long)pl * ((sl.upper >= 0 ? nup : 0) + (sl.lower >= 0 ? ndn : 0));
+  for (int i = 0; i < n; ++i) {
+    const size_t esz = items[i].esz, pl = esz * s2, comp = esz * S;
+    const int nup = clampn(items[i].nup), ndn = clampn(items[i].ndn);
+    for (int k = 0; k < items[i].ncomp; ++k) {
+      char* b = (char*)items[i].base + comp * k;
+      if (sl.upper >= 0) NCCL_CHECK(c, A->Send(b + pl * (size_t)(c->kz1 - 1 - nup), pl * (size_t)nup, ncclInt8, sl.upper, comm, st));
+      if (sl.lower >= 0) NCCL_CHECK(c, A->Send(b + pl * (size_t)(c->kz0 - 1), pl * (size_t)ndn, ncclInt8, sl.lower, comm, st));
+      if (sl.lower >= 0) NCCL_CHECK(c, A->Recv(b + pl * (size_t)(c->kz0 - 1 - nup), pl * (size_t)nup, ncclInt8, sl.lower, comm, st));
+      if (sl.upper >= 0) NCCL_CHECK(c, A->Recv(b + pl * (size_t)(c->kz1 - 1), pl * (size_t)ndn, ncclInt8, sl.upper, comm, st));
+      c->slab.bytes_sent += (long long)pl * ((sl.upper >= 0 ? nup : 0) + (sl.lower >= 0 ? ndn : 0));
+    }
   }
   NCCL_CHECK(c, A->GroupEnd());
   return 0;
+}
+int slab_exchange(ifadv_ctx* c, cudaStream_t st, void* base, size_t esz, int ncomp, int nup = -1, int ndn = -1) {
+  XItem it{base, esz, ncomp, nup, ndn};
+  return slab_exchange_batch(c, st, &it, 1);
+}
+
+// Set up the peer-to-peer path of a slab context: staging buffers + flag block, IPC handles swapped with both neighbours through the
+// NCCL communicator, all ranks agree (all-reduce) whether every mapping succeeded; on any failure everybody stays on NCCL.
+struct P2PHello {
+  cudaIpcMemHandle_t h[3];  // flags, stage[0], stage[1]
+  int ok;
+};
+int slab_p2p_setup(ifadv_ctx* c) {
+  ifadv_p2p& p = c->p2p;
+  const ifadv_slab& sl = c->slab;
+  NcclApi* A = nccl_api();
+  if (!A->ok) return 0;
+  const char* e = getenv("IFADV_SLAB_P2P");
+  int want = !(e && atoi(e) == 0);
+  const size_t esz = esize(c->dtype);
+  p.cap = (size_t)sl.G * (size_t)c->g.s2 * (4 * esz + 1);  // f + 3 components of ρu (or u) + c̄, G planes each
+  P2PHello mine{};
+  mine.ok = 0;
+  if (want && cudaMalloc(&p.flags, 64) == cudaSuccess && cudaMemset(p.flags, 0, 64) == cudaSuccess &&
+      cudaMalloc(&p.stage[0], p.cap) == cudaSuccess && cudaMalloc(&p.stage[1], p.cap) == cudaSuccess &&
+      cudaIpcGetMemHandle(&mine.h[0], p.flags) == cudaSuccess && cudaIpcGetMemHandle(&mine.h[1], p.stage[0]) == cudaSuccess &&
+      cudaIpcGetMemHandle(&mine.h[2], p.stage[1]) == cudaSuccess)
+    mine.ok = 1;
+  cudaGetLastError();
+  // swap hellos with the neighbours
+  P2PHello* dev = nullptr;  // [0] mine, [1] from lower, [2] from upper
+  P2PHello got[3];
+  memset(got, 0, sizeof got);
+  cudaStream_t st = nullptr;
+  CU_CHECK(c, cudaMalloc(&dev, 3 * sizeof(P2PHello)));
+  CU_CHECK(c, cudaMemset(dev, 0, 3 * sizeof(P2PHello)));
+  CU_CHECK(c, cudaMemcpy(dev, &mine, sizeof mine, cudaMemcpyHostToDevice));
+  ncclComm_t comm = (ncclComm_t)sl.comm;
+  NCCL_CHECK(c, A->GroupStart());
+  if (sl.upper >= 0) NCCL_CHECK(c, A->Send(dev, sizeof(P2PHello), ncclInt8, sl.upper, comm, st));
+  if (sl.lower >= 0) NCCL_CHECK(c, A->Send(dev, sizeof(P2PHello), ncclInt8, sl.lower, comm, st));
+  if (sl.lower >= 0) NCCL_CHECK(c, A->Recv(dev + 1, sizeof(P2PHello), ncclInt8, sl.lower, comm, st));
+  if (sl.upper >= 0) NCCL_CHECK(c, A->Recv(dev + 2, sizeof(P2PHello), ncclInt8, sl.upper, comm, st));
+  NCCL_CHECK(c, A->GroupEnd());
+  CU_CHECK(c, cudaStreamSynchronize(st));
+  CU_CHECK(c, cudaMemcpy(got, dev, sizeof got, cudaMemcpyDeviceToHost));
+  int ok = mine.ok;
+  for (auto& q : p.opened) q = nullptr;
+  auto open = [&](const cudaIpcMemHandle_t& h, int slot) -> void* {
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; return nullptr; }
+    p.opened[slot] = ptr;
+    return ptr;
+  };
+  if (ok && sl.lower >= 0) {
+    if (!got[1].ok) ok = 0;
+    else {
+      p.peer_flags[0] = (unsigned*)open(got[1].h[0], 0);
+      p.peer_stage[0] = (char*)open(got[1].h[2], 1);  // the lower neighbour's stage[1]: filled by ITS upper neighbour, me
+    }
+  }
+  if (ok && sl.upper >= 0) {
+    if (!got[2].ok) ok = 0;
+    else if (sl.upper == sl.lower) {  // two ranks, periodic z: one peer in both roles -- a handle is opened once per process
+      p.peer_flags[1] = p.peer_flags[0];
+      p.peer_stage[1] = (char*)open(got[2].h[1], 2);
+    } else {
+      p.peer_flags[1] = (unsigned*)open(got[2].h[0], 3);
+      p.peer_stage[1] = (char*)open(got[2].h[1], 4);  // the upper neighbour's stage[0]: filled by ITS lower neighbour, me
+    }
+  }
+  // everybody or nobody
+  int* okd = (int*)dev;
+  CU_CHECK(c, cudaMemcpy(okd, &ok, sizeof(int), cudaMemcpyHostToDevice));
+  NCCL_CHECK(c, A->AllReduce(okd, okd, 1, ncclInt32, ncclMin, comm, st));
+  CU_CHECK(c, cudaStreamSynchronize(st));
+  CU_CHECK(c, cudaMemcpy(&ok, okd, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(dev);
+  p.on = ok;
+  p.seq = 0;
+  return 0;
+}
+void slab_p2p_free(ifadv_ctx* c) {
+  ifadv_p2p& p = c->p2p;
+  for (auto& q : p.opened) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+  if (p.flags) cudaFree(p.flags);
+  if (p.stage[0]) cudaFree(p.stage[0]);
+  if (p.stage[1]) cudaFree(p.stage[1]);
+  p.flags = nullptr; p.stage[0] = p.stage[1] = nullptr; p.on = 0;
 }
 }  // namespace
 
@@ -433,9 +594,25 @@ static int advect_vof_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* al, const
                         double lr, int ns, unsigned per, const int* dirO, int flags, ifadv_report* rep) {
   const int D = c->D;
   c->g.per = per;
+  const bool want_rhouf = !(flags & IFADV_NO_RHOUF) && rhouf != nullptr;
+  if (D == 2 && c->use_march != 0 && (long long)(c->g.n[0] - 2) * (c->g.n[1] - 2) <= (1ll << 20)) {
+    // small 2-D grids (BASELINE config 1): the whole step -- slot reset, fill!(ρuf,0), both sweeps, BCf! -- in one cooperative launch
+    SweepCfg<T> q[2];
+    T* bufs2[3] = {f, ff, f};
+    for (int s = 0; s < 2; ++s) {
+      q[s] = SweepCfg<T>{};
+      q[s].f_in = bufs2[s]; q[s].f_out = bufs2[s + 1];
+      q[s].u = u; q[s].u0 = u0; q[s].cbar = cbar; q[s].rhouf = want_rhouf ? rhouf : nullptr;
+      q[s].dt = dt; q[s].lr = lr; q[s].scheme = ns; q[s].lim = 0; q[s].first = (s == 0); q[s].j = dirO[s] - 1;
+      q[s].red = c->red_dev + 8 * s;
+    }
+    int rc = launch_vof2d_step<T>(c, st, q[0], q[1], f, want_rhouf ? rhouf : nullptr);
+    if (rc) return rc;
+    if (rep) return finish_report<T>(c, st, dirO, 10.0 * (double)std::numeric_limits<T>::epsilon(), rep, u, u0);
+    return 0;
+  }
   red_init_kernel<<<1, 32, 0, st>>>(c->red_dev, 3);
   c->launches++;
-  const bool want_rhouf = !(flags & IFADV_NO_RHOUF) && rhouf != nullptr;
   if (want_rhouf) CU_CHECK(c, cudaMemsetAsync(rhouf, 0, sizeof(T) * c->g.S * D, st));  // fill!(ρuf,0), advection.jl:37
   T* bufs[4] = {f, ff, (D == 3) ? al : f, f};  // f -> fᶠ -> α -> f (3-D);  f -> fᶠ -> f (2-D)
   for (int s = 0; s < D; ++s) {
@@ -511,14 +688,9 @@ static int advect_vof_rhouu_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* Phi
       return r;
     };
     auto exchange_outputs = [&](cudaStream_t xs) -> int {
-      // one NCCL group for everything the next sweep needs from the neighbours: f 3 planes up / 2 down, ρu 2 / 2, c̄ 3 / 2
-      int r;
-      NCCL_CHECK(c, nccl_api()->GroupStart());
-      if ((r = slab_exchange(c, xs, fb[s + 1], sizeof(T), 1, 3, 2))) return r;
-      if ((r = slab_exchange(c, xs, rb[s + 1], sizeof(T), D, 2, 2))) return r;
-      if (s == 0 && (r = slab_exchange(c, xs, cbar, 1, 1, 3, 2))) return r;  // c̄ of the call (written by sweep 1 on owned planes)
-      NCCL_CHECK(c, nccl_api()->GroupEnd());
-      return 0;
+      // everything the next sweep needs from the neighbours in one batch: f 3 planes up / 2 down, ρu 2 / 2, c̄ 3 / 2 (once per call)
+      XItem it[3] = {{fb[s + 1], sizeof(T), 1, 3, 2}, {rb[s + 1], sizeof(T), D, 2, 2}, {cbar, 1, 1, 3, 2}};
+      return slab_exchange_batch(c, xs, it, s == 0 ? 3 : 2);
     };
     if (!split) {
       if ((rc = sweep_planes(z0, z1, true))) return rc;
@@ -606,6 +778,7 @@ int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int dev
   c->D = D; c->dtype = dtype; c->device = device; c->launches = 0;
   c->slab = ifadv_slab{nullptr, 0, 1, 0, 0, 0, -1, -1, 0, 0};
   c->slab_stream = nullptr; c->slab_ev[0] = c->slab_ev[1] = nullptr;
+  memset(&c->p2p, 0, sizeof c->p2p);
   c->g.n[0] = (int)Ng[0]; c->g.n[1] = (int)Ng[1]; c->g.n[2] = (D == 3) ? (int)Ng[2] : 1;
   c->g.s1 = c->g.n[0]; c->g.s2 = (long long)c->g.n[0] * c->g.n[1];
   c->g.S = c->g.s2 * c->g.n[2];
@@ -626,7 +799,6 @@ int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int dev
     c->use_march = (e && std::string(e) == "tile") ? 0 : ((e && std::string(e) == "march") ? 2 : 1);
     c->use_along2 = (e && std::string(e) == "along1") ? 0 : 1;  // "along1": the first register-marching kernel for y/z sweeps
     c->use_xrow = (e && std::string(e) == "xsweep") ? 0 : 1;    // "xsweep": the plane-marching kernel for CMOM x sweeps
-    c->use_arow = (e && std::string(e) == "along2") ? 0 : 1;    // "along2": the CTA-cooperative register-marching kernel for y/z sweeps
   }
   if (cudaMalloc(&c->red_dev, sizeof(unsigned long long) * 32) != cudaSuccess ||
       cudaMemset(c->red_dev, 0, sizeof(unsigned long long) * 32) != cudaSuccess ||
@@ -649,6 +821,7 @@ int ifadv_destroy(ifadv_ctx* c) {
   if (c->pin_u) cudaFreeHost(c->pin_u);
   if (c->pin_ru) cudaFreeHost(c->pin_ru);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  slab_p2p_free(c);
   if (c->slab_stream) { cudaStreamDestroy(c->slab_stream); cudaEventDestroy(c->slab_ev[0]); cudaEventDestroy(c->slab_ev[1]); }
   host_pipe_free(c);
   if (c->prof_ev) { for (int k = 0; k < 2 * IFADV_PROF_MAX; ++k) cudaEventDestroy(c->prof_ev[k]); delete[] c->prof_ev; delete[] c->prof_tag; }
@@ -937,7 +1110,7 @@ int host_pipe_build(ifadv_ctx* c, int cp) {
     CU_CHECK(c, cudaEventCreateWithFlags(&h.ev_out, cudaEventDisableTiming));
     hp->ch.push_back(h);
     if (ifadv_create(&hp->ch.back().ctx, 3, ng, c->dtype, c->device) != 0) { c->err = "child context creation failed"; return -3; }
-    hp->ch.back().ctx->use_march = c->use_march; hp->ch.back().ctx->use_along2 = c->use_along2; hp->ch.back().ctx->use_xrow = c->use_xrow; hp->ch.back().ctx->use_arow = c->use_arow;
+    hp->ch.back().ctx->use_march = c->use_march; hp->ch.back().ctx->use_along2 = c->use_along2; hp->ch.back().ctx->use_xrow = c->use_xrow;
     maxpl = std::max(maxpl, (size_t)(h.hi - h.lo));
   }
   hp->nset = (int)std::min<size_t>(3, hp->ch.size());
@@ -1182,9 +1355,11 @@ int ifadv_create_slab(ifadv_ctx** out, const int64_t Ng_local[3], int dtype, int
     CU_CHECK(c, cudaStreamCreateWithPriority(&c->slab_stream, cudaStreamNonBlocking, phi));
     CU_CHECK(c, cudaEventCreateWithFlags(&c->slab_ev[0], cudaEventDisableTiming));
     CU_CHECK(c, cudaEventCreateWithFlags(&c->slab_ev[1], cudaEventDisableTiming));
+    if ((rc = slab_p2p_setup(c))) return rc;
   }
   return 0;
 }
+int ifadv_slab_p2p(const ifadv_ctx* c) { return c ? c->p2p.on : 0; }
 int ifadv_slab_info(const ifadv_ctx* c, int* kz0, int* kz1, int* lower, int* upper, int64_t* bytes_sent) {
   if (!c) return -2;
   if (kz0) *kz0 = c->kz0;
@@ -1204,6 +1379,12 @@ int ifadv_check_nan(ifadv_ctx* c, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   CU_CHECK(c, cudaMemcpyAsync(c->red_host, c->red_dev, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost, st));
   CU_CHECK(c, cudaStreamSynchronize(st));
+  if (c->p2p.on) {  // a peer-to-peer exchange that gave up waiting for a neighbour (ranks out of step) is a communication error
+    unsigned t = 0;
+    CU_CHECK(c, cudaMemcpyAsync(&t, c->p2p.flags + 8, sizeof t, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(c, cudaStreamSynchronize(st));
+    if (t) return fail(c, -4, "slab exchange timed out waiting for a neighbour");
+  }
   bool nan = c->red_host[24] != 0ull;
   for (int s = 0; s < 3; ++s) nan = nan || c->red_host[8 * s + 4] != 0ull;  // the most recent call's own sweeps
   if (!nan) return 0;

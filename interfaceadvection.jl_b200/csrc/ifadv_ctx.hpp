@@ -19,8 +19,21 @@ struct ifadv_slab {
   long long bytes_sent; // by the exchanges of this context
   int overlap;          // 1: boundary planes first, exchange on slab_stream underneath the interior planes
 };
+// Peer-to-peer exchange path of a z-slab context: neighbours PUSH their boundary planes with the copy engines (cudaMemcpyAsync over
+// NVLink into a staging buffer of the receiver, mapped through CUDA IPC) and signal with flags in the receiver's memory.
+struct ifadv_p2p {
+  int on;                      // 1: in use (every rank of the communicator agreed at creation)
+  char* stage[2];              // mine: [0] filled by the lower neighbour, [1] by the upper neighbour
+  unsigned* flags;             // mine: [0] READY_LO [1] READY_UP (neighbour may be pushed to), [2] DONE_LO [3] DONE_UP (its push has landed); [8] timeout
+  char* peer_stage[2];         // [0]: the lower neighbour's stage[1] (I am its upper neighbour), [1]: the upper neighbour's stage[0]
+  unsigned* peer_flags[2];     // [0]: the lower neighbour's flag block, [1]: the upper neighbour's
+  void* opened[6];             // IPC mappings to close
+  size_t cap;                  // bytes per staging buffer
+  unsigned seq;                // exchange counter (identical on all ranks: SPMD)
+};
 struct ifadv_ctx {
   int D, dtype, device;
+  ifadv_p2p p2p;
   int kz0, kz1;  // planes [kz0, kz1) of dimension 3 the sweeps update: 2 .. n[2], or the owned planes of a z-slab
   ifadv_slab slab;
   cudaStream_t slab_stream;  // second stream of the overlapped exchange
@@ -47,7 +60,6 @@ struct ifadv_ctx {
   int use_march;  // 1: register-marching (y,z) + plane-marching (x) kernels (default); 2: plane-marching only; 0: v1 tile kernel
   int use_along2;  // 1 (default): lean register-marching kernel ifadv_along2.cuh for y/z sweeps; 0: ifadv_along.cuh
   int use_xrow;    // 1 (default): warp-autonomous row kernel ifadv_xrow.cuh for CMOM x sweeps; 0: ifadv_xsweep.cuh
-  int use_arow;    // 1: warp-autonomous column kernel ifadv_arow.cuh for Float32 y/z sweeps; 0: ifadv_along2.cuh
   int prof_on, prof_n;
   cudaEvent_t* prof_ev;  // 2 * IFADV_PROF_MAX events
   unsigned char* prof_tag;  // per launch: bit 0 = fused first sweep (10s+1 B/cell) / standard sweep (13s+1 B/cell); bits 1.. = 2*j + fused
@@ -79,6 +91,8 @@ template <class T> struct SweepCfg {
 };
 
 
+// the whole 2-D pure-VOF step in one cooperative launch (small grids are launch-latency bound); defined in the (T, 2, 0, 0) unit
+template <class T> int launch_vof2d_step(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& qa, const SweepCfg<T>& qb, T* f_final, T* rhouf);
 // one fused directional sweep; defined in ifadv_sweep_inst.cu, one translation unit per (T, D, MOM)
 template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 }  // namespace ifadv

@@ -101,17 +101,17 @@ template <int D, int J, int TX, int TY, int TZ> struct Tile {
   template <class T> static constexpr size_t smem_bytes(bool mom) { return sizeof(T) * (2 * (size_t)FN + (mom ? (size_t)D * UN : 0)); }
 };
 
+// one tile (bx, by, bz) of the sweep; the kernel below runs one tile per CTA, vof2d_step_kernel loops over tiles
 template <class T, int D, int J, int TX, int TY, int TZ, bool MOM, int NT>
-__global__ void __launch_bounds__(NT) sweep_kernel(const SweepP<T> P) {
+IFADV_DI void sweep_tile(const SweepP<T>& P, const int bx, const int by, const int bz, unsigned char* smem_raw) {
   using TL = Tile<D, J, TX, TY, TZ>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sFF = reinterpret_cast<T*>(smem_raw);  // volume flux fᶠ through lower J-faces
   T* sM = sFF + TL::FN;                     // mass flux: ρuf/δt (MOM) or ρuf (pure VOF)
   T* sU = sM + TL::FN;                      // u★ components (MOM)
 
   const Geo g = P.g;
   const int tid = threadIdx.x;
-  const int o0 = 2 + blockIdx.x * TL::T0, o1 = 2 + blockIdx.y * TL::T1, o2 = (D == 3) ? 2 + blockIdx.z * TL::T2 : 1;
+  const int o0 = 2 + bx * TL::T0, o1 = 2 + by * TL::T1, o2 = (D == 3) ? 2 + bz * TL::T2 : 1;
   const bool per0 = g.per & 1u, per1 = g.per & 2u, per2 = (D == 3) && (g.per & 4u);
   const bool perJ = (J == 0) ? per0 : ((J == 1) ? per1 : per2);
   const int nJ = g.n[J];
@@ -319,6 +319,12 @@ __global__ void __launch_bounds__(NT) sweep_kernel(const SweepP<T> P) {
       if (rnan) atomicAdd(P.red + 4, 1ull);
     }
   }
+}
+
+template <class T, int D, int J, int TX, int TY, int TZ, bool MOM, int NT>
+__global__ void __launch_bounds__(NT) sweep_kernel(const SweepP<T> P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  sweep_tile<T, D, J, TX, TY, TZ, MOM, NT>(P, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, smem_raw);
 }
 
 }  // namespace ifadv

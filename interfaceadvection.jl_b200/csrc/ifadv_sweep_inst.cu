@@ -8,9 +8,11 @@
 #include <cstdlib>
 #include <limits>
 
+#include <cooperative_groups.h>
+
 #include "ifadv_ctx.hpp"
 #ifndef IFADV_FAM
-#error "compile with -DIFADV_FAM=0..6"
+#error "compile with -DIFADV_FAM=0..5"
 #endif
 #if IFADV_FAM == 0
 #include "ifadv_sweep.cuh"
@@ -22,10 +24,8 @@
 #include "ifadv_along2.cuh"
 #elif IFADV_FAM == 4
 #include "ifadv_xsweep.cuh"
-#elif IFADV_FAM == 5
-#include "ifadv_xrow.cuh"
 #else
-#include "ifadv_arow.cuh"
+#include "ifadv_xrow.cuh"
 #endif
 
 namespace ifadv {
@@ -256,49 +256,12 @@ static int launch_xrow_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
 }
 #endif
 
-#if IFADV_FAM == 6
-#ifndef IFADV_XP_AROW_MB
-#define IFADV_XP_AROW_MB 2
-#endif
-// v6: warp-autonomous column kernel for sweeps along y / z (3-D only, even row pitch, vector-aligned arrays)
-template <class T, int J, bool MOM, bool FUSED, bool KOREN, int MINB, bool SAMEU>
-static int launch_arow_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
-  using TL = ARTile;
-  SweepP<T> P;
-  fill_params<T>(c, q, J, P);
-  if ((unsigned long long)c->g.S * 3ull >= 0xffffffffull) { c->err = "grid too large for 32-bit element offsets"; return -2; }
-  const size_t smem = TL::template Bytes<T>::cta;
-  auto kern = arow_kernel<T, J, MOM, FUSED, KOREN, MINB, SAMEU>;
-  static unsigned long long attr_devs = 0ull;
-  if (!((attr_devs >> (c->device & 63)) & 1ull)) {
-    CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_devs |= 1ull << (c->device & 63);
-  }
-  constexpr int DCC = (J == 1) ? 2 : 1;
-  const int nzo = c->kz1 - c->kz0;  // planes of dimension 3 to update (all of them on one GPU, the owned ones of a z-slab)
-  const int nx = c->g.n[0] - 2, ncc = (DCC == 2) ? nzo : c->g.n[DCC] - 2, na = (J == 2) ? nzo : c->g.n[J] - 2;
-  const unsigned gx = (unsigned)((nx + TL::TX) / TL::TX), gy = (unsigned)((ncc + TL::NW - 1) / TL::NW);  // elements 1..nx in tiles [62b, 62b+61]
-  int chunk = 128;  // four warm-up planes per chunk
-  while (chunk > 32 && (long long)gx * gy * ((na + chunk - 1) / chunk) < 148 * 8) chunk >>= 1;
-  if (const char* e = getenv("IFADV_CHUNK")) chunk = std::max(8, atoi(e));  // measurement override
-  dim3 grid(gx, gy, (unsigned)((na + chunk - 1) / chunk));
-  const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
-  if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
-  kern<<<grid, 256, smem, st>>>(P, chunk);
-  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_tag[c->prof_n] = (unsigned char)((q.fused ? 1 : 0) | ((2 * q.j + (q.fused ? 1 : 0)) << 1)); c->prof_n++; }
-  c->launches++;
-  CU_CHECK(c, cudaGetLastError());
-  return 0;
-}
-#endif
-
 // per-family entry points (3-D only), each defined and explicitly instantiated in its own translation unit
 template <class T, bool MOM> int launch_fam_march(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 template <class T, bool MOM> int launch_fam_along(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 template <class T, bool MOM> int launch_fam_along2(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 template <class T, bool MOM> int launch_fam_xsweep(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 template <class T, bool MOM> int launch_fam_xrow(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
-template <class T, bool MOM> int launch_fam_arow(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 // the row kernel moves two cells per access: rows must start vector-aligned (even row pitch) and so must every array
 template <class T> static bool xrow_ok(const ifadv_ctx* c, const SweepCfg<T>& q) {
   if (c->g.n[0] & 1) return false;
@@ -316,10 +279,7 @@ template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStrea
   }
   if constexpr (D == 3) {
     if (c->use_march == 1 && c->use_along2) {
-      if (q.j != 0) {
-        if (c->use_arow && sizeof(T) == 4 && xrow_ok<T>(c, q)) return launch_fam_arow<T, MOM>(c, st, q);
-        return launch_fam_along2<T, MOM>(c, st, q);
-      }
+      if (q.j != 0) return launch_fam_along2<T, MOM>(c, st, q);
       if (c->use_xrow && xrow_ok<T>(c, q)) return launch_fam_xrow<T, MOM>(c, st, q);
       if constexpr (MOM) return launch_fam_xsweep<T, MOM>(c, st, q);
     }
@@ -336,6 +296,75 @@ template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStrea
   }
 }
 template int launch_sweep_dim<IFADV_T, IFADV_D, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
+
+#if IFADV_D == 2 && IFADV_MOM == 0
+// The whole 2-D pure-VOF step (advectVOF!, advection.jl:34-78) as ONE cooperative launch: reduction-slot reset, fill!(ρuf,0), the two
+// directional sweeps and the final BCf!, separated by grid-wide barriers.  Small 2-D grids (BASELINE config 1: 128², 16 k cells) are
+// launch-latency bound: five launches of ~13 µs each become one.
+namespace cg = cooperative_groups;
+template <class T, int JA, int JB>
+__global__ void __launch_bounds__(256) vof2d_step_kernel(const SweepP<T> PA, const SweepP<T> PB, T* f_final, T* rhouf, const long long nruf,
+                                                          unsigned long long* red, const unsigned per) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::grid_group grid = cg::this_grid();
+  const Geo g = PA.g;
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x, gs = (long long)gridDim.x * blockDim.x;
+  if (gt < 3) {  // red_init_kernel
+    unsigned long long* r = red + 8 * gt;
+    if (r[4] != 0ull) atomicOr(red + 24, 1ull);
+    r[0] = 0ull; r[1] = ~0ull; r[2] = 0ull; r[3] = ~0ull; r[4] = 0ull; r[5] = 0ull; r[6] = 0ull; r[7] = 0ull;
+  }
+  if (rhouf != nullptr)
+    for (long long i = gt; i < nruf; i += gs) rhouf[i] = T(0);  // fill!(ρuf,0), advection.jl:37
+  grid.sync();
+  auto sweep = [&](auto ja, const SweepP<T>& P) {
+    constexpr int J = decltype(ja)::value;
+    constexpr int TX = (J == 0) ? 64 : 32, TY = (J == 0) ? 8 : 16;
+    const int gx = (g.n[0] - 2 + TX - 1) / TX, gy = (g.n[1] - 2 + TY - 1) / TY;
+    for (int t = blockIdx.x; t < gx * gy; t += gridDim.x) {
+      sweep_tile<T, 2, J, TX, TY, 1, false, 256>(P, t % gx, t / gx, 0, smem_raw);
+      __syncthreads();  // the next tile reuses the shared planes
+    }
+  };
+  sweep(std::integral_constant<int, JA>{}, PA);
+  grid.sync();
+  sweep(std::integral_constant<int, JB>{}, PB);
+  grid.sync();
+  // BCf!(f;perdir), VOFutil.jl:64-75: every ghost cell takes the value of its interior-equivalent cell
+  const long long n0 = g.n[0], n1 = g.n[1], c0 = 2 * n1, c1 = 2 * n0;
+  for (long long t = gt; t < c0 + c1; t += gs) {
+    int x, y;
+    if (t < c0) { x = (t & 1) ? (int)n0 : 1; y = (int)(t >> 1) + 1; }
+    else { const long long q = t - c0; y = (q & 1) ? (int)n1 : 1; x = (int)(q >> 1) + 1; }
+    const int mx = mapc(x, g.n[0], per & 1u), my = mapc(y, g.n[1], per & 2u);
+    f_final[lin3(g, x, y, 1)] = f_final[lin3(g, mx, my, 1)];
+  }
+}
+
+template <class T> int launch_vof2d_step(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& qa, const SweepCfg<T>& qb, T* f_final, T* rhouf) {
+  SweepP<T> PA, PB;
+  fill_params<T>(c, qa, qa.j, PA);
+  fill_params<T>(c, qb, qb.j, PB);
+  const size_t smem = std::max(Tile<2, 0, 64, 8, 1>::template smem_bytes<T>(false), Tile<2, 1, 32, 16, 1>::template smem_bytes<T>(false));
+  void* kern = (qa.j == 0) ? (void*)vof2d_step_kernel<T, 0, 1> : (void*)vof2d_step_kernel<T, 1, 0>;
+  int per_sm = 0, sms = 0;
+  CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU_CHECK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+  CU_CHECK(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+  const int nx = c->g.n[0] - 2, ny = c->g.n[1] - 2;
+  const int tiles = std::max(((nx + 63) / 64) * ((ny + 7) / 8), ((nx + 31) / 32) * ((ny + 15) / 16));
+  const int grid = std::max(1, std::min(tiles, per_sm * sms));
+  T* ruf = rhouf;
+  long long nruf = (long long)c->g.S * 2;
+  unsigned long long* red = c->red_dev;
+  unsigned per = c->g.per;
+  void* args[] = {&PA, &PB, &f_final, &ruf, &nruf, &red, &per};
+  CU_CHECK(c, cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(256), args, smem, st));
+  c->launches++;
+  return 0;
+}
+template int launch_vof2d_step<IFADV_T>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&, const SweepCfg<IFADV_T>&, IFADV_T*, IFADV_T*);
+#endif
 
 #elif IFADV_FAM == 1
 template <class T, bool MOM> int launch_fam_march(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
@@ -418,9 +447,13 @@ template <class T, bool MOM> int launch_fam_xrow(ifadv_ctx* c, cudaStream_t st, 
   // Float32: two rows per warp at 128 registers (2 CTAs/SM); Float64: one row per warp at 222 registers without spills (1 CTA/SM) --
   // two rows spill at 128 registers (x-sweep 2.01 ms at 256^3) and need 254 at 1 CTA/SM (1.44 ms); one row: 1.28 ms
   constexpr int RR = (sizeof(T) == 4) ? IFADV_XP_XROW_R : 1, MB = (sizeof(T) == 4) ? IFADV_XP_XROW_MB : 1;
-  if constexpr (!MOM) {  // pure VOF (advect!): no limiter, no momentum streams
-    if (q.u == q.u0) return launch_xrow_t<T, RR, false, false, true, MB, true>(c, st, q);
-    return launch_xrow_t<T, RR, false, false, true, MB, false>(c, st, q);
+  if constexpr (!MOM) {  // pure VOF (advect!): no limiter, no momentum streams; little work per plane, so more resident warps pay
+#ifndef IFADV_XP_XROW_MB_VOF
+#define IFADV_XP_XROW_MB_VOF 3
+#endif
+    constexpr int MBV = (sizeof(T) == 4) ? IFADV_XP_XROW_MB_VOF : MB;
+    if (q.u == q.u0) return launch_xrow_t<T, RR, false, false, true, MBV, true>(c, st, q);
+    return launch_xrow_t<T, RR, false, false, true, MBV, false>(c, st, q);
   } else {
     const bool koren = q.lim == 2;
     if (koren && q.u == q.u0) {  // one velocity array for u¹ and u² (MPFMomStep!): the SAMEU instantiations
@@ -437,22 +470,6 @@ template <class T, bool MOM> int launch_fam_xrow(ifadv_ctx* c, cudaStream_t st, 
 }
 template int launch_fam_xrow<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
 
-#elif IFADV_FAM == 6
-template <class T, bool MOM> int launch_fam_arow(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
-  constexpr int MB = IFADV_XP_AROW_MB;
-  if constexpr (!MOM) {
-    if (q.u == q.u0) return q.j == 1 ? launch_arow_t<T, 1, false, false, true, MB, true>(c, st, q) : launch_arow_t<T, 2, false, false, true, MB, true>(c, st, q);
-    return q.j == 1 ? launch_arow_t<T, 1, false, false, true, MB, false>(c, st, q) : launch_arow_t<T, 2, false, false, true, MB, false>(c, st, q);
-  } else {
-    const bool koren = q.lim == 2;
-    if (koren && q.u == q.u0) {
-      if (q.fused) return q.j == 1 ? launch_arow_t<T, 1, true, true, true, MB, true>(c, st, q) : launch_arow_t<T, 2, true, true, true, MB, true>(c, st, q);
-      return q.j == 1 ? launch_arow_t<T, 1, true, false, true, MB, true>(c, st, q) : launch_arow_t<T, 2, true, false, true, MB, true>(c, st, q);
-    }
-    return launch_fam_along2<T, MOM>(c, st, q);  // general instantiations: the CTA-cooperative kernel
-  }
-}
-template int launch_fam_arow<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
 #endif
 
 }  // namespace ifadv

@@ -191,6 +191,10 @@ class SlabRunner:
     def bytes_sent(self) -> int:
         return self.ctx.slab_info()["bytes_sent"] if self.geom.world > 1 else 0
 
+    @property
+    def transport(self) -> str:
+        return self.ctx.slab_info()["transport"] if self.geom.world > 1 else "none"
+
     def step(self, project=None):
         self.ia.mom_advect_step(self.flow, self.intf, 1.0, project=project)
         self.flow.dt.append(1.0)
