@@ -98,21 +98,23 @@ int ifadv_advect_vof(ifadv_ctx* ctx, void* stream, void* f, void* ff, void* alph
  * reference: fᶠ, Φ hold f ping-pong copies, r and ρuf hold ρu ping-pong copies, c̄ is
  * rewritten.  uStar/dilaU may alias n̂/α as in advectfq! (flow.jl:157-160); they are not touched.
  * dρ is only READ (plane Ng[j] of component j, which the reference never writes).  uBC: constant tuple.
- * exitBC = true is rejected (-2): the reference reads stale scratch in that case. */
+ * exitBC = true (BC!'s saveexit at flow.jl:197,207): plane N of component 1 of u★ keeps the value the caller's r array
+ * holds there at entry (the reference reads r[N,·,·,1] as left by its previous use: identical for the first sweep,
+ * unspecified scratch afterwards -- DESIGN.md §5) and the exit face keeps its computed mass flux instead of uBC[1]. */
 int ifadv_advect_vof_rhouu(ifadv_ctx* ctx, void* stream, void* f, void* ff, void* alpha, void* nhat, const void* u,
                            const void* u0, double dt, int8_t* cbar, void* rhou, void* r, void* Phi, void* rhouf, void* uStar,
                            const void* uOld, void* dilaU, const void* drho, double lambda_rho, int limiter, int normal_scheme,
                            const double uBC[3], unsigned perdir_mask, int exitBC, const int dirO[3], ifadv_report* report);
 
 /* Fused form of the three calls MPFMomStep! makes back to back (src/flow.jl:61,69-70 and :89-92):
- *     f .= f_src;  u2ρu!(ρu,uOld,f,λρ);  BC!(ρu,uBC,false,perdir);  advectVOFρuu!(f,…,ρu,…,uOld,…)
+ *     f .= f_src;  u2ρu!(ρu,uOld,f,λρ);  BC!(ρu,uBC,exitBC,perdir);  advectVOFρuu!(f,…,ρu,…,uOld,…; exitBC)
  * Both call sites build ρu from the very velocity array they pass as uOld, so the first directional sweep can form
  * ρu = BC!(uOld·ρ(f̄)) on the fly: the u2ρu! pass, the BC! launch, the f⁰←f copy and three of the thirteen input streams
  * of sweep 1 disappear.  Results are bit-identical to the three separate calls.  f_src may equal f.  ρu is output only. */
 int ifadv_u2rhou_advect_vof_rhouu(ifadv_ctx* ctx, void* stream, const void* f_src, void* f, void* ff, void* Phi, const void* u,
                                   const void* u0, double dt, int8_t* cbar, void* rhou, void* r, void* rhouf, const void* uOld,
                                   const void* drho, double lambda_rho, int limiter, int normal_scheme, const double uBC[3],
-                                  unsigned perdir_mask, const int dirO[3], ifadv_report* report);
+                                  unsigned perdir_mask, int exitBC, const int dirO[3], ifadv_report* report);
 
 /* ---- secondary seams on the path ------------------------------------------------------------------------ */
 /* u2ρu!(ρu,u,f,λρ) / ρu2u!(u,ρu,f,λρ)                                           src/VOFutil.jl:198-211 */

@@ -49,7 +49,7 @@ def lib():
         L.ifadv_advect_vof_rhouu.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, i32, i32,
                                              dblp, u32, i32, i32p, rep]
         L.ifadv_u2rhou_advect_vof_rhouu.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp, dbl, i32, i32, dblp, u32,
-                                                    i32p, rep]
+                                                    i32, i32p, rep]
         L.ifadv_u2rhou.argtypes = [vp, vp, vp, vp, vp, dbl]
         L.ifadv_rhou2u.argtypes = [vp, vp, vp, vp, vp, dbl]
         L.ifadv_bc_vec.argtypes = [vp, vp, vp, dblp, i32, u32]
@@ -176,11 +176,11 @@ class Context:
                                                       _d3(uBC, self.D), perdir_mask(perdir), int(bool(exitBC)), _i3(dirO, self.D), r))
 
     def u2rhou_advect_vof_rhouu(self, stream, f_src, f, ff, Phi, u, u0, dt, cbar, rhou, r_, rhouf, uOld, drho, lam_rho, limiter, scheme,
-                                uBC, perdir, dirO, report=None):
+                                uBC, perdir, exitBC, dirO, report=None):
         r = C.byref(report) if report is not None else None
         return self._chk(lib().ifadv_u2rhou_advect_vof_rhouu(self._h, stream, f_src, f, ff, Phi, u, u0, float(dt), cbar, rhou, r_, rhouf,
                                                              uOld, drho, float(lam_rho), int(limiter), int(scheme),
-                                                             _d3(uBC, self.D), perdir_mask(perdir), _i3(dirO, self.D), r))
+                                                             _d3(uBC, self.D), perdir_mask(perdir), int(bool(exitBC)), _i3(dirO, self.D), r))
 
     def u2rhou(self, stream, rhou, u, f, lam_rho):
         return self._chk(lib().ifadv_u2rhou(self._h, stream, rhou, u, f, float(lam_rho)))

@@ -318,13 +318,11 @@ def MPCFL(a: Flow, c: cVOF, dt_max=1.0, safety=0.8) -> float:
 def u2rhou_advectfq(a: Flow, c: cVOF, f_src, f, u1, u2, uOld, dt=None, check=False):
     """Fused  f .= f_src; u2ρu!(c.ρu,uOld,f,λρ); BC!(c.ρu,…); advectfq!(a,c,f,u¹,u²,uOld,dt)  -- the three calls MPFMomStep! makes
     back to back at src/flow.jl:61,69-70 and :89-92 (ifadv_u2rhou_advect_vof_rhouu; bit-identical to the separate calls)."""
-    if a.exitBC:
-        raise IfadvError("exitBC=true is not supported by the B200 path")
     dt = a.dt[-1] if dt is None else dt
     rep = Report() if check else None
     st = context_for(f).u2rhou_advect_vof_rhouu(_stream(f), _p(f_src), _p(f), _p(c.ff), _p(a.sigma), _p(u1), _p(u2), dt, _p(c.cbar),
                                                 _p(c.rhou), _p(a.f), _p(c.rhouf), _p(uOld), _p(c.drho), c.lam_rho, _lim(a.lam),
-                                                _ns(c.normalScheme), a.uBC, a.perdir, _dirO(a, a.D), rep)
+                                                _ns(c.normalScheme), a.uBC, a.perdir, a.exitBC, _dirO(a, a.D), rep)
     return _report(st, rep) if check else st
 
 

@@ -638,9 +638,13 @@ template <class T> static int bcvec_t(ifadv_ctx* c, cudaStream_t st, T* a, const
 template <class T>
 static int advect_vof_rhouu_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* Phi, const T* u, const T* u0, double dt, int8_t* cbar, T* rhou,
                               T* r, T* rhouf, const T* uOld, const T* drho, double lr, int lim, int ns, const double* uBC, unsigned per,
-                              const int* dirO, ifadv_report* rep, cudaEvent_t wait_f, const T* f_src = nullptr, int fused = 0) {
+                              const int* dirO, ifadv_report* rep, cudaEvent_t wait_f, int exitBC, const T* f_src = nullptr, int fused = 0) {
   const int D = c->D;
   c->g.per = per;
+  // exitBC (BC!'s saveexit at flow.jl:197,207): plane N of component x of u★ keeps the value the caller's r array holds there and the
+  // exit face keeps its computed mass flux.  The lean kernels never write a ghost plane of r, so every sweep reads the entry value.
+  if (exitBC && (per & 1u)) exitBC = 0;  // no boundary planes in a periodic direction
+  if (exitBC && c->use_march != 0 && D == 3 && !c->use_along2) return fail(c, -2, "exitBC needs the lean kernels or the tile kernel (IFADV_KERNEL unset or tile)");
   // wait_f (ifadv_defer_f_writes_until): one-shot event this call waits for before its first write to f
   if (fused && (D == 2 || c->use_march == 0)) {
     if (f_src && f_src != f) {
@@ -649,7 +653,7 @@ static int advect_vof_rhouu_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* Phi
     }
     int rc0 = u2rhou_t<T>(c, st, rhou, uOld, f, lr, true);
     if (rc0) return rc0;
-    if ((rc0 = bcvec_t<T>(c, st, rhou, uBC, 0, per))) return rc0;
+    if ((rc0 = bcvec_t<T>(c, st, rhou, uBC, exitBC, per))) return rc0;
     f_src = nullptr;
     fused = 0;
   }
@@ -661,7 +665,7 @@ static int advect_vof_rhouu_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* Phi
     SweepCfg<T> q{};
     q.f_in = fb[s]; q.f_out = fb[s + 1];
     q.rhou_in = rb[s]; q.rhou_out = rb[s + 1];
-    q.u = u; q.u0 = u0; q.uOld = uOld; q.drho = drho; q.cbar = cbar; q.rhouf = nullptr;
+    q.u = u; q.u0 = u0; q.uOld = uOld; q.drho = drho; q.cbar = cbar; q.rhouf = nullptr; q.uexit = exitBC ? r : nullptr;
     q.dt = dt; q.lr = lr; q.scheme = ns; q.lim = lim; q.first = (s == 0); q.j = dirO[s] - 1;
     q.fused = (s == 0) ? fused : 0;
     for (int i = 0; i < 3; ++i) q.A[i] = (i < D) ? uBC[i] : 0.0;
@@ -893,23 +897,22 @@ int ifadv_advect_vof_rhouu(ifadv_ctx* c, void* stream, void* f, void* ff, void* 
   int rc = check_common(c, normal_scheme, dirO);
   if (rc) return rc;
   if (limiter < 0 || limiter > 10) return fail(c, -2, "invalid limiter");
-  if (exitBC) return fail(c, -2, "exitBC=true is not supported: the reference reads stale scratch on the exit plane (DESIGN.md)");
   if (!f || !ff || !u || !u0 || !cbar || !rhou || !r || !uOld || !drho || !uBC || (c->D == 3 && (!Phi || !rhouf)))
     return fail(c, -2, "null array");
   cudaStream_t st = (cudaStream_t)stream;
   if (c->dtype == IFADV_F32)
     return advect_vof_rhouu_t<float>(c, st, (float*)f, (float*)ff, (float*)Phi, (const float*)u, (const float*)u0, dt, cbar, (float*)rhou,
                                      (float*)r, (float*)rhouf, (const float*)uOld, (const float*)drho, lambda_rho, limiter, normal_scheme,
-                                     uBC, perdir_mask, dirO, report, wait_f);
+                                     uBC, perdir_mask, dirO, report, wait_f, exitBC);
   return advect_vof_rhouu_t<double>(c, st, (double*)f, (double*)ff, (double*)Phi, (const double*)u, (const double*)u0, dt, cbar,
                                     (double*)rhou, (double*)r, (double*)rhouf, (const double*)uOld, (const double*)drho, lambda_rho, limiter,
-                                    normal_scheme, uBC, perdir_mask, dirO, report, wait_f);
+                                    normal_scheme, uBC, perdir_mask, dirO, report, wait_f, exitBC);
 }
 
 int ifadv_u2rhou_advect_vof_rhouu(ifadv_ctx* c, void* stream, const void* f_src, void* f, void* ff, void* Phi, const void* u, const void* u0,
                                   double dt, int8_t* cbar, void* rhou, void* r, void* rhouf, const void* uOld, const void* drho,
                                   double lambda_rho, int limiter, int normal_scheme, const double uBC[3], unsigned perdir_mask,
-                                  const int dirO[3], ifadv_report* report) {
+                                  int exitBC, const int dirO[3], ifadv_report* report) {
   cudaEvent_t wait_f = nullptr;
   if (c) { wait_f = c->wait_f; c->wait_f = nullptr; }  // one-shot, consumed even when the call is rejected below
   int rc = check_common(c, normal_scheme, dirO);
@@ -921,10 +924,10 @@ int ifadv_u2rhou_advect_vof_rhouu(ifadv_ctx* c, void* stream, const void* f_src,
   if (c->dtype == IFADV_F32)
     return advect_vof_rhouu_t<float>(c, st, (float*)f, (float*)ff, (float*)Phi, (const float*)u, (const float*)u0, dt, cbar, (float*)rhou,
                                      (float*)r, (float*)rhouf, (const float*)uOld, (const float*)drho, lambda_rho, limiter, normal_scheme,
-                                     uBC, perdir_mask, dirO, report, wait_f, (const float*)f_src, 1);
+                                     uBC, perdir_mask, dirO, report, wait_f, exitBC, (const float*)f_src, 1);
   return advect_vof_rhouu_t<double>(c, st, (double*)f, (double*)ff, (double*)Phi, (const double*)u, (const double*)u0, dt, cbar,
                                     (double*)rhou, (double*)r, (double*)rhouf, (const double*)uOld, (const double*)drho, lambda_rho, limiter,
-                                    normal_scheme, uBC, perdir_mask, dirO, report, wait_f, (const double*)f_src, 1);
+                                    normal_scheme, uBC, perdir_mask, dirO, report, wait_f, exitBC, (const double*)f_src, 1);
 }
 
 int ifadv_u2rhou(ifadv_ctx* c, void* stream, void* rhou, const void* u, const void* f, double lr) {
@@ -1163,11 +1166,11 @@ int host_step_pipelined(ifadv_ctx* c, char* fh, const char* uh, char* rh, double
     CU_CHECK(c, cudaMemcpyAsync(u0, u, 3 * Sc, cudaMemcpyDeviceToDevice, hp->s_cmp));
     int rc;
     if ((rc = ifadv_u2rhou_advect_vof_rhouu(h.ctx, hp->s_cmp, f, f0, ff, Phi, u, u, dt, cbar, ru, r, ruf, u, drho, lambda_rho, limiter,
-                                            normal_scheme, uBC, perdir_mask, dirO, nullptr)) < 0) { c->err = h.ctx->err; return rc; }
+                                            normal_scheme, uBC, perdir_mask, 0, dirO, nullptr)) < 0) { c->err = h.ctx->err; return rc; }
     if ((rc = ifadv_axpby(h.ctx, hp->s_cmp, f0, 0.5, f0, 0.5, f))) { c->err = h.ctx->err; return rc; }
     CU_CHECK(c, cudaMemcpyAsync(f0, f, Sc, cudaMemcpyDeviceToDevice, hp->s_cmp));
     if ((rc = ifadv_u2rhou_advect_vof_rhouu(h.ctx, hp->s_cmp, f, f, ff, Phi, u, u, dt, cbar, ru, r, ruf, u0, drho, lambda_rho, limiter,
-                                            normal_scheme, uBC, perdir_mask, dirO, nullptr)) < 0) { c->err = h.ctx->err; return rc; }
+                                            normal_scheme, uBC, perdir_mask, 0, dirO, nullptr)) < 0) { c->err = h.ctx->err; return rc; }
     if (report) CU_CHECK(c, cudaMemcpyAsync(h.ctx->red_host, h.ctx->red_dev, sizeof(unsigned long long) * 24, cudaMemcpyDeviceToHost, hp->s_cmp));
     CU_CHECK(c, cudaEventRecord(h.ev_cmp, hp->s_cmp));
     // D2H of the owned planes
@@ -1273,12 +1276,12 @@ int ifadv_mom_advect_step_host(ifadv_ctx* c, void* f_host, const void* u_host, v
   // predictor: copyto!(f⁰,f); u2ρu!(ρu,u⁰,f⁰); BC!; advectfq!(f⁰; u⁰,u,uOld=u)     flow.jl:61,69-70 (fused entry)
   // (u is passed for both velocity arguments: u⁰≡u here, and one array selects the kernels without the second velocity stream)
   if ((rc = ifadv_u2rhou_advect_vof_rhouu(c, st, f, f0, ff, Phi, u, u, dt, cbar, ru, r, ruf, u, drho, lambda_rho, limiter, normal_scheme,
-                                          uBC, perdir_mask, dirO, nullptr)) < 0) return rc;
+                                          uBC, perdir_mask, 0, dirO, nullptr)) < 0) return rc;
   if ((rc = ifadv_axpby(c, st, f0, 0.5, f0, 0.5, f))) return rc;  // flow.jl:74
   // corrector: copyto!(f⁰,f); u2ρu!(ρu,u⁰,f); BC!; advectfq!(f; u,u,uOld=u⁰)         flow.jl:89-92
   CU_CHECK(c, cudaMemcpyAsync(f0, f, sb, cudaMemcpyDeviceToDevice, st));
   rc = ifadv_u2rhou_advect_vof_rhouu(c, st, f, f, ff, Phi, u, u, dt, cbar, ru, r, ruf, u0, drho, lambda_rho, limiter, normal_scheme, uBC,
-                                     perdir_mask, dirO, report);
+                                     perdir_mask, 0, dirO, report);
   if (rc < 0) return rc;
   CU_CHECK(c, cudaMemcpyAsync(pf ? f_host : c->pin_f, f, sb, cudaMemcpyDeviceToHost, st));
   CU_CHECK(c, cudaMemcpyAsync(pr ? rhou_host : c->pin_ru, ru, vb, cudaMemcpyDeviceToHost, st));

@@ -80,7 +80,7 @@ struct ifadv_ctx {
 
 namespace ifadv {
 template <class T> struct SweepCfg {
-  const T *f_in, *u, *u0, *rhou_in, *uOld, *drho;
+  const T *f_in, *u, *u0, *rhou_in, *uOld, *drho, *uexit;
   T *f_out, *rhou_out, *rhouf;
   int8_t* cbar;
   double dt, lr;

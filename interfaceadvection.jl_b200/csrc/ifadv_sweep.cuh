@@ -46,6 +46,7 @@ template <class T> struct SweepP {
   T* rhou_out;
   const T* uOld;
   const T* drho;
+  const T* uexit;  // exitBC (BC!'s saveexit, flow.jl:197,207): the array whose plane N of component x holds the saved exit value of u★; else null
   T* rhouf_j;  // optional (pure VOF): ρuf[:, j]
   T dt, hdt, idt, lr, omlr, tol, onemtol;
   T A[3];
@@ -177,7 +178,9 @@ IFADV_DI void sweep_tile(const SweepP<T>& P, const int bx, const int by, const i
       if (need) {
         const int vi = (i == 0) ? v0 : ((i == 1) ? v1 : v2);
         const bool peri = (i == 0) ? per0 : ((i == 1) ? per1 : per2);
-        if (!peri && (vi == 1 || vi == 2 || vi == g.n[i])) val = P.A[i];  // Dirichlet planes of BC!
+        if (!peri && i == 0 && vi == g.n[0] && P.uexit != nullptr)  // exitBC: BC! with saveexit keeps plane N of component x
+          val = __ldg(P.uexit + lin3(g, v0, mapc(v1, g.n[1], per1), (D == 3) ? mapc(v2, g.n[2], per2) : 1));
+        else if (!peri && (vi == 1 || vi == 2 || vi == g.n[i])) val = P.A[i];  // Dirichlet planes of BC!
         else {
           v0 = (i == 0) ? (peri ? wrapc(v0, g.n[0]) : v0) : mapc(v0, g.n[0], per0);
           v1 = (i == 1) ? (peri ? wrapc(v1, g.n[1]) : v1) : mapc(v1, g.n[1], per1);
@@ -230,7 +233,7 @@ IFADV_DI void sweep_tile(const SweepP<T>& P, const int bx, const int by, const i
       // BC-aware mass flux (velocity BC! on ρuf, flow.jl:207): Dirichlet planes of component j
       auto Mat = [&](int m0, int m1, int m2) -> T {
         const int pp = ((J == 0) ? o0 + m0 : ((J == 1) ? o1 + m1 : o2 + m2));
-        if (!perJ && (pp == 1 || pp == 2 || pp == nJ)) return P.A[J];
+        if (!perJ && (pp == 1 || pp == 2 || (pp == nJ && !(J == 0 && P.uexit != nullptr)))) return P.A[J];  // exitBC keeps the computed flux of face N
         return sM[TL::fidx(m0, m1, m2)];
       };
 #pragma unroll

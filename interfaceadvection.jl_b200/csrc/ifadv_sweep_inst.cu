@@ -40,7 +40,7 @@ static int launch_sweep_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   P.u = q.u; P.u0 = q.u0;
   P.uj = q.u + (long long)J * c->g.S; P.u0j = q.u0 + (long long)J * c->g.S;
   P.cbar = q.cbar;
-  P.rhou_in = q.rhou_in; P.rhou_out = q.rhou_out; P.uOld = q.uOld; P.drho = q.drho;
+  P.rhou_in = q.rhou_in; P.rhou_out = q.rhou_out; P.uOld = q.uOld; P.drho = q.drho; P.uexit = q.uexit;
   P.rhouf_j = q.rhouf ? q.rhouf + (long long)J * c->g.S : nullptr;
   P.dt = (T)q.dt; P.hdt = P.dt / T(2); P.idt = T(1) / P.dt; P.lr = (T)q.lr; P.omlr = T(1) - P.lr;
   P.tol = T(10) * std::numeric_limits<T>::epsilon(); P.onemtol = T(1) - P.tol;
@@ -72,7 +72,7 @@ template <class T> static void fill_params(ifadv_ctx* c, const SweepCfg<T>& q, i
   P.u = q.u; P.u0 = q.u0;
   P.uj = q.u + (long long)J * c->g.S; P.u0j = q.u0 + (long long)J * c->g.S;
   P.cbar = q.cbar;
-  P.rhou_in = q.rhou_in; P.rhou_out = q.rhou_out; P.uOld = q.uOld; P.drho = q.drho;
+  P.rhou_in = q.rhou_in; P.rhou_out = q.rhou_out; P.uOld = q.uOld; P.drho = q.drho; P.uexit = q.uexit;
   P.rhouf_j = q.rhouf ? q.rhouf + (long long)J * c->g.S : nullptr;
   P.dt = (T)q.dt; P.hdt = P.dt / T(2); P.idt = T(1) / P.dt; P.lr = (T)q.lr; P.omlr = T(1) - P.lr;
   P.tol = T(10) * std::numeric_limits<T>::epsilon(); P.onemtol = T(1) - P.tol;
@@ -302,8 +302,9 @@ template int launch_sweep_dim<IFADV_T, IFADV_D, (IFADV_MOM != 0)>(ifadv_ctx*, cu
 // directional sweeps and the final BCf!, separated by grid-wide barriers.  Small 2-D grids (BASELINE config 1: 128², 16 k cells) are
 // launch-latency bound: five launches of ~13 µs each become one.
 namespace cg = cooperative_groups;
+constexpr int V2_NT = 128, V2_TX = 32, V2_TY = 4;  // small tiles: the step is latency bound, so spread it over as many SMs as there are tiles
 template <class T, int JA, int JB>
-__global__ void __launch_bounds__(256) vof2d_step_kernel(const SweepP<T> PA, const SweepP<T> PB, T* f_final, T* rhouf, const long long nruf,
+__global__ void __launch_bounds__(V2_NT) vof2d_step_kernel(const SweepP<T> PA, const SweepP<T> PB, T* f_final, T* rhouf, const long long nruf,
                                                           unsigned long long* red, const unsigned per) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cg::grid_group grid = cg::this_grid();
@@ -319,10 +320,10 @@ __global__ void __launch_bounds__(256) vof2d_step_kernel(const SweepP<T> PA, con
   grid.sync();
   auto sweep = [&](auto ja, const SweepP<T>& P) {
     constexpr int J = decltype(ja)::value;
-    constexpr int TX = (J == 0) ? 64 : 32, TY = (J == 0) ? 8 : 16;
+    constexpr int TX = V2_TX, TY = V2_TY;
     const int gx = (g.n[0] - 2 + TX - 1) / TX, gy = (g.n[1] - 2 + TY - 1) / TY;
     for (int t = blockIdx.x; t < gx * gy; t += gridDim.x) {
-      sweep_tile<T, 2, J, TX, TY, 1, false, 256>(P, t % gx, t / gx, 0, smem_raw);
+      sweep_tile<T, 2, J, TX, TY, 1, false, V2_NT>(P, t % gx, t / gx, 0, smem_raw);
       __syncthreads();  // the next tile reuses the shared planes
     }
   };
@@ -345,21 +346,21 @@ template <class T> int launch_vof2d_step(ifadv_ctx* c, cudaStream_t st, const Sw
   SweepP<T> PA, PB;
   fill_params<T>(c, qa, qa.j, PA);
   fill_params<T>(c, qb, qb.j, PB);
-  const size_t smem = std::max(Tile<2, 0, 64, 8, 1>::template smem_bytes<T>(false), Tile<2, 1, 32, 16, 1>::template smem_bytes<T>(false));
+  const size_t smem = std::max(Tile<2, 0, V2_TX, V2_TY, 1>::template smem_bytes<T>(false), Tile<2, 1, V2_TX, V2_TY, 1>::template smem_bytes<T>(false));
   void* kern = (qa.j == 0) ? (void*)vof2d_step_kernel<T, 0, 1> : (void*)vof2d_step_kernel<T, 1, 0>;
   int per_sm = 0, sms = 0;
   CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CU_CHECK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+  CU_CHECK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, V2_NT, smem));
   CU_CHECK(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
   const int nx = c->g.n[0] - 2, ny = c->g.n[1] - 2;
-  const int tiles = std::max(((nx + 63) / 64) * ((ny + 7) / 8), ((nx + 31) / 32) * ((ny + 15) / 16));
+  const int tiles = ((nx + V2_TX - 1) / V2_TX) * ((ny + V2_TY - 1) / V2_TY);
   const int grid = std::max(1, std::min(tiles, per_sm * sms));
   T* ruf = rhouf;
   long long nruf = (long long)c->g.S * 2;
   unsigned long long* red = c->red_dev;
   unsigned per = c->g.per;
   void* args[] = {&PA, &PB, &f_final, &ruf, &nruf, &red, &per};
-  CU_CHECK(c, cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(256), args, smem, st));
+  CU_CHECK(c, cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(V2_NT), args, smem, st));
   c->launches++;
   return 0;
 }

@@ -99,7 +99,7 @@ IFADV_DI void xrow_body(const SweepP<T>& P, const int chunk, unsigned char* smem
     if (EDGE) {
       xm[c] = (unsigned)(mapc(v, nA, perA) - 1);
       xs[c] = (unsigned)((perA ? wrapc(v, nA) : min(max(v, 1), nA)) - 1);
-      flg[c] = WALL ? xflags(v, nA, perA) : (unsigned)XF_NEEDM;
+      flg[c] = WALL ? xflags(v, nA, perA, P.uexit != nullptr) : (unsigned)XF_NEEDM;
       okc[c] = lane >= 1 && lane <= 30 && v >= 2 && v <= nA - 1;
     } else {
       xm[c] = xs[c] = (unsigned)(v - 1);
@@ -283,7 +283,8 @@ IFADV_DI void xrow_body(const SweepP<T>& P, const int chunk, unsigned char* smem
             o[j][2] = ldg2(P.uOld + (ob + cC + xm[0]));
           }
         } else {
-          q[j][0].x = __ldg(rsrc + (ob + xs[0])); q[j][0].y = __ldg(rsrc + (ob + xs[1]));
+          // exitBC: the cell at plane nA takes the saved exit value of u★ (component x) instead of ρu/ρ
+          q[j][0].x = __ldg(((flg[0] & XF_EXIT) ? P.uexit : rsrc) + (ob + xs[0])); q[j][0].y = __ldg(((flg[1] & XF_EXIT) ? P.uexit : rsrc) + (ob + xs[1]));
           q[j][1].x = __ldg(rsrc + (ob + cB + xm[0])); q[j][1].y = __ldg(rsrc + (ob + cB + xm[1]));
           q[j][2].x = __ldg(rsrc + (ob + cC + xm[0])); q[j][2].y = __ldg(rsrc + (ob + cC + xm[1]));
           if (!FUSED) {
@@ -380,7 +381,7 @@ IFADV_DI void xrow_body(const SweepP<T>& P, const int chunk, unsigned char* smem
         const T ra = t_div(FUSED ? qa * h[c][0] : qa, h[c][0]);
         const T rb = t_div(FUSED ? qb * h[c][1] : qb, h[c][1]);
         const T rc = t_div(FUSED ? qc * h[c][2] : qc, h[c][2]);
-        us[c][0] = (EDGE && (flg[c] & XF_DIRA)) ? AA : ra;  // Dirichlet planes of BC!
+        us[c][0] = (EDGE && (flg[c] & XF_DIRA)) ? AA : ((EDGE && (flg[c] & XF_EXIT)) ? qa : ra);  // Dirichlet planes of BC! / saved exit plane
         us[c][1] = dirB[j] ? AB : rb;
         us[c][2] = dirC ? AC : rc;
       }

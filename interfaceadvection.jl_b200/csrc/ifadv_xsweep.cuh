@@ -41,13 +41,15 @@ enum : unsigned {
   XH_DIL = 1u << 10,   // dilation (column -1; row -1)
   XH_FL = 1u << 11,    // SynDRoM flux of the face x+32
   XH_DIRB = 1u << 12,  // Dirichlet plane of component y at this row
+  XF_EXIT = 1u << 13,  // exitBC: plane nA of component x keeps its saved value (BC! with saveexit) and the face nA its computed mass flux
 };
 
-IFADV_DI unsigned xflags(int va, int nA, bool perA) {
+IFADV_DI unsigned xflags(int va, int nA, bool perA, bool exitbc = false) {
   unsigned f = 0;
   if (va <= nA && (perA || va >= 2)) f |= XF_NEEDM;
   if (!perA) {
-    if (va == 1 || va == 2 || va == nA) f |= XF_DIRA;
+    if (va == 1 || va == 2 || (va == nA && !exitbc)) f |= XF_DIRA;
+    if (va == nA && exitbc) f |= XF_EXIT;
     if (va - 1 == 1 || va - 1 == 2 || va - 1 == nA) f |= XF_DIRAM;
     if (va == 1) f |= XF_DILSH;
     if (va == 2) f |= XF_LVAR;
@@ -95,7 +97,7 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
 
   // ---- per-thread constants: own cells (one column, CPT rows) and (for the first NH threads) one halo entry --------------------
   const int vx = ox + tx;
-  const unsigned cflg = XB ? xflags(vx, nA, perA) : XF_NEEDM;
+  const unsigned cflg = XB ? xflags(vx, nA, perA, P.uexit != nullptr) : XF_NEEDM;
   const int e0 = (tx + 3) + WX * (ty + 2);  // shared entry of cell 0; cell j adds j*TR*WX
   // x as stored minus x mapped: non-zero only in a ghost column (the thread at va = nA evaluates the boundary face from u_x[nA])
   const unsigned gox = XB ? (unsigned)((perA ? wrapc(vx, nA) : min(max(vx, 1), nA)) - mapc(vx, nA, perA)) : 0u;
@@ -128,7 +130,7 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
     const unsigned yo = (unsigned)(mapc(vb, nB, perB) - 1) * s1;
     ghm = (unsigned)(mapc(va, nA, perA) - 1) + yo;
     gho = (unsigned)((perA ? wrapc(va, nA) : min(max(va, 1), nA)) - 1) + yo;  // x as stored (component x, u_x faces)
-    if (XB) hflg |= xflags(va, nA, perA); else hflg |= XF_NEEDM;
+    if (XB) hflg |= xflags(va, nA, perA, P.uexit != nullptr); else hflg |= XF_NEEDM;
     if (!perB && (vb == 2 || vb == nB)) hflg |= XH_DIRB;
   }
   const bool hUS = (hflg & XH_US) != 0, hM = (hflg & XH_M) != 0, hDIL = (hflg & XH_DIL) != 0, hFL = (hflg & XH_FL) != 0;
@@ -150,7 +152,7 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
       cp_async_s(se0 + dF + j * JS, P.f_in + gmv);
       cp_async_s(se0 + dU + j * JS, P.u + (gmv + gox));
       if (!SAMEU) cp_async_s(se0 + dU0 + j * JS, P.u0 + (gmv + gox));
-      cp_async_s(se0 + dR + j * JS, rsrc + (gmv + gox));
+      cp_async_s(se0 + dR + j * JS, ((XB && (cflg & XF_EXIT)) ? P.uexit : rsrc) + (gmv + gox));  // exitBC: saved exit value of u★
       cp_async_s(se0 + dR + PL * SZ + j * JS, rsrc + (gmv + cB));
       cp_async_s(se0 + dR + 2 * PL * SZ + j * JS, rsrc + (gm[j] + cC + pov));
     }
@@ -161,7 +163,7 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
         if (!SAMEU) cp_async_s(seh + dU0, P.u0 + (gho + pmv));
       }
       if (hUS) {
-        cp_async_s(seh + dR, rsrc + (gho + pmv));
+        cp_async_s(seh + dR, ((XB && (hflg & XF_EXIT)) ? P.uexit : rsrc) + (gho + pmv));
         cp_async_s(seh + dR + PL * SZ, rsrc + (ghm + cB + pmv));
         cp_async_s(seh + dR + 2 * PL * SZ, rsrc + (ghm + cC + pov));
       }
@@ -352,7 +354,7 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
       const T ra = t_div(FUSED ? qa2 * h2[0][j] : qa2, h2[0][j]);
       const T rb = t_div(FUSED ? qb2 * h2[1][j] : qb2, h2[1][j]);
       const T rc = t_div(FUSED ? qc2 * h2[2][j] : qc2, h2[2][j]);
-      us2[0][j] = (XB && (cflg & XF_DIRA)) ? AA : ra;  // Dirichlet planes of BC!
+      us2[0][j] = (XB && (cflg & XF_DIRA)) ? AA : ((XB && (cflg & XF_EXIT)) ? qa2 : ra);  // Dirichlet planes of BC! / saved exit plane
       us2[1][j] = dirB[j] ? AB : rb;
       us2[2][j] = dirC2 ? AC : rc;
 #pragma unroll
@@ -373,7 +375,7 @@ IFADV_DI void xsweep_body(const SweepP<T>& P, const int chunk, T* sm) {
         const T ha = rho_face(fh, fhxm, lr, omlr), hb = rho_face(fh, sm[qF2 + eh - WX], lr, omlr), hc = rho_face(fh, sm[qF1 + eh], lr, omlr);
         const T a = sm[qR + eh], b = sm[qR + PL + eh], c = sm[qR + 2 * PL + eh];
         const T ra = t_div(FUSED ? a * ha : a, ha), rb = t_div(FUSED ? b * hb : b, hb), rc = t_div(FUSED ? c * hc : c, hc);
-        sm[wUS + eh] = (XB && (hflg & XF_DIRA)) ? AA : ra;
+        sm[wUS + eh] = (XB && (hflg & XF_DIRA)) ? AA : ((XB && (hflg & XF_EXIT)) ? a : ra);
         sm[wUS + PL + eh] = (hflg & XH_DIRB) ? AB : rb;
         sm[wUS + 2 * PL + eh] = dirC2 ? AC : rc;
       }

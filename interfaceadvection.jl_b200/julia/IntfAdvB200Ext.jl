@@ -149,7 +149,6 @@ end
 # Each of the two groups `copyto!(f⁰,f); u2ρu!(ρu,u⁰,·); BC!(ρu); advectfq!(…)` (flow.jl:61,69-70 and :89-92) becomes ONE call of
 # ifadv_u2rhou_advect_vof_rhouu (bit-identical to the separate calls, include/ifadv.h); forcing and projection stay WaterLily's.
 function fused_group!(a::Flow{D,T}, c::cVOF, fsrc, f, u¹, u², uOld, δt) where {D,T}
-    a.exitBC && error("IntfAdvB200Ext: exitBC=true is not supported (DESIGN.md §5)")
     a.uBC isa Function && error("IntfAdvB200Ext: function-valued uBC is not supported (no fallback)")
     ctx = context(f)
     dirv = Cint[ntuple(i -> mod(length(a.Δt) + i, D) + 1, D)...; zeros(Cint, 3 - D)]   # flow.jl:163
@@ -158,11 +157,11 @@ function fused_group!(a::Flow{D,T}, c::cVOF, fsrc, f, u¹, u², uOld, δt) where
     want = (CALLS[] += 1) % CHECK_EVERY[] == 0
     rc = ccall((:ifadv_u2rhou_advect_vof_rhouu, LIB), Cint,
                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid},
-                Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Cint, Ptr{Cdouble}, Cuint, Ptr{Cint},
+                Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Cint, Ptr{Cdouble}, Cuint, Cint, Ptr{Cint},
                 Ptr{IfadvReport}),
                ctx, stream_ptr(), dptr(fsrc), dptr(f), dptr(c.fᶠ), dptr(a.σ), dptr(u¹), dptr(u²), δt, dptr(c.c̄),
                dptr(c.ρu), dptr(a.f), dptr(c.ρuf), dptr(uOld), dptr(c.dρ), c.λρ, limiter_enum(a.λ), normal_enum(c.normalScheme),
-               A, perdir_mask(a.perdir), dirv, want ? rep : C_NULL)
+               A, perdir_mask(a.perdir), Cint(a.exitBC), dirv, want ? rep : C_NULL)
     report(check(ctx, rc), rep[])
     nothing
 end

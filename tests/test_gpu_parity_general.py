@@ -406,3 +406,80 @@ def test_rejected_calls_leave_the_context_clean(ia):
     torch.cuda.synchronize()
     assert ia.advectVOFrhouu(fd, d["ff"], d["alpha"], d["nhat"], ud, ud, 1.0, d["cbar"], d["rhou"], d["r"], d["Phi"], d["rhouf"], d["nhat"], ud,
                              d["alpha"], d["drho"], 1e-3, "Koren", "WH", (0, 0, 0), (), False, (3, 1, 2)) == 0
+
+
+# ---- exitBC = true (BC!'s saveexit, flow.jl:197,207) -----------------------------------------------------------------------------
+def _exit_case(N, kind, T, perdir):
+    """Inflow uBC[1] through x = 1, 2 and a free exit plane x = N: u[N,·,1] differs from uBC, the caller's r array holds an arbitrary
+    'saved' exit value of u★ on plane N of component 1 and garbage everywhere else (only that plane may be read)."""
+    D = len(N)
+    uBC = (0.2,) + (0.0,) * (D - 1)
+    st = make_state(N, kind, T, perdir=perdir, uBC=uBC, scale_u=0.5)
+    rng = np.random.default_rng(20261018)
+    u = st["u"]
+    u[-1, ..., 0] = (0.2 + 0.05 * rng.standard_normal(u[-1, ..., 0].shape)).astype(T)  # exit plane: outflow, not the Dirichlet value
+    O.BC(u, uBC, True, perdir)
+    a = alloc_cmom(st)
+    a["r"][...] = rng.standard_normal(a["r"].shape).astype(T)
+    a["r"][-1, ..., 0] = (0.2 + 0.05 * rng.standard_normal(a["r"][-1, ..., 0].shape)).astype(T)
+    O.u2rhou(a["rhou"], u, st["f"], st["lam_rho"]); O.BC(a["rhou"], uBC, True, perdir)
+    return st, a
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("N,kind,perdir", [((24, 16), "C1", (2,)), ((20, 12), "C3", ()), ((24, 14, 10), "C2", (2, 3)), ((70, 12, 9), "C3", ())])
+def test_cmom_exit_bc_matches_oracle(ia, T, N, kind, perdir):
+    """advectVOFρuu! with exitBC=true.  The reference never defines plane N of component 1 of u★: BC! with saveexit keeps whatever
+    r[N,·,1] holds (flow.jl:197) -- the caller's value in the first sweep, flux residue of the previous advectρuu1D! afterwards.  The B200
+    path reads the caller's value in every sweep, so it equals the oracle bit for bit (f64) when x is swept first, and
+    everywhere except the last interior x-plane of ρu[:,1] for the other orders.  The exit face keeps its computed mass flux."""
+    D = len(N)
+    orders = [(1, 2), (2, 1)] if D == 2 else [(1, 2, 3), (3, 1, 2), (2, 3, 1)]
+    for dirO in orders:
+        st, a = _exit_case(N, kind, T, perdir)
+        ao = {k: v.copy(order="F") for k, v in a.items()}
+        f_o = st["f"].copy(order="F")
+        so, rep = O.advectVOFrhouu(f_o, ao["ff"], ao["alpha"], ao["nhat"], st["u"], st["u"], 1.0, ao["cbar"], ao["rhou"], ao["r"], ao["Phi"],
+                                   ao["rhouf"], ao["nhat"], st["u"], ao["alpha"], ao["drho"], st["lam_rho"], "Koren", "WH", st["uBC"], perdir,
+                                   True, dirO)
+        d = _dev(ia, a)
+        fd, ud = ia.from_numpy(st["f"]), ia.from_numpy(st["u"])
+        sc = ia.advectVOFrhouu(fd, d["ff"], d["alpha"], d["nhat"], ud, ud, 1.0, d["cbar"], d["rhou"], d["r"], d["Phi"], d["rhouf"], d["nhat"],
+                               ud, d["alpha"], d["drho"], st["lam_rho"], "Koren", "WH", st["uBC"], perdir, True, dirO)
+        assert sc == so
+        assert np.abs(ia.to_numpy(fd) - f_o).max() <= TOL[T], dirO
+        ru_c, ru_o = inside(ia.to_numpy(d["rhou"]), D), inside(ao["rhou"], D)
+        err = np.abs(ru_c - ru_o)
+        if dirO[0] != 1:
+            err[-1, ..., 0] = 0  # the reference's u★[N,·,1] is unspecified scratch there (see the docstring)
+        scale = max(1.0, np.abs(ru_o).max())
+        assert err.max() <= TOL[T] * scale, (dirO, err.max(), np.unravel_index(err.argmax(), err.shape))
+        # the exit really is free: the result differs from the Dirichlet treatment of plane N
+        if dirO[0] == 1:
+            st2, a2 = _exit_case(N, kind, T, perdir)
+            d2 = _dev(ia, a2)
+            fd2 = ia.from_numpy(st2["f"])
+            ia.advectVOFrhouu(fd2, d2["ff"], d2["alpha"], d2["nhat"], ud, ud, 1.0, d2["cbar"], d2["rhou"], d2["r"], d2["Phi"], d2["rhouf"],
+                              d2["nhat"], ud, d2["alpha"], d2["drho"], st["lam_rho"], "Koren", "WH", st["uBC"], perdir, False, dirO)
+            assert np.abs(inside(ia.to_numpy(d2["rhou"]), D)[-1, ..., 0] - ru_c[-1, ..., 0]).max() > 1e-4
+
+
+def test_exit_bc_through_the_fused_entry_and_the_mirror(ia):
+    """The fused entry (u2ρu! + BC!(…, exitBC) + advectVOFρuu!) equals the three separate calls with exitBC=true (Float64: bit for bit)."""
+    T, N, perdir = np.float64, (70, 12, 9), ()
+    st, a = _exit_case(N, "C3", T, perdir)
+    dirO = (1, 2, 3)
+    d = _dev(ia, a)
+    fd, ud = ia.from_numpy(st["f"]), ia.from_numpy(st["u"])
+    ia.advectVOFrhouu(fd, d["ff"], d["alpha"], d["nhat"], ud, ud, 1.0, d["cbar"], d["rhou"], d["r"], d["Phi"], d["rhouf"], d["nhat"], ud,
+                      d["alpha"], d["drho"], st["lam_rho"], "Koren", "WH", st["uBC"], perdir, True, dirO)
+    st2, a2 = _exit_case(N, "C3", T, perdir)
+    d2 = _dev(ia, a2)
+    f2, u2 = ia.from_numpy(st2["f"]), ia.from_numpy(st2["u"])
+    ctx = ia.context_for(f2)
+    p = lambda t: t.data_ptr()
+    ctx.u2rhou_advect_vof_rhouu(0, p(f2), p(f2), p(d2["ff"]), p(d2["Phi"]), p(u2), p(u2), 1.0, p(d2["cbar"]), p(d2["rhou"]), p(d2["r"]),
+                                p(d2["rhouf"]), p(u2), p(d2["drho"]), st["lam_rho"], 2, 0, st["uBC"], perdir, True, dirO)
+    torch.cuda.synchronize()
+    assert np.array_equal(ia.to_numpy(f2), ia.to_numpy(fd))
+    assert np.array_equal(inside(ia.to_numpy(d2["rhou"]), 3), inside(ia.to_numpy(d["rhou"]), 3))
