@@ -5,6 +5,7 @@
 // dtype: 0 = Float32, 1 = Float64.  Directions, sweep order (dirO) and cell indices are 1-based as in
 // the Julia reference; perdir is a bit mask (bit j-1 set <=> j ∈ perdir).
 #include "oracle_flow.hpp"
+#include "oracle_forcing.hpp"
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -206,6 +207,54 @@ int orc_sum_inside(int dtype, int D, const int64_t* Ng, const void* f, double* o
         for (int64_t i = r.lo[0]; i <= r.hi[0]; ++i) s += (double)p[lin(g, I3{{i, j, k}})];
   });
   *out = s;
+  return 0;
+}
+
+// ---- explicit forcing: src/flow.jl:113-153,244-259, src/VOFutil.jl:186-191, src/surfaceTension.jl ----------------
+// getμ(i,j,I,fFace,λμ,μ,λρ); i, j, I 1-based
+int orc_getmu(int dtype, int D, const int64_t* Ng, void* fFace, int i, int j, const int64_t* I, double lmu, double mu, double lr, double* out) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, { *out = (double)getmu<T>(i - 1, j - 1, mkI(D, I), VF<T>{(T*)fFace, &g}, (T)lmu, (T)mu, (T)lr); });
+  return 0;
+}
+// getPopinetHeight(I,f,i) / getCurvature(I,f,i); i: signed 1-based direction
+int orc_popinet_height(int dtype, int D, const int64_t* Ng, void* f, const int64_t* I, int i, double* out) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, { *out = (double)getPopinetHeight<T>(g, mkI(D, I), SF<T>{(T*)f, &g}, i); });
+  return 0;
+}
+int orc_curvature(int dtype, int D, const int64_t* Ng, void* f, const int64_t* I, int i, double* out) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, { *out = (double)getCurvature<T>(g, mkI(D, I), SF<T>{(T*)f, &g}, i); });
+  return 0;
+}
+// viscSurfTenρu!(r,u,Φ,f,α,n̂,fbuffer,λμ,μ,λρ,η;perdir); has_mu / has_eta = 0 stand for `nothing`
+int orc_visc_surften_rhou(int dtype, int D, const int64_t* Ng, void* r, void* u, void* Phi, void* f, void* alpha, void* nhat, void* fbuffer,
+                          double lmu, double mu, int has_mu, double lr, double eta, int has_eta, unsigned perdir) {
+  (void)alpha;
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, {
+    viscSurfTenRhou<T>(g, VF<T>{(T*)r, &g}, VF<T>{(T*)u, &g}, SF<T>{(T*)Phi, &g}, SF<T>{(T*)f, &g}, VF<T>{(T*)nhat, &g}, SF<T>{(T*)fbuffer, &g},
+                       (T)lmu, (T)mu, has_mu != 0, (T)lr, (T)eta, has_eta != 0, perdir);
+  });
+  return 0;
+}
+// updateU!(u,ρu,ρu⁰,forcing,dt,f,λρ,tNow,g,uBC,w) with a constant gravity vector (grav == NULL: g = nothing)
+int orc_update_u(int dtype, int D, const int64_t* Ng, void* u, void* rhou, void* rhou0, void* forcing, double dt, void* f, double lr,
+                 const double* grav, double w) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, {
+    T gg[3] = {0, 0, 0};
+    if (grav) for (int i = 0; i < D; ++i) gg[i] = (T)grav[i];
+    updateU<T>(g, VF<T>{(T*)u, &g}, VF<T>{(T*)rhou, &g}, VF<T>{(T*)rhou0, &g}, VF<T>{(T*)forcing, &g}, (T)dt, SF<T>{(T*)f, &g}, (T)lr,
+               grav ? gg : nullptr, (T)w);
+  });
+  return 0;
+}
+// updateL!(μ₀,f,λρ;perdir)
+int orc_update_l(int dtype, int D, const int64_t* Ng, void* mu0, void* f, double lr, unsigned perdir) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, { updateL<T>(g, VF<T>{(T*)mu0, &g}, SF<T>{(T*)f, &g}, (T)lr, perdir); });
   return 0;
 }
 

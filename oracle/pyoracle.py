@@ -28,7 +28,7 @@ def build(force: bool = False) -> None:
     """Compile liboracle.so / liboracle_omp.so with the committed Makefile (g++ only, a few seconds)."""
     need = force or not all(os.path.exists(os.path.join(_HERE, n)) for n in ("liboracle.so", "liboracle_omp.so"))
     if not need:
-        srcs = [os.path.join(_HERE, n) for n in ("oracle.cpp", "oracle_core.hpp", "oracle_fields.hpp", "oracle_flow.hpp")]
+        srcs = [os.path.join(_HERE, n) for n in ("oracle.cpp", "oracle_core.hpp", "oracle_fields.hpp", "oracle_flow.hpp", "oracle_forcing.hpp")]
         newest = max(os.path.getmtime(s) for s in srcs)
         need = any(os.path.getmtime(os.path.join(_HERE, n)) < newest for n in ("liboracle.so", "liboracle_omp.so"))
     if need:
@@ -250,6 +250,55 @@ def sum_inside(f) -> float:
     out = C.c_double()
     lib().orc_sum_inside(_dt(f), D, ng, _p(f), C.byref(out))
     return out.value
+
+
+# ---- explicit forcing -------------------------------------------------------------------------------------------
+def getmu(i, j, I, fFace, lam_mu, mu, lam_rho) -> float:
+    """getμ(i,j,I,fFace,λμ,μ,λρ) (VOFutil.jl:186-191); i, j, I 1-based."""
+    D = fFace.ndim - 1
+    ng = (C.c_int64 * 3)(*(list(fFace.shape[:D]) + [1] * (3 - D)))
+    out = C.c_double()
+    lib().orc_getmu(_dt(fFace), D, ng, _p(fFace), int(i), int(j), _i3(I), C.c_double(lam_mu), C.c_double(mu), C.c_double(lam_rho),
+                    C.byref(out))
+    return out.value
+
+
+def getPopinetHeight(I, f, i) -> float:
+    """getPopinetHeight(I,f,i) (surfaceTension.jl:67-99); i: signed 1-based direction."""
+    D, ng = _ng(f)
+    out = C.c_double()
+    lib().orc_popinet_height(_dt(f), D, ng, _p(f), _i3(I), int(i), C.byref(out))
+    return out.value
+
+
+def getCurvature(I, f, i) -> float:
+    """getCurvature(I,f,i) (surfaceTension.jl:31-65)."""
+    D, ng = _ng(f)
+    out = C.c_double()
+    lib().orc_curvature(_dt(f), D, ng, _p(f), _i3(I), int(i), C.byref(out))
+    return out.value
+
+
+def viscSurfTenrhou(r, u, Phi, f, alpha, nhat, fbuffer, lam_mu, mu, lam_rho, eta, perdir=(), omp=False):
+    """viscSurfTenρu!(r,u,Φ,f,α,n̂,fbuffer,λμ,μ,λρ,η;perdir) (flow.jl:113-117); mu / eta = None stand for `nothing`."""
+    D, ng = _ng(f)
+    lib(omp).orc_visc_surften_rhou(_dt(f), D, ng, _p(r), _p(u), _p(Phi), _p(f), _p(alpha), _p(nhat), _p(fbuffer), C.c_double(lam_mu),
+                                   C.c_double(0.0 if mu is None else mu), int(mu is not None), C.c_double(lam_rho),
+                                   C.c_double(0.0 if eta is None else eta), int(eta is not None), mask(perdir))
+
+
+def updateU(u, rhou, rhou0, forcing, dt, f, lam_rho, g=None, w=1.0, omp=False):
+    """updateU!(u,ρu,ρu⁰,forcing,dt,f,λρ,tNow,g,uBC,w) (flow.jl:244-252) with a constant gravity vector g (None = nothing)."""
+    D, ng = _ng(f)
+    gv = None if g is None else (C.c_double * 3)(*(list(map(float, g))[:D] + [0.0] * (3 - D)))
+    lib(omp).orc_update_u(_dt(f), D, ng, _p(u), _p(rhou), _p(rhou0), _p(forcing), C.c_double(dt), _p(f), C.c_double(lam_rho), gv,
+                          C.c_double(w))
+
+
+def updateL(mu0, f, lam_rho, perdir=(), omp=False):
+    """updateL!(μ₀,f,λρ;perdir) (flow.jl:254-259)."""
+    D, ng = _ng(f)
+    lib(omp).orc_update_l(_dt(f), D, ng, _p(mu0), _p(f), C.c_double(lam_rho), mask(perdir))
 
 
 def num_threads(omp=True) -> int:
