@@ -138,6 +138,25 @@ int ifadv_sum_inside(ifadv_ctx* ctx, void* stream, const void* f, double* out);
 int ifadv_apply_vof_samples(ifadv_ctx* ctx, void* stream, void* f, void* alpha, void* nhat, const void* sc, const void* sp,
                             const void* sm);
 
+/* ---- explicit forcing between advection and projection (single-GPU contexts) ----------------------------
+ * viscSurfTenρu!(r,u,Φ,f,α,n̂,fbuffer,λμ,μ,λρ,η;perdir)                          src/flow.jl:113-117
+ *   = fill!(r,0); visc! (flow.jl:120-152, getμ VOFutil.jl:186-191); surfTen! (src/surfaceTension.jl:8-101: staggered f̄ = ϕ(d,·,f),
+ *   Weymouth-Yue normal, Popinet column heights, height-function curvature).  Out: r on inside(f) (the reference also accumulates
+ *   into upper ghost entries nothing reads).  mu <= 0 / eta <= 0 stand for `nothing`.  f, u carry valid ghosts.  Φ, α are unused;
+ *   n̂ is only READ: plane N_d of component d, which f2face!+BCv! never write in a non-periodic direction (the reference reads it as
+ *   left by BC! on u★≡n̂ in the previous advectfq!, i.e. uBC[d]); fbuffer is rewritten for every d exactly like the reference
+ *   (plane N_d of a non-periodic d keeps the caller's values: BCf!(d,·) skips it). */
+int ifadv_visc_surften_rhou(ifadv_ctx* ctx, void* stream, void* r, const void* u, void* Phi, const void* f, void* alpha, void* nhat,
+                            void* fbuffer, double lambda_mu, double mu, double lambda_rho, double eta, unsigned perdir_mask);
+/* updateU!(u,ρu,ρu⁰,forcing,dt,f,λρ,tNow,g,uBC,w)                                  src/flow.jl:244-252
+ *   ρu ← (a ρu⁰ + ρu + forcing·dt)·w with a = 1/w - 1 (ALL entries); u ← ρu/ρ(f̄) on inside(f); forcing ← g; u ← u + dt·w·g.
+ *   g: constant gravity vector (accelerate! with g(i,x,t) = g[i]) or NULL (`nothing`; time-dependent uBC is not supported). */
+int ifadv_update_u(ifadv_ctx* ctx, void* stream, void* u, void* rhou, const void* rhou0, void* forcing, double dt, const void* f,
+                   double lambda_rho, const double g[3], double w);
+/* updateL!(μ₀,f,λρ;perdir): μ₀[I,d] /= ρ(f̄) on inside(f); BC!(μ₀,0,false,perdir)     src/flow.jl:254-259
+ *   fill_one != 0 folds the fill!(a.μ₀,1) that precedes it in MPFMomStep! (flow.jl:73,96) into the same pass. */
+int ifadv_update_l(ifadv_ctx* ctx, void* stream, void* mu0, const void* f, double lambda_rho, unsigned perdir_mask, int fill_one);
+
 /* Stream overlap aid for MPFMomStep! (src/flow.jl:74,89): the midpoint f⁰=(f⁰+f)/2 and the copy f⁰<-f only READ the f that the
  * corrector's advectfq! is about to advance, and that call does not write f before its last directional sweep.  A caller that
  * runs those two field operations on a second stream records an event behind them and passes it here; the NEXT

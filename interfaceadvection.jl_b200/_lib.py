@@ -61,6 +61,9 @@ def lib():
         L.ifadv_mom_advect_step_host.argtypes = [vp, vp, vp, vp, dbl, dbl, i32, i32, dblp, u32, i32p, rep]
         L.ifadv_host_step_bytes.argtypes = [vp, i64p, i64p, i32p]
         L.ifadv_defer_f_writes_until.argtypes = [vp, vp]
+        L.ifadv_visc_surften_rhou.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, dbl, dbl, dbl, u32]
+        L.ifadv_update_u.argtypes = [vp, vp, vp, vp, vp, vp, dbl, vp, dbl, dblp, dbl]
+        L.ifadv_update_l.argtypes = [vp, vp, vp, vp, dbl, u32, i32]
         L.ifadv_check_nan.argtypes = [vp, vp]
         L.ifadv_create_slab.argtypes = [C.POINTER(vp), i64p, i32, i32, vp, i32, i32, i32, i32]
         L.ifadv_slab_info.argtypes = [vp, i32p, i32p, i32p, i32p, i64p]
@@ -209,6 +212,18 @@ class Context:
 
     def apply_vof_samples(self, stream, f, alpha, nhat, sc, sp, sm):
         return self._chk(lib().ifadv_apply_vof_samples(self._h, stream, f, alpha, nhat, sc, sp, sm))
+
+    def visc_surften_rhou(self, stream, r, u, Phi, f, alpha, nhat, fbuffer, lam_mu, mu, lam_rho, eta, perdir):
+        """viscSurfTenρu! (ifadv_visc_surften_rhou); mu / eta None or 0 stand for `nothing`."""
+        return self._chk(lib().ifadv_visc_surften_rhou(self._h, stream, r, u, Phi, f, alpha, nhat, fbuffer, float(lam_mu), float(mu or 0.0),
+                                                       float(lam_rho), float(eta or 0.0), perdir_mask(perdir)))
+
+    def update_u(self, stream, u, rhou, rhou0, forcing, dt, f, lam_rho, g=None, w=1.0):
+        gv = None if g is None else _d3(g, self.D)
+        return self._chk(lib().ifadv_update_u(self._h, stream, u, rhou, rhou0, forcing, float(dt), f, float(lam_rho), gv, float(w)))
+
+    def update_l(self, stream, mu0, f, lam_rho, perdir, fill_one=False):
+        return self._chk(lib().ifadv_update_l(self._h, stream, mu0, f, float(lam_rho), perdir_mask(perdir), int(bool(fill_one))))
 
     def defer_f_writes_until(self, event):
         """One-shot: the next CMOM advect call waits for `event` (cudaEvent_t handle) before its first write to f."""

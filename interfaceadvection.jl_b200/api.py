@@ -220,6 +220,8 @@ class Flow:
         self.u0 = self.u.clone(memory_format=torch.preserve_format)
         self.f = jl_zeros(Ng + (D,), T, device)
         self.sigma = jl_zeros(Ng, T, device)
+        self.mu0 = jl_zeros(Ng + (D,), T, device)  # μ₀: the projection's face coefficients (updateL!, flow.jl:254-259)
+        self.mu0.fill_(1)
         self.dt = [float(dt)]  # Δt
         self.nu, self.g = nu, g
 
@@ -310,7 +312,7 @@ def MPCFL(a: Flow, c: cVOF, dt_max=1.0, safety=0.8) -> float:
     """MPCFL(a,c)  (src/flow.jl:262-281)"""
     gnorm = 0.0
     if a.g is not None:
-        gnorm = math.sqrt(sum(float(a.g(i + 1, [0.0] * a.D, sum(a.dt))) ** 2 for i in range(a.D)))
+        gnorm = math.sqrt(sum(x * x for x in _gvec(a.g, a.D, sum(a.dt))))
     return context_for(c.f).mpcfl(_stream(c.f), _p(a.u), nu=a.nu, mu=c.mu or 0.0, lam_mu=c.lam_mu, lam_rho=c.lam_rho, eta=c.eta or 0.0,
                                   gnorm=gnorm, dt_max=dt_max, safety=safety)
 
@@ -388,23 +390,101 @@ def mom_advect_step(a: Flow, c: cVOF, dt=None, project: Optional[Callable] = Non
         ctx.exchange_planes(s, _p(a.u), a.D, a.u.element_size())
 
 
-def MPFMomStep(a: Flow, b, c: cVOF, d=None, dt=None, project: Optional[Callable] = None, check=False):
+# ---- explicit forcing between advection and projection ---------------------------------------------------------
+def viscSurfTenrhou(r, u, Phi, f, alpha, nhat, fbuffer, lam_mu, mu, lam_rho, eta, perdir=()):
+    """viscSurfTenρu!(r,u,Φ,f,α,n̂,fbuffer,λμ,μ,λρ,η;perdir)  (src/flow.jl:113-117; visc! :120-152; surfTen! src/surfaceTension.jl:8-21).
+    mu / eta = None stand for `nothing`."""
+    return context_for(f).visc_surften_rhou(_stream(f), _p(r), _p(u), _p(Phi), _p(f), _p(alpha), _p(nhat), _p(fbuffer), lam_mu, mu,
+                                            lam_rho, eta, perdir)
+
+
+def _gvec(g, D, t):
+    """WaterLily's g(i,x,t) evaluated as a constant vector (the only form accelerate! is restated for)."""
+    if g is None:
+        return None
+    if callable(g):
+        return tuple(float(g(i + 1, [0.0] * D, t)) for i in range(D))
+    return tuple(float(x) for x in g)
+
+
+def updateU(u, rhou, rhou0, forcing, dt, f, lam_rho, tNow=0.0, g=None, uBC=None, w=1.0):
+    """updateU!(u,ρu,ρu⁰,forcing,dt,f,λρ,tNow,g,uBC,w)  (src/flow.jl:244-252); g: None, a constant vector or g(i,x,t) sampled at x=0."""
+    return context_for(f).update_u(_stream(f), _p(u), _p(rhou), _p(rhou0), _p(forcing), dt, _p(f), lam_rho, _gvec(g, f.dim(), tNow), w)
+
+
+def updateL(mu0, f, lam_rho, perdir=(), fill_one=False):
+    """updateL!(μ₀,f,λρ;perdir)  (src/flow.jl:254-259); fill_one folds the preceding fill!(μ₀,1) (flow.jl:73,96) into the pass."""
+    return context_for(f).update_l(_stream(f), _p(mu0), _p(f), lam_rho, perdir, fill_one)
+
+
+def _ustar_top_planes(nhat, uBC, perdir, exitBC):
+    """In the reference n̂ ≡ u★ leaves advectfq! with BC! applied (flow.jl:197): plane N_d of component d holds uBC[d].  visc! reads
+    exactly that plane as `fFace` (f2face!+BCv! never write it).  The B200 sweeps do not materialise u★, so the mirror writes the
+    D planes the reference's side effect leaves behind (exitBC: plane N of component 1 is skipped by BC!, like there)."""
+    D = nhat.dim() - 1
+    for d in range(D):
+        if (d + 1) in perdir or (exitBC and d == 0):
+            continue
+        idx = [slice(None)] * D + [d]
+        idx[d] = -1
+        nhat[tuple(idx)] = float(uBC[d])
+
+
+def mom_step_forcing(a: Flow, c: cVOF, dt=None, project: Optional[Callable] = None, check=False):
+    """MPFMomStep! with its explicit forcing (src/flow.jl:60-107): transport (B200 sweeps), viscSurfTenρu!, updateU!, BC!, updateL! for
+    the predictor (weight 1/2) and the corrector.  `project(a, c, stage)` stands for update!(b); myproject!(a,b[,1/2]) (WaterLily's
+    Poisson solve, out of scope) and is called at its place (:82, :106); without it u stays unprojected."""
+    dt = a.dt[-1] if dt is None else dt
+    ctx, s = context_for(c.f), _stream(c.f)
+    t1 = sum(a.dt); t0 = t1 - dt; tm = t1 - dt / 2
+    _copy(a.u0, a.u)                                                          # :61
+    u2rhou_advectfq(a, c, c.f, c.f0, a.u0, a.u, a.u, dt, check=check)          # :61 (f⁰←f), :69, :70
+    ctx.axpby(s, _p(c.f0), 0.5, _p(c.f0), 0.5, _p(c.f))                        # :74
+    _ustar_top_planes(c.nhat, a.uBC, a.perdir, a.exitBC)
+    viscSurfTenrhou(a.f, a.u, a.sigma, c.f0, c.alpha, c.nhat, c.ff, c.lam_mu, c.mu, c.lam_rho, c.eta, a.perdir)  # :75
+    u2rhou(c.nhat, a.u0, c.f, c.lam_rho)                                       # :76
+    updateU(a.u, c.rhou, c.nhat, a.f, dt, c.f0, c.lam_rho, tm, a.g, a.uBC, 0.5)  # :77
+    BC(a.u, a.uBC, a.exitBC, a.perdir)                                         # :79
+    updateL(a.mu0, c.f0, c.lam_rho, a.perdir, fill_one=True)                   # :73, :80
+    if project is not None:
+        project(a, c, "predictor")                                             # :81-82
+        BC(a.u, a.uBC, a.exitBC, a.perdir)
+    _copy(c.f0, c.f)                                                           # :89
+    u2rhou_advectfq(a, c, c.f, c.f, a.u, a.u, a.u0, dt, check=check)           # :91, :92
+    _ustar_top_planes(c.nhat, a.uBC, a.perdir, a.exitBC)
+    viscSurfTenrhou(a.f, a.u, a.sigma, c.f, c.alpha, c.nhat, c.ff, c.lam_mu, c.mu, c.lam_rho, c.eta, a.perdir)   # :98
+    u2rhou(c.nhat, a.u0, c.f, c.lam_rho)                                       # :99
+    _copy(a.u0, a.u)                                                           # :100
+    updateU(a.u, c.rhou, c.nhat, a.f, dt, c.f, c.lam_rho, t1, a.g, a.uBC)      # :101
+    BC(a.u, a.uBC, a.exitBC, a.perdir)                                         # :103
+    updateL(a.mu0, c.f, c.lam_rho, a.perdir, fill_one=True)                    # :96, :104
+    if project is not None:
+        project(a, c, "corrector")                                             # :105-106
+        BC(a.u, a.uBC, a.exitBC, a.perdir)
+
+
+def MPFMomStep(a: Flow, b, c: cVOF, d=None, dt=None, project: Optional[Callable] = None, check=False, forcing=False):
     """Transport part of MPFMomStep!(a,b,c,d)  (src/flow.jl:60-109).
 
     Lines 61, 69-70, 74, 89-92 and 108 run on the B200 kernels.  The forcing (viscSurfTenρu!, updateU!) and the
     pressure projection (myproject!) stay on WaterLily's backend; `project(a, c, stage)` is the hook
-    where a caller plugs them in.  Without it velocities are prescribed: u is left untouched between the stages."""
+    where a caller plugs them in.  Without it velocities are prescribed: u is left untouched between the stages.
+    forcing=True runs the reference's whole sequence except the Poisson solve -- viscSurfTenρu!, updateU!, BC!, updateL! on the B200
+    kernels too (mom_step_forcing) -- and `project` then stands for update!(b); myproject! only."""
     dt = a.dt[-1] if dt is None else dt
-    mom_advect_step(a, c, dt, project=project, check=check)
+    if forcing:
+        mom_step_forcing(a, c, dt, project=project, check=check)
+    else:
+        mom_advect_step(a, c, dt, project=project, check=check)
     a.dt.append(min(MPCFL(a, c), 1.2 * dt))                           # :108
 
 
-def sim_step(sim: TwoPhaseSimulation, t_end: Optional[float] = None, project=None, check=False):
+def sim_step(sim: TwoPhaseSimulation, t_end: Optional[float] = None, project=None, check=False, forcing=False):
     """sim_step!(sim[,t_end])  (src/InterfaceAdvection.jl:100-103 + WaterLily's generic loop)"""
     if t_end is None:
-        return MPFMomStep(sim.flow, sim.pois, sim.intf, sim.body, project=project, check=check)
+        return MPFMomStep(sim.flow, sim.pois, sim.intf, sim.body, project=project, check=check, forcing=forcing)
     while sim_time(sim) < t_end:
-        MPFMomStep(sim.flow, sim.pois, sim.intf, sim.body, project=project, check=check)
+        MPFMomStep(sim.flow, sim.pois, sim.intf, sim.body, project=project, check=check, forcing=forcing)
 
 
 def sim_time(sim: TwoPhaseSimulation) -> float:

@@ -16,6 +16,7 @@
 
 #include "../../include/ifadv.h"
 #include "ifadv_ctx.hpp"
+#include "ifadv_forcing.cuh"
 
 using namespace ifadv;
 
@@ -762,6 +763,58 @@ template <class T> static int axpby_t(ifadv_ctx* c, cudaStream_t st, T* out, dou
   return 0;
 }
 
+// ---- explicit forcing (ifadv_forcing.cuh) ------------------------------------------------------------------------------------
+static inline dim3 all_grid(const Geo& g, int D, int bx) {
+  return dim3((unsigned)((g.n[0] + bx - 1) / bx), (unsigned)g.n[1], (unsigned)(D == 3 ? g.n[2] : 1));
+}
+template <class T>
+static int visc_surften_t(ifadv_ctx* c, cudaStream_t st, T* r, const T* u, const T* f, const T* nhat, T* fb, double lmu, double mu, double lr,
+                          double eta, unsigned per) {
+  Geo g = c->g;
+  g.per = per;
+  const int bx = 128;
+  const dim3 gi = row_grid(g, c->D, bx), ga = all_grid(g, c->D, bx);
+  const int has_mu = mu > 0.0, has_eta = eta > 0.0;
+  if (c->D == 2) visc_kernel<T, 2><<<gi, bx, 0, st>>>(r, u, f, nhat, g, (T)lmu, (T)mu, (T)lr, has_mu);
+  else visc_kernel<T, 3><<<gi, bx, 0, st>>>(r, u, f, nhat, g, (T)lmu, (T)mu, (T)lr, has_mu);
+  c->launches++;
+  if (has_eta)
+    for (int d = 0; d < c->D; ++d) {
+      if (c->D == 2) {
+        fbuffer_kernel<T, 2><<<ga, bx, 0, st>>>(fb, f, g, d);
+        surften_kernel<T, 2><<<gi, bx, 0, st>>>(r, fb, f, g, d, (T)eta);
+      } else {
+        fbuffer_kernel<T, 3><<<ga, bx, 0, st>>>(fb, f, g, d);
+        surften_kernel<T, 3><<<gi, bx, 0, st>>>(r, fb, f, g, d, (T)eta);
+      }
+      c->launches += 2;
+    }
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+template <class T>
+static int update_u_t(ifadv_ctx* c, cudaStream_t st, T* u, T* ru, const T* ru0, T* fo, double dt, const T* f, double lr, const double* grav,
+                      double w) {
+  const int bx = 128;
+  const dim3 ga = all_grid(c->g, c->D, bx);
+  const T G0 = grav ? (T)grav[0] : T(0), G1 = grav ? (T)grav[1] : T(0), G2 = (grav && c->D == 3) ? (T)grav[2] : T(0);
+  if (c->D == 2) update_u_kernel<T, 2><<<ga, bx, 0, st>>>(u, ru, ru0, fo, f, c->g, (T)dt, (T)lr, (T)w, G0, G1, G2, grav != nullptr);
+  else update_u_kernel<T, 3><<<ga, bx, 0, st>>>(u, ru, ru0, fo, f, c->g, (T)dt, (T)lr, (T)w, G0, G1, G2, grav != nullptr);
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+template <class T> static int update_l_t(ifadv_ctx* c, cudaStream_t st, T* mu0, const T* f, double lr, unsigned per, int fill_one) {
+  const int bx = 128;
+  const dim3 gi = row_grid(c->g, c->D, bx);
+  if (c->D == 2) update_l_kernel<T, 2><<<gi, bx, 0, st>>>(mu0, f, c->g, (T)lr, fill_one);
+  else update_l_kernel<T, 3><<<gi, bx, 0, st>>>(mu0, f, c->g, (T)lr, fill_one);
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  const double Z[3] = {0.0, 0.0, 0.0};
+  return bcvec_t<T>(c, st, mu0, Z, 0, per);  // BC!(μ₀,zeros,false,perdir), flow.jl:258
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------------------
@@ -1290,6 +1343,39 @@ int ifadv_mom_advect_step_host(ifadv_ctx* c, void* f_host, const void* u_host, v
   if (!pf) memcpy(f_host, c->pin_f, sb);
   if (!pr) memcpy(rhou_host, c->pin_ru, vb);
   return rc;
+}
+
+int ifadv_visc_surften_rhou(ifadv_ctx* c, void* stream, void* r, const void* u, void* Phi, const void* f, void* alpha, void* nhat,
+                            void* fbuffer, double lambda_mu, double mu, double lambda_rho, double eta, unsigned perdir_mask) {
+  (void)Phi; (void)alpha;
+  if (!c) return -2;
+  if (c->slab.nranks > 1) return fail(c, -2, "the forcing entry points are single-GPU (the height-function column walks are unbounded along z)");
+  if (!r || !u || !f || (mu > 0.0 && !nhat) || (eta > 0.0 && !fbuffer)) return fail(c, -2, "null array");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->dtype == IFADV_F32)
+    return visc_surften_t<float>(c, st, (float*)r, (const float*)u, (const float*)f, (const float*)nhat, (float*)fbuffer, lambda_mu, mu,
+                                 lambda_rho, eta, perdir_mask);
+  return visc_surften_t<double>(c, st, (double*)r, (const double*)u, (const double*)f, (const double*)nhat, (double*)fbuffer, lambda_mu, mu,
+                                lambda_rho, eta, perdir_mask);
+}
+
+int ifadv_update_u(ifadv_ctx* c, void* stream, void* u, void* rhou, const void* rhou0, void* forcing, double dt, const void* f,
+                   double lambda_rho, const double g[3], double w) {
+  if (!c) return -2;
+  if (!u || !rhou || !rhou0 || !forcing || !f) return fail(c, -2, "null array");
+  if (!(w > 0.0)) return fail(c, -2, "invalid weight w");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->dtype == IFADV_F32)
+    return update_u_t<float>(c, st, (float*)u, (float*)rhou, (const float*)rhou0, (float*)forcing, dt, (const float*)f, lambda_rho, g, w);
+  return update_u_t<double>(c, st, (double*)u, (double*)rhou, (const double*)rhou0, (double*)forcing, dt, (const double*)f, lambda_rho, g, w);
+}
+
+int ifadv_update_l(ifadv_ctx* c, void* stream, void* mu0, const void* f, double lambda_rho, unsigned perdir_mask, int fill_one) {
+  if (!c) return -2;
+  if (!mu0 || !f) return fail(c, -2, "null array");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->dtype == IFADV_F32) return update_l_t<float>(c, st, (float*)mu0, (const float*)f, lambda_rho, perdir_mask, fill_one);
+  return update_l_t<double>(c, st, (double*)mu0, (const double*)f, lambda_rho, perdir_mask, fill_one);
 }
 
 int ifadv_defer_f_writes_until(ifadv_ctx* c, void* event) {

@@ -106,3 +106,34 @@ def oracle_mom_step_hook(st, f, u, dt, dirO, hook, lam="Koren", scheme="WH"):
                      a["alpha"], a["drho"], st["lam_rho"], lam, scheme, st["uBC"], st["perdir"], False, dirO)  # :92
     hook(u, a["rhou"], f, "corrector")                                                                 # :95-106
     return a["rhou"]
+
+
+def oracle_mom_step_forcing(st, a, f, u, dt, dirO, mu, lam_mu, eta, g, lam="Koren", scheme="WH"):
+    """MPFMomStep! with its explicit forcing and without the Poisson solve (flow.jl:60-107 minus :81-82,:105-106) on the oracle.
+    `a` is the persistent array set of alloc_cmom (the reference's aliasing: uStar≡n̂, dilaU≡α, r≡flow.f, Φ≡flow.σ, fbuffer≡fᶠ) plus
+    "mu0"; f and u are advanced in place.  Mirrors api.mom_step_forcing."""
+    T = st["dtype"]
+    lr, uBC, pd = st["lam_rho"], st["uBC"], st["perdir"]
+    u0 = u.copy(order="F"); f0 = f.copy(order="F")                                                      # :61
+    O.u2rhou(a["rhou"], u0, f0, lr); O.BC(a["rhou"], uBC, False, pd)                                    # :69
+    O.advectVOFrhouu(f0, a["ff"], a["alpha"], a["nhat"], u0, u, dt, a["cbar"], a["rhou"], a["r"], a["Phi"], a["rhouf"], a["nhat"], u,
+                     a["alpha"], a["drho"], lr, lam, scheme, uBC, pd, False, dirO)                      # :70
+    a["mu0"][...] = 1                                                                                   # :73
+    f0[...] = (f0 + f) * T(0.5)                                                                         # :74
+    O.viscSurfTenrhou(a["r"], u, a["Phi"], f0, a["alpha"], a["nhat"], a["ff"], lam_mu, mu, lr, eta, pd)  # :75
+    O.u2rhou(a["nhat"], u0, f, lr)                                                                      # :76
+    O.updateU(u, a["rhou"], a["nhat"], a["r"], dt, f0, lr, g, 0.5)                                      # :77
+    O.BC(u, uBC, False, pd)                                                                             # :79
+    O.updateL(a["mu0"], f0, lr, pd)                                                                     # :80
+    f0[...] = f                                                                                         # :89
+    O.u2rhou(a["rhou"], u0, f, lr); O.BC(a["rhou"], uBC, False, pd)                                     # :91
+    O.advectVOFrhouu(f, a["ff"], a["alpha"], a["nhat"], u, u, dt, a["cbar"], a["rhou"], a["r"], a["Phi"], a["rhouf"], a["nhat"], u0,
+                     a["alpha"], a["drho"], lr, lam, scheme, uBC, pd, False, dirO)                      # :92
+    a["mu0"][...] = 1                                                                                   # :96
+    O.viscSurfTenrhou(a["r"], u, a["Phi"], f, a["alpha"], a["nhat"], a["ff"], lam_mu, mu, lr, eta, pd)   # :98
+    O.u2rhou(a["nhat"], u0, f, lr)                                                                      # :99
+    u0[...] = u                                                                                         # :100
+    O.updateU(u, a["rhou"], a["nhat"], a["r"], dt, f, lr, g, 1.0)                                       # :101
+    O.BC(u, uBC, False, pd)                                                                             # :103
+    O.updateL(a["mu0"], f, lr, pd)                                                                      # :104
+    return a["rhou"]
