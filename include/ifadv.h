@@ -144,10 +144,12 @@ int ifadv_apply_vof_samples(ifadv_ctx* ctx, void* stream, void* f, void* alpha, 
  *   Weymouth-Yue normal, Popinet column heights, height-function curvature).  Out: r on inside(f) (the reference also accumulates
  *   into upper ghost entries nothing reads).  mu <= 0 / eta <= 0 stand for `nothing`.  f, u carry valid ghosts.  Φ, α are unused;
  *   n̂ is only READ: plane N_d of component d, which f2face!+BCv! never write in a non-periodic direction (the reference reads it as
- *   left by BC! on u★≡n̂ in the previous advectfq!, i.e. uBC[d]); fbuffer is rewritten for every d exactly like the reference
- *   (plane N_d of a non-periodic d keeps the caller's values: BCf!(d,·) skips it). */
-int ifadv_visc_surften_rhou(ifadv_ctx* ctx, void* stream, void* r, const void* u, void* Phi, const void* f, void* alpha, void* nhat,
-                            void* fbuffer, double lambda_mu, double mu, double lambda_rho, double eta, unsigned perdir_mask);
+ *   left by BC! on u★≡n̂ in the previous advectfq!, i.e. uBC[d]); fbuffer is only READ as well: the staggered fields ϕ(d,·,f) with the
+ *   ghost rules of BCf!(d,·) are evaluated from f where the stencils need them, and plane N_d of a non-periodic d, which BCf!(d,·)
+ *   skips, resolves like in the reference's sequential passes (previous direction's field; the caller's values for d = 1).  The
+ *   reference leaves ϕ(D,·,f) behind in fbuffer, which nothing reads; here the array is untouched. */
+int ifadv_visc_surften_rhou(ifadv_ctx* ctx, void* stream, void* r, const void* u, void* Phi, const void* f, void* alpha, const void* nhat,
+                            const void* fbuffer, double lambda_mu, double mu, double lambda_rho, double eta, unsigned perdir_mask);
 /* updateU!(u,ρu,ρu⁰,forcing,dt,f,λρ,tNow,g,uBC,w)                                  src/flow.jl:244-252
  *   ρu ← (a ρu⁰ + ρu + forcing·dt)·w with a = 1/w - 1 (ALL entries); u ← ρu/ρ(f̄) on inside(f); forcing ← g; u ← u + dt·w·g.
  *   g: constant gravity vector (accelerate! with g(i,x,t) = g[i]) or NULL (`nothing`; time-dependent uBC is not supported). */

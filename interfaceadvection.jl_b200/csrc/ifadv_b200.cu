@@ -768,27 +768,52 @@ static inline dim3 all_grid(const Geo& g, int D, int bx) {
   return dim3((unsigned)((g.n[0] + bx - 1) / bx), (unsigned)g.n[1], (unsigned)(D == 3 ? g.n[2] : 1));
 }
 template <class T>
-static int visc_surften_t(ifadv_ctx* c, cudaStream_t st, T* r, const T* u, const T* f, const T* nhat, T* fb, double lmu, double mu, double lr,
-                          double eta, unsigned per) {
+static int visc_surften_t(ifadv_ctx* c, cudaStream_t st, T* r, const T* u, const T* f, const T* nhat, const T* fb, double lmu, double mu,
+                          double lr, double eta, unsigned per) {
   Geo g = c->g;
   g.per = per;
   const int bx = 128;
-  const dim3 gi = row_grid(g, c->D, bx), ga = all_grid(g, c->D, bx);
+  const dim3 gi = row_grid(g, c->D, bx);
   const int has_mu = mu > 0.0, has_eta = eta > 0.0;
   if (c->D == 2) visc_kernel<T, 2><<<gi, bx, 0, st>>>(r, u, f, nhat, g, (T)lmu, (T)mu, (T)lr, has_mu);
-  else visc_kernel<T, 3><<<gi, bx, 0, st>>>(r, u, f, nhat, g, (T)lmu, (T)mu, (T)lr, has_mu);
-  c->launches++;
-  if (has_eta)
-    for (int d = 0; d < c->D; ++d) {
-      if (c->D == 2) {
-        fbuffer_kernel<T, 2><<<ga, bx, 0, st>>>(fb, f, g, d);
-        surften_kernel<T, 2><<<gi, bx, 0, st>>>(r, fb, f, g, d, (T)eta);
-      } else {
-        fbuffer_kernel<T, 3><<<ga, bx, 0, st>>>(fb, f, g, d);
-        surften_kernel<T, 3><<<gi, bx, 0, st>>>(r, fb, f, g, d, (T)eta);
-      }
-      c->launches += 2;
+  else if (!has_mu) visc_kernel<T, 3><<<gi, bx, 0, st>>>(r, u, f, nhat, g, (T)lmu, (T)mu, (T)lr, 0);
+  else {
+    auto kern = visc3m_kernel<T>;
+    const size_t smem = ViscM::bytes<T>();
+    static unsigned long long attr_devs = 0ull;
+    if (!((attr_devs >> (c->device & 63)) & 1ull)) {
+      CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_devs |= 1ull << (c->device & 63);
     }
+    const int nz = g.n[2] - 2;
+    const long long tiles = (long long)((g.n[0] - 2 + ViscM::TX - 1) / ViscM::TX) * ((g.n[1] - 2 + ViscM::TY - 1) / ViscM::TY);
+    int chunk = 64;  // one extra staged plane per chunk
+    while (chunk > 8 && tiles * ((nz + chunk - 1) / chunk) < 148 * 16) chunk >>= 1;
+    const dim3 gt((unsigned)((g.n[0] - 2 + ViscM::TX - 1) / ViscM::TX), (unsigned)((g.n[1] - 2 + ViscM::TY - 1) / ViscM::TY),
+                  (unsigned)((nz + chunk - 1) / chunk));
+    kern<<<gt, ViscM::NT, smem, st>>>(r, u, f, nhat, g, (T)lmu, (T)mu, (T)lr, chunk);
+  }
+  c->launches++;
+  if (has_eta) {
+    if (!c->st_list) {  // capacity per direction: an eighth of the cells (interfaces are surfaces); an overflow falls back to scanning every cell
+      const unsigned cap = (unsigned)std::min<long long>(std::max<long long>(c->g.S / 8, 1 << 16), 1ll << 27);
+      CU_CHECK(c, cudaMalloc(&c->st_list, sizeof(int) * (size_t)cap * 3));
+      CU_CHECK(c, cudaMalloc(&c->st_cnt, sizeof(unsigned) * 4));
+      c->st_cap = cap;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    CU_CHECK(c, cudaMemsetAsync(c->st_cnt, 0, sizeof(unsigned) * 4, st));
+    const dim3 gs((unsigned)((g.n[0] - 2 + bx - 1) / bx), (unsigned)((g.n[1] - 2 + 3) / 4), (unsigned)(c->D == 3 ? g.n[2] - 2 : 1));
+    if (c->D == 2) {
+      stscan_kernel<T, 2><<<gs, bx, 0, st>>>(f, g, c->st_list, c->st_cnt, c->st_cap);
+      surften_kernel<T, 2><<<(unsigned)sms * 8, 128, 0, st>>>(r, f, fb, g, (T)eta, c->st_list, c->st_cnt, c->st_cap);
+    } else {
+      stscan_kernel<T, 3><<<gs, bx, 0, st>>>(f, g, c->st_list, c->st_cnt, c->st_cap);
+      surften_kernel<T, 3><<<(unsigned)sms * 8, 128, 0, st>>>(r, f, fb, g, (T)eta, c->st_list, c->st_cnt, c->st_cap);
+    }
+    c->launches += 2;
+  }
   CU_CHECK(c, cudaGetLastError());
   return 0;
 }
@@ -845,6 +870,7 @@ int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int dev
   for (auto& p : c->w) p = nullptr;
   c->pin_f = c->pin_u = c->pin_ru = nullptr;
   c->own_stream = nullptr;
+  c->st_list = nullptr; c->st_cnt = nullptr; c->st_cap = 0;
   c->pipe = nullptr;
   c->wait_f = nullptr;
   c->host_h2d = c->host_d2h = 0; c->host_slabs = 0;
@@ -878,6 +904,8 @@ int ifadv_destroy(ifadv_ctx* c) {
   if (c->pin_u) cudaFreeHost(c->pin_u);
   if (c->pin_ru) cudaFreeHost(c->pin_ru);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->st_list) cudaFree(c->st_list);
+  if (c->st_cnt) cudaFree(c->st_cnt);
   slab_p2p_free(c);
   if (c->slab_stream) { cudaStreamDestroy(c->slab_stream); cudaEventDestroy(c->slab_ev[0]); cudaEventDestroy(c->slab_ev[1]); }
   host_pipe_free(c);
@@ -1345,17 +1373,17 @@ int ifadv_mom_advect_step_host(ifadv_ctx* c, void* f_host, const void* u_host, v
   return rc;
 }
 
-int ifadv_visc_surften_rhou(ifadv_ctx* c, void* stream, void* r, const void* u, void* Phi, const void* f, void* alpha, void* nhat,
-                            void* fbuffer, double lambda_mu, double mu, double lambda_rho, double eta, unsigned perdir_mask) {
+int ifadv_visc_surften_rhou(ifadv_ctx* c, void* stream, void* r, const void* u, void* Phi, const void* f, void* alpha, const void* nhat,
+                            const void* fbuffer, double lambda_mu, double mu, double lambda_rho, double eta, unsigned perdir_mask) {
   (void)Phi; (void)alpha;
   if (!c) return -2;
   if (c->slab.nranks > 1) return fail(c, -2, "the forcing entry points are single-GPU (the height-function column walks are unbounded along z)");
   if (!r || !u || !f || (mu > 0.0 && !nhat) || (eta > 0.0 && !fbuffer)) return fail(c, -2, "null array");
   cudaStream_t st = (cudaStream_t)stream;
   if (c->dtype == IFADV_F32)
-    return visc_surften_t<float>(c, st, (float*)r, (const float*)u, (const float*)f, (const float*)nhat, (float*)fbuffer, lambda_mu, mu,
+    return visc_surften_t<float>(c, st, (float*)r, (const float*)u, (const float*)f, (const float*)nhat, (const float*)fbuffer, lambda_mu, mu,
                                  lambda_rho, eta, perdir_mask);
-  return visc_surften_t<double>(c, st, (double*)r, (const double*)u, (const double*)f, (const double*)nhat, (double*)fbuffer, lambda_mu, mu,
+  return visc_surften_t<double>(c, st, (double*)r, (const double*)u, (const double*)f, (const double*)nhat, (const double*)fbuffer, lambda_mu, mu,
                                 lambda_rho, eta, perdir_mask);
 }
 

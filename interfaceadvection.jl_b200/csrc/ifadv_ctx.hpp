@@ -52,6 +52,9 @@ struct ifadv_ctx {
   void* pin_u;
   void* pin_ru;
   cudaStream_t own_stream;
+  int* st_list;        // interface-cell list of the surface-tension kernels (ifadv_forcing.cuh), allocated lazily
+  unsigned* st_cnt;    // its device-side counter
+  unsigned st_cap;
   cudaEvent_t wait_f;  // one-shot: the next CMOM advect call waits for it before its first write to f (ifadv_defer_f_writes_until)
   void* pipe;  // z-slab pipeline of the host-buffer entry point (HostPipe, ifadv_b200.cu), built lazily
   int64_t host_h2d, host_d2h;  // bytes the last ifadv_mom_advect_step_host call copied in / out
