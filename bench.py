@@ -510,6 +510,17 @@ def run_b200(args):
                    "note": "BASELINE config 5 (sloshing tank 2048x1024x1024 over 8 GPUs): this is its per-GPU slab at N GPUs; weak-scaling "
                            "efficiency of the named shape = value(N) / (N * value(1)) of this sub-line"}
 
+    # ---- next to the path: the explicit forcing of MPFMomStep! on the same grid, timed on its own ----
+    forcing_line = None
+    if not args.no_extra and world == 1:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("time_forcing", os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "time_forcing.py"))
+        tf = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(tf)
+        ia.api._contexts.clear()
+        torch.cuda.empty_cache()
+        forcing_line = tf.measure(w["N"][0], w["dtype"] == "float64", 5, dev)
+
     # ---- e2e: the reference-facing C-ABI call with HOST buffers (H2D/D2H inside the timed region) ----
     e2e = None
     if not args.no_e2e:
@@ -544,7 +555,7 @@ def run_b200(args):
                        "nccl_bytes_sent_per_rank_per_step": int(sent / (args.steps + args.warmup)) if world > 1 else 0,
                        "mass_drift_rel": r["mass_drift_rel"]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": r["launches"], "clocks": r["clocks"],
-            "slab_check": bitwise, "tgv_line": tgv_line, "c5": c5_line,
+            "slab_check": bitwise, "tgv_line": tgv_line, "c5": c5_line, "forcing": forcing_line,
         }
         print(json.dumps(line))
     if dist is not None:

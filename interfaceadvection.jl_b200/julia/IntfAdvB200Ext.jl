@@ -4,7 +4,8 @@
 # It replaces ext/IntfAdvCUDAExt.jl ON THIS PATH: instead of only allowing scalar indexing (the 8 lines the stock
 # extension consists of, ext/IntfAdvCUDAExt.jl:19-23) it overrides the two sweep drivers
 #     advectVOF!     (src/advection.jl:34)      and      advectVOFρuu!  (src/flow.jl:165)
-# plus the secondary seams u2ρu!/ρu2u! (src/VOFutil.jl:198-211) and MPCFL (src/flow.jl:262) for CuArray{Float32|Float64}.
+# plus the secondary seams u2ρu!/ρu2u! (src/VOFutil.jl:198-211), MPCFL (src/flow.jl:262) and the explicit forcing viscSurfTenρu! /
+# updateU! / updateL! (src/flow.jl:113-117,244-259) for CuArray{Float32|Float64}.
 # No KernelAbstractions, no multi-backend dispatch, no CPU fallback: unsupported argument combinations raise.
 #
 # STATUS: UNTESTED.  No Julia toolchain exists in the environment this library was built in, so this file has been written
@@ -18,6 +19,7 @@ using CUDA
 using InterfaceAdvection
 import Random
 import InterfaceAdvection: advectVOF!, advectVOFρuu!, u2ρu!, ρu2u!, MPCFL, _scalar_op, cVOF
+import InterfaceAdvection: viscSurfTenρu!, updateU!, updateL!
 import InterfaceAdvection: getInterfaceNormal_WH!, getInterfaceNormal_WY!, getInterfaceNormal_Column!, getInterfaceNormal_PCD!,
                            getInterfaceNormal_SLIC!, getInterfaceNormal_MYC!, getInterfaceNormal_Y!, getInterfaceNormal_CD!,
                            getInterfaceNormal_XYLIC!
@@ -145,9 +147,32 @@ function MPCFL(a::Flow{D,T}, c::cVOF; Δt_max=one(T), safetyMargin=T(0.8)) where
     T(out[])
 end
 
+# ---- explicit forcing between advection and projection (src/flow.jl:113-117, 244-259) --------------------------------------------
+function viscSurfTenρu!(r::CuArray{T}, u, Φ, f::CuArray{T}, α, n̂, fbuffer, λμ, μ, λρ, η; perdir=()) where {T<:Union{Float32,Float64}}
+    ctx = context(f)
+    check(ctx, ccall((:ifadv_visc_surften_rhou, LIB), Cint,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble,
+                      Cdouble, Cdouble, Cuint),
+                     ctx, stream_ptr(), dptr(r), dptr(u), dptr(Φ), dptr(f), dptr(α), dptr(n̂), dptr(fbuffer), λμ, isnothing(μ) ? 0.0 : μ, λρ,
+                     isnothing(η) ? 0.0 : η, perdir_mask(perdir))); nothing
+end
+function updateU!(u::CuArray{T}, ρu, ρu⁰, forcing, dt, f::CuArray{T,D}, λρ, tNow, g, uBC, w=one(T)) where {T<:Union{Float32,Float64},D}
+    uBC isa Function && error("IntfAdvB200Ext: function-valued uBC is not supported (no fallback)")
+    ctx = context(f)
+    gv = isnothing(g) ? Ptr{Cdouble}(C_NULL) : Cdouble[(g(i, zeros(T, D), tNow) for i in 1:D)...; zeros(3 - D)]   # constant gravity only
+    GC.@preserve gv check(ctx, ccall((:ifadv_update_u, LIB), Cint,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cdouble, Ptr{Cdouble}, Cdouble),
+                     ctx, stream_ptr(), dptr(u), dptr(ρu), dptr(ρu⁰), dptr(forcing), dt, dptr(f), λρ, gv, w)); nothing
+end
+function updateL!(μ₀::CuArray{T}, f::CuArray{T}, λρ; perdir=()) where {T<:Union{Float32,Float64}}
+    ctx = context(f)
+    check(ctx, ccall((:ifadv_update_l, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cuint, Cint),
+                     ctx, stream_ptr(), dptr(μ₀), dptr(f), λρ, perdir_mask(perdir), 0)); nothing
+end
+
 # ---- MPFMomStep!  (src/flow.jl:60-109) with the transport half on the fused entry points ---------------------------------------
 # Each of the two groups `copyto!(f⁰,f); u2ρu!(ρu,u⁰,·); BC!(ρu); advectfq!(…)` (flow.jl:61,69-70 and :89-92) becomes ONE call of
-# ifadv_u2rhou_advect_vof_rhouu (bit-identical to the separate calls, include/ifadv.h); forcing and projection stay WaterLily's.
+# ifadv_u2rhou_advect_vof_rhouu (bit-identical to the separate calls, include/ifadv.h); the forcing runs through the three overrides above, only udf! and the projection stay WaterLily's.
 function fused_group!(a::Flow{D,T}, c::cVOF, fsrc, f, u¹, u², uOld, δt) where {D,T}
     a.uBC isa Function && error("IntfAdvB200Ext: function-valued uBC is not supported (no fallback)")
     ctx = context(f)
@@ -168,7 +193,7 @@ end
 function InterfaceAdvection.MPFMomStep!(a::Flow{D,T}, b::WaterLily.AbstractPoisson, c::cVOF{D,T,<:CuArray}, d::WaterLily.AbstractBody;
                                         δt=last(a.Δt), udf=nothing, kwargs...) where {D,T<:Union{Float32,Float64}}
     t₁ = sum(a.Δt); t₀ = t₁ - δt; tₘ = t₁ - δt / 2
-    stage!(fNow, tNow, tUdf, w, dtUdf) = begin   # forcing + projection of one RK stage (flow.jl:73-82 / :94-106), WaterLily side
+    stage!(fNow, tNow, tUdf, w, dtUdf) = begin   # forcing + projection of one RK stage (flow.jl:73-82 / :94-106)
         fill!(a.μ₀, 1)
         InterfaceAdvection.viscSurfTenρu!(a.f, a.u, a.σ, fNow, c.α, c.n̂, c.fᶠ, c.λμ, c.μ, c.λρ, c.η; perdir=a.perdir)
         u2ρu!(c.n̂, a.u⁰, c.f, c.λρ)
