@@ -211,9 +211,10 @@ int ifadv_mom_advect_step_host(ifadv_ctx* ctx, void* f_host, const void* u_host,
                                int limiter, int normal_scheme, const double uBC[3], unsigned perdir_mask, const int dirO[3],
                                ifadv_report* report);
 /* Bytes the last ifadv_mom_advect_step_host call copied host->device / device->host and the number of z-slabs it was
- * pipelined over (1 = single pass).  Large 3-D grids that are not periodic in z are split into z-slabs (a quarter of the planes
+ * pipelined over (1 = single pass).  Large 3-D grids that are not periodic in z are split into z-slabs (an eighth of the planes
  * each, IFADV_HOST_CHUNK=<planes> overrides, 0 disables) extended by 8 overlap planes per interior end, so that the copies of
- * consecutive slabs overlap the kernels; the result is bit-identical to the single pass.  Needs page-locked host buffers. */
+ * consecutive slabs overlap the kernels; the planes of u a slab shares with its predecessor are copied on the device instead of
+ * over PCIe again; the result is bit-identical to the single pass.  Needs page-locked host buffers. */
 int ifadv_host_step_bytes(const ifadv_ctx* ctx, int64_t* h2d_bytes, int64_t* d2h_bytes, int* slabs);
 
 #ifdef __cplusplus

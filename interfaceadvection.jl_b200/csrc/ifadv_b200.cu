@@ -882,6 +882,8 @@ int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int dev
     c->use_march = (e && std::string(e) == "tile") ? 0 : ((e && std::string(e) == "march") ? 2 : 1);
     c->use_along2 = (e && std::string(e) == "along1") ? 0 : 1;  // "along1": the first register-marching kernel for y/z sweeps
     c->use_xrow = (e && std::string(e) == "xsweep") ? 0 : 1;    // "xsweep": the plane-marching kernel for CMOM x sweeps
+    const char* ev = getenv("IFADV_VOF_KERNEL");
+    c->use_vofcell = (e || (ev && std::string(ev) == "lean")) ? 0 : 1;  // pure VOF, 3-D: cell-parallel kernel unless an older generation is asked for
   }
   if (cudaMalloc(&c->red_dev, sizeof(unsigned long long) * 32) != cudaSuccess ||
       cudaMemset(c->red_dev, 0, sizeof(unsigned long long) * 32) != cudaSuccess ||
@@ -1164,12 +1166,14 @@ void host_pipe_free(ifadv_ctx* c) {
   c->pipe = nullptr;
 }
 
-// planes per slab: IFADV_HOST_CHUNK (0 = single pass); default: a quarter of the interior planes for grids of >= 256 planes
+// planes per slab: IFADV_HOST_CHUNK (0 = single pass); default: an eighth of the interior planes for grids of >= 256 planes (512^3 f32:
+// 57.1 ms per step with 8 slabs, 59.5 with 6, 62.3 with 4, 58.0 with 16 -- PCIe runs both directions at ~78 GB/s combined, so the
+// short pipeline fill / drain of small slabs outweighs their extra overlap planes)
 int host_chunk_planes(const ifadv_ctx* c, unsigned perdir_mask) {
   if (c->D != 3 || (perdir_mask & 4u)) return 0;  // a periodic z would need wrapped overlaps: single pass
   const int NI = c->g.n[2] - 2;
   const char* e = getenv("IFADV_HOST_CHUNK");
-  int cp = e ? atoi(e) : (NI >= 256 ? (NI + 3) / 4 : 0);
+  int cp = e ? atoi(e) : (NI >= 256 ? (NI + 7) / 8 : 0);
   if (cp <= 0 || cp >= NI) return 0;
   return cp;
 }
@@ -1194,7 +1198,7 @@ int host_pipe_build(ifadv_ctx* c, int cp) {
     CU_CHECK(c, cudaEventCreateWithFlags(&h.ev_out, cudaEventDisableTiming));
     hp->ch.push_back(h);
     if (ifadv_create(&hp->ch.back().ctx, 3, ng, c->dtype, c->device) != 0) { c->err = "child context creation failed"; return -3; }
-    hp->ch.back().ctx->use_march = c->use_march; hp->ch.back().ctx->use_along2 = c->use_along2; hp->ch.back().ctx->use_xrow = c->use_xrow;
+    hp->ch.back().ctx->use_march = c->use_march; hp->ch.back().ctx->use_along2 = c->use_along2; hp->ch.back().ctx->use_xrow = c->use_xrow; hp->ch.back().ctx->use_vofcell = c->use_vofcell;
     maxpl = std::max(maxpl, (size_t)(h.hi - h.lo));
   }
   hp->nset = (int)std::min<size_t>(3, hp->ch.size());
@@ -1238,10 +1242,23 @@ int host_step_pipelined(ifadv_ctx* c, char* fh, const char* uh, char* rh, double
     // H2D: the buffer set is free once the slab that used it before has been copied out
     if (i >= hp->nset) CU_CHECK(c, cudaStreamWaitEvent(hp->s_in, hp->ch[i - hp->nset].ev_out, 0));
     CU_CHECK(c, cudaMemcpyAsync(f, fh + pl * h.lo, Sc, cudaMemcpyHostToDevice, hp->s_in));
-    for (int d = 0; d < 3; ++d)
-      CU_CHECK(c, cudaMemcpyAsync((char*)u + Sc * d, uh + Sp * d + pl * h.lo, Sc, cudaMemcpyHostToDevice, hp->s_in));
+    // u is read-only in the step, so the planes this slab shares with the previous one (its overlap + the neighbour's overlap + two
+    // child ghost planes) are already on the device: copy them from the previous slab's buffer instead of over PCIe again
+    size_t nshare = 0;
+    if (i > 0 && hp->nset >= 2 && !getenv("IFADV_HOST_NOSHARE")) {
+      const HostChunk& p = hp->ch[i - 1];
+      const size_t Scp = pl * (size_t)(p.hi - p.lo);
+      const void* up = hp->w[(i - 1) % hp->nset][4];
+      nshare = (size_t)std::min(std::max(p.hi - h.lo, 0), h.hi - h.lo);
+      for (int d = 0; d < 3 && nshare; ++d)
+        CU_CHECK(c, cudaMemcpyAsync((char*)u + Sc * d, (const char*)up + Scp * d + pl * (size_t)(h.lo - p.lo), pl * nshare,
+                                    cudaMemcpyDeviceToDevice, hp->s_in));
+    }
+    for (int d = 0; d < 3 && npl > nshare; ++d)
+      CU_CHECK(c, cudaMemcpyAsync((char*)u + Sc * d + pl * nshare, uh + Sp * d + pl * (h.lo + nshare), pl * (npl - nshare),
+                                  cudaMemcpyHostToDevice, hp->s_in));
     CU_CHECK(c, cudaEventRecord(h.ev_in, hp->s_in));
-    c->host_h2d += (int64_t)(4 * Sc);
+    c->host_h2d += (int64_t)(Sc + 3 * pl * (npl - nshare));
     // the step of this slab (same sequence as the single-pass entry)
     CU_CHECK(c, cudaStreamWaitEvent(hp->s_cmp, h.ev_in, 0));
     CU_CHECK(c, cudaMemcpyAsync(u0, u, 3 * Sc, cudaMemcpyDeviceToDevice, hp->s_cmp));

@@ -1,9 +1,10 @@
 // ifadv_sweep_inst.cu -- instantiates the fused sweep kernels for ONE (T, D, MOM, family) combination, chosen with
-// -DIFADV_T=float|double -DIFADV_D=2|3 -DIFADV_MOM=0|1 -DIFADV_FAM=0..5, so that the instantiations compile in parallel:
+// -DIFADV_T=float|double -DIFADV_D=2|3 -DIFADV_MOM=0|1 -DIFADV_FAM=0..6, so that the instantiations compile in parallel:
 //   FAM 0  dispatcher (launch_sweep_dim) + v1 tile kernel        FAM 1  plane-marching kernel (march)
 //   FAM 2  register-marching kernel (along)                      FAM 3  lean register marching (along2), y / z sweeps
 //   FAM 4  lean plane marching along x (xsweep, CMOM only)       FAM 5  warp-autonomous rows along x (xrow, CMOM only)
-//   families 1-5 exist for 3-D grids only
+//   FAM 6  cell-parallel pure-VOF sweep (vofcell, advect! only)
+//   families 1-6 exist for 3-D grids only
 #include <algorithm>
 #include <cstdlib>
 #include <limits>
@@ -24,8 +25,10 @@
 #include "ifadv_along2.cuh"
 #elif IFADV_FAM == 4
 #include "ifadv_xsweep.cuh"
-#else
+#elif IFADV_FAM == 5
 #include "ifadv_xrow.cuh"
+#else
+#include "ifadv_vofcell.cuh"
 #endif
 
 namespace ifadv {
@@ -256,12 +259,45 @@ static int launch_xrow_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
 }
 #endif
 
+#if IFADV_FAM == 6
+// v6: cell-parallel pure-VOF sweep (3-D only): no shared memory, no staging
+template <class T, int J, bool SAMEU> static int launch_vofcell_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  SweepP<T> P;
+  fill_params<T>(c, q, J, P);
+  if ((unsigned long long)c->g.S >= 0x7fffffffull) { c->err = "grid too large for 32-bit element offsets"; return -2; }
+  if (!c->st_list) {  // list of deferred (interface) cells, shared with the surface-tension kernels: an eighth of the cells per direction
+    const unsigned cap = (unsigned)std::min<long long>(std::max<long long>(c->g.S / 8, 1 << 16), 1ll << 27);
+    CU_CHECK(c, cudaMalloc(&c->st_list, sizeof(int) * (size_t)cap * 3));
+    CU_CHECK(c, cudaMalloc(&c->st_cnt, sizeof(unsigned) * 4));
+    c->st_cap = cap;
+  }
+  const int nx = c->g.n[0] - 2, ny = c->g.n[1] - 2, nz = c->g.n[2] - 2;
+  const long long tiles = (long long)((nx + 31) / 32) * ((ny + 7) / 8);
+  int chunk = 16;
+  while (chunk > 4 && tiles * ((nz + chunk - 1) / chunk) < 148 * 16) chunk >>= 1;
+  if (const char* e = getenv("IFADV_CHUNK")) chunk = std::max(1, atoi(e));  // measurement override
+  dim3 grid((unsigned)((nx + 31) / 32), (unsigned)((ny + 7) / 8), (unsigned)((nz + chunk - 1) / chunk));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
+  CU_CHECK(c, cudaMemsetAsync(c->st_cnt, 0, sizeof(unsigned), st));
+  if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
+  vofcell_kernel<T, J, SAMEU><<<grid, 256, 0, st>>>(P, chunk, c->st_list, c->st_cnt, c->st_cap * 3);
+  vofcell_fix_kernel<T, J, SAMEU><<<(unsigned)sms * 16, 128, 0, st>>>(P, c->st_list, c->st_cnt, c->st_cap * 3);
+  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_tag[c->prof_n] = (unsigned char)((2 * q.j) << 1); c->prof_n++; }
+  c->launches += 2;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+#endif
+
 // per-family entry points (3-D only), each defined and explicitly instantiated in its own translation unit
 template <class T, bool MOM> int launch_fam_march(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 template <class T, bool MOM> int launch_fam_along(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 template <class T, bool MOM> int launch_fam_along2(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 template <class T, bool MOM> int launch_fam_xsweep(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 template <class T, bool MOM> int launch_fam_xrow(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
+template <class T> int launch_fam_vofcell(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 // the row kernel moves two cells per access: rows must start vector-aligned (even row pitch) and so must every array
 template <class T> static bool xrow_ok(const ifadv_ctx* c, const SweepCfg<T>& q) {
   if (c->g.n[0] & 1) return false;
@@ -278,6 +314,9 @@ template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStrea
     return -2;
   }
   if constexpr (D == 3) {
+    if constexpr (!MOM) {
+      if (c->use_vofcell) return launch_fam_vofcell<T>(c, st, q);
+    }
     if (c->use_march == 1 && c->use_along2) {
       if (q.j != 0) return launch_fam_along2<T, MOM>(c, st, q);
       if (c->use_xrow && xrow_ok<T>(c, q)) return launch_fam_xrow<T, MOM>(c, st, q);
@@ -470,6 +509,17 @@ template <class T, bool MOM> int launch_fam_xrow(ifadv_ctx* c, cudaStream_t st, 
   }
 }
 template int launch_fam_xrow<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
+
+#elif IFADV_FAM == 6
+template <class T> int launch_fam_vofcell(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
+  const bool same = q.u == q.u0;
+  switch (q.j) {
+    case 0: return same ? launch_vofcell_t<T, 0, true>(c, st, q) : launch_vofcell_t<T, 0, false>(c, st, q);
+    case 1: return same ? launch_vofcell_t<T, 1, true>(c, st, q) : launch_vofcell_t<T, 1, false>(c, st, q);
+    default: return same ? launch_vofcell_t<T, 2, true>(c, st, q) : launch_vofcell_t<T, 2, false>(c, st, q);
+  }
+}
+template int launch_fam_vofcell<IFADV_T>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
 
 #endif
 

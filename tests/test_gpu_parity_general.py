@@ -483,3 +483,46 @@ def test_exit_bc_through_the_fused_entry_and_the_mirror(ia):
     torch.cuda.synchronize()
     assert np.array_equal(ia.to_numpy(f2), ia.to_numpy(fd))
     assert np.array_equal(inside(ia.to_numpy(d2["rhou"]), 3), inside(ia.to_numpy(d["rhou"]), 3))
+
+
+# ---- pure VOF, 3-D: the cell-parallel kernel (ifadv_vofcell.cuh, default) against the marching generation and the oracle ---------
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("N,kind,perdir,dirO", [((70, 40, 36), "C2", (), (1, 2, 3)), ((33, 18, 21), "C2", (1, 2, 3), (3, 1, 2)),
+                                                 ((40, 24, 20), "C3", (2,), (2, 3, 1)), ((36, 20, 12), "C4", (1, 3), (1, 2, 3))])
+def test_pure_vof_cell_kernel_matches_oracle_and_marching_kernels(ia, T, N, kind, perdir, dirO):
+    """advectVOF! with u⁰ ≠ u through both 3-D pure-VOF kernel generations: each within the north star's tolerance of the oracle
+    (f, ρuf on inside_uWB faces, c̄, status) and bit-identical to each other in Float64."""
+    import os
+    from interfaceadvection.jl_b200 import api
+    st = make_state(N, kind, T, perdir=perdir)
+    u0 = second_velocity(st, 3, 0.8, 0.05)
+    a = alloc_cmom(st)
+    f_o = st["f"].copy(order="F")
+    so, rep = O.advectVOF(f_o, a["ff"], a["alpha"], a["nhat"], u0, st["u"], 1.0, a["cbar"], a["rhouf"], st["lam_rho"], "WH", perdir, dirO)
+    res = {}
+    try:
+        for gen in (None, "lean"):
+            api._contexts.clear()
+            if gen is None:
+                os.environ.pop("IFADV_VOF_KERNEL", None)
+            else:
+                os.environ["IFADV_VOF_KERNEL"] = gen
+            d = _dev(ia, alloc_cmom(st))
+            fd, ud, u0d = ia.from_numpy(st["f"]), ia.from_numpy(st["u"]), ia.from_numpy(u0)
+            sc = ia.advectVOF(fd, d["ff"], d["alpha"], d["nhat"], u0d, ud, 1.0, d["cbar"], d["rhouf"], st["lam_rho"], "WH", perdir, dirO)
+            res[gen] = (sc, ia.to_numpy(fd), ia.to_numpy(d["rhouf"]), ia.to_numpy(d["cbar"]))
+    finally:
+        os.environ.pop("IFADV_VOF_KERNEL", None)
+        api._contexts.clear()
+    for gen, (sc, f_c, ruf_c, cb_c) in res.items():
+        assert sc == so, gen
+        assert np.abs(f_c - f_o).max() <= TOL[T], gen
+        for j in range(3):
+            sl = [slice(1, -1)] * 3; sl[j] = slice(1, None)
+            assert np.abs(ruf_c[tuple(sl) + (j,)] - a["rhouf"][tuple(sl) + (j,)]).max() <= TOL[T], (gen, j)
+        assert np.array_equal(inside(cb_c, 3), inside(a["cbar"], 3)), gen
+    if T == np.float64:
+        assert np.array_equal(res[None][1], res["lean"][1])
+        for j in range(3):
+            sl = [slice(1, -1)] * 3; sl[j] = slice(1, None)
+            assert np.array_equal(res[None][2][tuple(sl) + (j,)], res["lean"][2][tuple(sl) + (j,)])
