@@ -515,15 +515,7 @@ __global__ void __launch_bounds__(NT, MINB) along2_kernel(const SweepP<T> P, con
       rnan |= onan;
     }
     if ((tid & 31) == 0) {
-      if (rmax > -INFINITY) {
-        atomicMax(P.red + 0, ord_key((double)rmax));
-        atomicMax(P.red + 2, ((unsigned long long)ord_key32((float)rmax) << 32) | amax);
-      }
-      if (rmin < INFINITY) {
-        atomicMin(P.red + 1, ord_key((double)rmin));
-        atomicMin(P.red + 3, ((unsigned long long)ord_key32((float)rmin) << 32) | amin);
-      }
-      if (rnan) atomicAdd(P.red + 4, 1ull);
+      red_commit<T>(P.red, rmax, rmin, amax, amin, rnan);
     }
   }
 }

@@ -69,6 +69,23 @@ IFADV_DI unsigned int ord_key32(float v) {
   return (b < 0) ? (unsigned int)(~b) : ((unsigned int)b | 0x80000000u);
 }
 
+// Commit a warp's fill-error extrema.  Almost every warp ends with max = 1, min = 0 exactly, so look before issuing an atomic: tens of
+// thousands of warps hitting ONE address serialise at the L2 (measured on the pure-VOF sweep at 256³: 0.043 ms of a 0.17 ms launch).
+template <class T> IFADV_DI void red_commit(unsigned long long* red, T rmax, T rmin, unsigned amax, unsigned amin, int rnan) {
+  const volatile unsigned long long* vr = red;
+  if (rmax > -INFINITY) {
+    const unsigned long long k = ord_key((double)rmax), kp = ((unsigned long long)ord_key32((float)rmax) << 32) | amax;
+    if (k > vr[0]) atomicMax(red + 0, k);
+    if (kp > vr[2]) atomicMax(red + 2, kp);
+  }
+  if (rmin < INFINITY) {
+    const unsigned long long k = ord_key((double)rmin), kp = ((unsigned long long)ord_key32((float)rmin) << 32) | amin;
+    if (k < vr[1]) atomicMin(red + 1, k);
+    if (kp < vr[3]) atomicMin(red + 3, kp);
+  }
+  if (rnan) atomicAdd(red + 4, 1ull);
+}
+
 template <class T, int D> struct FMap {  // f with the BCf! ghost rule applied through the index map
   const T* f;
   Geo g;

@@ -273,8 +273,8 @@ template <class T, int J, bool SAMEU> static int launch_vofcell_t(ifadv_ctx* c, 
   }
   const int nx = c->g.n[0] - 2, ny = c->g.n[1] - 2, nz = c->g.n[2] - 2;
   const long long tiles = (long long)((nx + 31) / 32) * ((ny + 7) / 8);
-  int chunk = 16;
-  while (chunk > 4 && tiles * ((nz + chunk - 1) / chunk) < 148 * 16) chunk >>= 1;
+  int chunk = 32;  // 256³: 16 / 32 / 64 / 128 planes -> 0.378 / 0.337 / 0.340 / 0.48 ms per step (Float32)
+  while (chunk > 4 && tiles * ((nz + chunk - 1) / chunk) < 148 * 8) chunk >>= 1;
   if (const char* e = getenv("IFADV_CHUNK")) chunk = std::max(1, atoi(e));  // measurement override
   dim3 grid((unsigned)((nx + 31) / 32), (unsigned)((ny + 7) / 8), (unsigned)((nz + chunk - 1) / chunk));
   int sms = 148;
@@ -282,7 +282,15 @@ template <class T, int J, bool SAMEU> static int launch_vofcell_t(ifadv_ctx* c, 
   const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
   CU_CHECK(c, cudaMemsetAsync(c->st_cnt, 0, sizeof(unsigned), st));
   if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
-  vofcell_kernel<T, J, SAMEU><<<grid, 256, 0, st>>>(P, chunk, c->st_list, c->st_cnt, c->st_cap * 3);
+  // measurement switches: IFADV_VKB = planes loaded together (1, 2, 4), IFADV_VMB = resident CTAs asked of the compiler (4, 8)
+  static const int vkb = getenv("IFADV_VKB") ? atoi(getenv("IFADV_VKB")) : 4, vmb = getenv("IFADV_VMB") ? atoi(getenv("IFADV_VMB")) : 4;
+  auto go = [&](auto kern) { kern<<<grid, 256, 0, st>>>(P, chunk, c->st_list, c->st_cnt, c->st_cap * 3); };
+  if (vkb == 1 && vmb == 8) go(vofcell_kernel<T, J, SAMEU, 1, 8>);
+  else if (vkb == 2 && vmb == 8) go(vofcell_kernel<T, J, SAMEU, 2, 8>);
+  else if (vkb == 4 && vmb == 8) go(vofcell_kernel<T, J, SAMEU, 4, 8>);
+  else if (vkb == 1) go(vofcell_kernel<T, J, SAMEU, 1, 4>);
+  else if (vkb == 2) go(vofcell_kernel<T, J, SAMEU, 2, 4>);
+  else go(vofcell_kernel<T, J, SAMEU, 4, 4>);
   vofcell_fix_kernel<T, J, SAMEU><<<(unsigned)sms * 16, 128, 0, st>>>(P, c->st_list, c->st_cnt, c->st_cap * 3);
   if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_tag[c->prof_n] = (unsigned char)((2 * q.j) << 1); c->prof_n++; }
   c->launches += 2;

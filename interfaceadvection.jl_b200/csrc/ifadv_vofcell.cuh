@@ -99,33 +99,25 @@ template <class T> IFADV_DI void vof_reduce(const SweepP<T>& P, T rmax, T rmin, 
     if (omin < rmin) { rmin = omin; amin = oamin; }
     rnan |= onan;
   }
-  if ((threadIdx.x & 31) == 0) {
-    if (rmax > -INFINITY) {
-      atomicMax(P.red + 0, ord_key((double)rmax));
-      atomicMax(P.red + 2, ((unsigned long long)ord_key32((float)rmax) << 32) | amax);
-    }
-    if (rmin < INFINITY) {
-      atomicMin(P.red + 1, ord_key((double)rmin));
-      atomicMin(P.red + 3, ((unsigned long long)ord_key32((float)rmin) << 32) | amin);
-    }
-    if (rnan) atomicAdd(P.red + 4, 1ull);
-  }
+  if ((threadIdx.x & 31) == 0) red_commit<T>(P.red, rmax, rmin, amax, amin, rnan);
 }
 
-template <class T, int J, bool SAMEU>
-__global__ void __launch_bounds__(256) vofcell_kernel(const SweepP<T> P, const int chunk, int* __restrict__ list, unsigned* __restrict__ cnt,
-                                                      const unsigned cap) {
+// EDGE = false: every cell of the CTA's tile and both neighbours along the sweep are inside(f) and the tile is full -- no index maps,
+// no ghost upwind cells, no lane shadows (chosen per CTA; all but the outermost tiles).  KB: planes whose loads are issued together.
+template <class T, int J, bool SAMEU, bool EDGE, int KB>
+IFADV_DI void vofcell_body(const SweepP<T>& P, const int chunk, int* __restrict__ list, unsigned* __restrict__ cnt, const unsigned cap) {
   const Geo& g = P.g;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int xr = 2 + blockIdx.x * 32 + tx, yr = 2 + blockIdx.y * 8 + ty;
-  const bool ok = xr <= g.n[0] - 1 && yr <= g.n[1] - 1;
-  const int x = min(xr, g.n[0] - 1), y = min(yr, g.n[1] - 1);  // lanes beyond the grid shadow the last cell and store nothing
+  const bool ok = !EDGE || (xr <= g.n[0] - 1 && yr <= g.n[1] - 1);
+  const int x = EDGE ? min(xr, g.n[0] - 1) : xr, y = EDGE ? min(yr, g.n[1] - 1) : yr;  // lanes beyond the grid shadow the last cell
   const int k0 = 2 + blockIdx.z * chunk, k1 = min(k0 + chunk, g.n[2]);  // planes k0 .. k1-1
   const int nA = g.n[J];
   const bool perA = (g.per >> J) & 1u;
-  const long long sA = (J == 0) ? 1 : ((J == 1) ? g.s1 : g.s2);
+  const unsigned s1 = (unsigned)g.s1, s2 = (unsigned)g.s2;
+  const unsigned sA = (J == 0) ? 1u : ((J == 1) ? s1 : s2);
   const bool first = P.first != 0;
-  const T dt = P.dt;
+  const T dt = P.dt, hdt = P.hdt;
   const T* __restrict__ fin = P.f_in;
   const T* __restrict__ uj = P.uj;
   const T* __restrict__ u0j = P.u0j;
@@ -133,30 +125,40 @@ __global__ void __launch_bounds__(256) vofcell_kernel(const SweepP<T> P, const i
   unsigned int amax = 0, amin = 0;
   const int lane = threadIdx.x & 31;
 
-  const long long lxy = (long long)(x - 1) + g.s1 * (y - 1);
-  // J = 0, 1: the neighbour offsets along the sweep do not change with the plane
+  const unsigned lxy = (unsigned)(x - 1) + s1 * (unsigned)(y - 1);  // 32-bit element offsets (S < 2^31 is checked by the launcher)
+  // J = 0, 1: the neighbour offsets along the sweep and the ghost status of the upwind candidates do not change with the plane
   const int cJ01 = (J == 0) ? x : y;
-  const long long om = (J == 2) ? 0 : (long long)(map1(cJ01 - 1, nA, perA) - cJ01) * sA;
-  const long long op = (J == 2) ? 0 : (long long)(map1(cJ01 + 1, nA, perA) - cJ01) * sA;
+  const unsigned om = (J == 2 || !EDGE) ? (0u - sA) : (unsigned)(map1(cJ01 - 1, nA, perA) - cJ01) * sA;
+  const unsigned op = (J == 2 || !EDGE) ? sA : (unsigned)(map1(cJ01 + 1, nA, perA) - cJ01) * sA;
+  const bool gdn01 = EDGE && J != 2 && !perA && cJ01 - 1 < 2;       // lower neighbour is a ghost cell on a non-periodic side
+  const bool gup01 = EDGE && J != 2 && !perA && cJ01 + 1 > nA - 1;  // upper neighbour
   const int kup = perA ? 2 : nA - 1;  // J = 2: the plane that stands for plane nA (wrap / clamp)
-  // the values one plane needs
+  // flux through a face between the cells `flo | fhi`; glo / ghi: that cell is a ghost cell on a non-periodic side
+  auto face = [&](T usum, T flo, T fhi, bool glo, bool ghi) -> VFace<T> {
+    T dl = hdt * usum;
+    dl = (dl != T(0)) ? dl : T(0);
+    const bool up = dl > T(0);
+    const T fc = up ? flo : fhi;
+    const bool gho = EDGE && (up ? glo : ghi);
+    return VFace<T>{fc * dl, dl, dl != T(0) && !gho && !fullorempty(fc)};
+  };
   struct In { T fc, fm, fp, ulo, uhi, u0lo, u0hi; int cb; };
   auto load = [&](int k) -> In {
     In r;
-    const long long l = lxy + g.s2 * (k - 1);
+    const unsigned l = lxy + s2 * (unsigned)(k - 1);
     if (J == 2) {
-      r.fp = __ldg(fin + lxy + g.s2 * (((k + 1 <= nA - 1) ? k + 1 : kup) - 1));
-      r.uhi = __ldg(uj + l + g.s2);
-      r.u0hi = SAMEU ? r.uhi : __ldg(u0j + l + g.s2);
+      r.fp = __ldg(fin + (lxy + s2 * (unsigned)(((!EDGE || k + 1 <= nA - 1) ? k + 1 : kup) - 1)));
+      r.uhi = __ldg(uj + (l + s2));
+      r.u0hi = SAMEU ? r.uhi : __ldg(u0j + (l + s2));
       r.fc = r.fm = r.ulo = r.u0lo = T(0);  // rolled
     } else {
       r.fc = __ldg(fin + l);
-      r.fm = __ldg(fin + l + om);
-      r.fp = __ldg(fin + l + op);
+      r.fm = __ldg(fin + (l + om));
+      r.fp = __ldg(fin + (l + op));
       r.ulo = __ldg(uj + l);
-      r.uhi = __ldg(uj + l + sA);
+      r.uhi = __ldg(uj + (l + sA));
       r.u0lo = SAMEU ? r.ulo : __ldg(u0j + l);
-      r.u0hi = SAMEU ? r.uhi : __ldg(u0j + l + sA);
+      r.u0hi = SAMEU ? r.uhi : __ldg(u0j + (l + sA));
     }
     r.cb = first ? 0 : (int)P.cbar[l];
     return r;
@@ -165,16 +167,13 @@ __global__ void __launch_bounds__(256) vofcell_kernel(const SweepP<T> P, const i
   T fm = T(0), fc = T(0), ulo = T(0), u0lo = T(0);
   VFace<T> lo{T(0), T(0), false};
   if (J == 2) {
-    const long long l = lxy + g.s2 * (k0 - 1);
-    fm = __ldg(fin + lxy + g.s2 * (map1(k0 - 1, nA, perA) - 1));
+    const unsigned l = lxy + s2 * (unsigned)(k0 - 1);
+    fm = __ldg(fin + (lxy + s2 * (unsigned)(map1(k0 - 1, nA, perA) - 1)));
     fc = __ldg(fin + l);
     ulo = __ldg(uj + l);
     u0lo = SAMEU ? ulo : __ldg(u0j + l);
-    lo = vof_face<T, J, false>(P, ulo + u0lo, fm, fc, k0, x, y, k0);
+    lo = face(ulo + u0lo, fm, fc, !perA && k0 - 1 < 2, false);
   }
-  // blocks of KB planes: all loads of a block are in flight before its first value is used (a thread has no other way to cover the
-  // DRAM latency: there is no staging and only ~100 instructions of arithmetic per plane)
-  constexpr int KB = 4;
 #pragma unroll 1
   for (int kb = k0; kb < k1; kb += KB) {
     In in[KB];
@@ -184,16 +183,16 @@ __global__ void __launch_bounds__(256) vofcell_kernel(const SweepP<T> P, const i
     for (int i = 0; i < KB; ++i) {
       const int k = kb + i;
       if (k < k1) {  // block-uniform
-        const long long l = lxy + g.s2 * (k - 1);
+        const unsigned l = lxy + s2 * (unsigned)(k - 1);
         const In& cur = in[i];
         T fp = cur.fp, uhi = cur.uhi, u0hi = cur.u0hi;
         VFace<T> hi;
         if (J == 2) {
-          hi = vof_face<T, J, false>(P, uhi + u0hi, fc, fp, k + 1, x, y, k);
+          hi = face(uhi + u0hi, fc, fp, false, !perA && k + 1 > nA - 1);
         } else {
           fc = cur.fc; fm = cur.fm; ulo = cur.ulo; u0lo = cur.u0lo;
-          lo = vof_face<T, J, false>(P, ulo + u0lo, fm, fc, cJ01, x, y, k);
-          hi = vof_face<T, J, false>(P, uhi + u0hi, fc, fp, cJ01 + 1, x, y, k);
+          lo = face(ulo + u0lo, fm, fc, gdn01, false);
+          hi = face(uhi + u0hi, fc, fp, false, gup01);
         }
         const int cb = first ? ((fc < T(0.5)) ? 0 : 1) : cur.cb;  // advection.jl:40 (c̄ from the incoming f)
         if (first && ok) P.cbar[l] = (int8_t)cb;
@@ -201,7 +200,7 @@ __global__ void __launch_bounds__(256) vofcell_kernel(const SweepP<T> P, const i
         if (ok && !defer) {
           const T div = (uhi - ulo) + (u0hi - u0lo);  // ∂(d,I,u)+∂(d,I,u⁰)
           const T dv = ((cb ? div : T(0)) * dt) / T(2);
-          vof_cell_finish<T, J>(P, l, (J == 2) ? k : cJ01, fc, lo, hi, dv, rmax, rmin, amax, amin);
+          vof_cell_finish<T, J>(P, (long long)l, (J == 2) ? k : cJ01, fc, lo, hi, dv, rmax, rmin, amax, amin);
         }
         const unsigned m = __ballot_sync(0xffffffffu, defer);
         if (m) {
@@ -217,6 +216,20 @@ __global__ void __launch_bounds__(256) vofcell_kernel(const SweepP<T> P, const i
     }
   }
   vof_reduce<T>(P, rmax, rmin, amax, amin);
+}
+
+template <class T, int J, bool SAMEU, int KB, int MINB>
+__global__ void __launch_bounds__(256, MINB) vofcell_kernel(const SweepP<T> P, const int chunk, int* __restrict__ list, unsigned* __restrict__ cnt,
+                                                            const unsigned cap) {
+  const Geo& g = P.g;
+  const int ox = 2 + blockIdx.x * 32, oy = 2 + blockIdx.y * 8, k0 = 2 + blockIdx.z * chunk;
+  // the tile is full and neither it nor its neighbours along the sweep touch a ghost index
+  bool interior = ox + 31 <= g.n[0] - 1 && oy + 7 <= g.n[1] - 1;
+  if (J == 0) interior = interior && ox >= 3 && ox + 32 <= g.n[0] - 1;
+  if (J == 1) interior = interior && oy >= 3 && oy + 8 <= g.n[1] - 1;
+  if (J == 2) interior = interior && k0 >= 3 && k0 + chunk <= g.n[2] - 1;
+  if (interior) vofcell_body<T, J, SAMEU, false, KB>(P, chunk, list, cnt, cap);
+  else vofcell_body<T, J, SAMEU, true, KB>(P, chunk, list, cnt, cap);
 }
 
 // the deferred cells, lane-dense.  When the list overflowed every cell is examined again instead.

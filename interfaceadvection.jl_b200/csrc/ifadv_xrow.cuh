@@ -534,15 +534,7 @@ IFADV_DI void xrow_body(const SweepP<T>& P, const int chunk, unsigned char* smem
       rnan |= onan;
     }
     if (lane == 0) {
-      if (rmax > -INFINITY) {
-        atomicMax(P.red + 0, ord_key((double)rmax));
-        atomicMax(P.red + 2, ((unsigned long long)ord_key32((float)rmax) << 32) | amax);
-      }
-      if (rmin < INFINITY) {
-        atomicMin(P.red + 1, ord_key((double)rmin));
-        atomicMin(P.red + 3, ((unsigned long long)ord_key32((float)rmin) << 32) | amin);
-      }
-      if (rnan) atomicAdd(P.red + 4, 1ull);
+      red_commit<T>(P.red, rmax, rmin, amax, amin, rnan);
     }
   }
 }
