@@ -6,6 +6,7 @@
 // the Julia reference; perdir is a bit mask (bit j-1 set <=> j ∈ perdir).
 #include "oracle_flow.hpp"
 #include "oracle_forcing.hpp"
+#include "oracle_post.hpp"
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -255,6 +256,77 @@ int orc_update_u(int dtype, int D, const int64_t* Ng, void* u, void* rhou, void*
 int orc_update_l(int dtype, int D, const int64_t* Ng, void* mu0, void* f, double lr, unsigned perdir) {
   Grid g = make_grid(D, Ng);
   DISPATCH(dtype, { updateL<T>(g, VF<T>{(T*)mu0, &g}, SF<T>{(T*)f, &g}, (T)lr, perdir); });
+  return 0;
+}
+
+// ---- post-processing: src/redistaning.jl, src/metrics.jl ---------------------------------------------------------
+int orc_gradphi2(int dtype, double a, double b, double c, double d, double e, double s, double* out) {
+  DISPATCH(dtype, { *out = (double)gradphi2<T>((T)a, (T)b, (T)c, (T)d, (T)e, (T)s); });
+  return 0;
+}
+int orc_compute_l(int dtype, int D, const int64_t* Ng, void* L, void* phi, void* phi_ini, unsigned perdir) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, { computeL<T>(g, SF<T>{(T*)L, &g}, SF<T>{(T*)phi, &g}, SF<T>{(T*)phi_ini, &g}, perdir); });
+  return 0;
+}
+int orc_redist_stage(int dtype, int D, const int64_t* Ng, void* phi, void* phi0, void* phi_ini, void* L, double dtau, double alpha, unsigned perdir) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, { redistStage<T>(g, SF<T>{(T*)phi, &g}, SF<T>{(T*)phi0, &g}, SF<T>{(T*)phi_ini, &g}, SF<T>{(T*)L, &g}, (T)dtau, (T)alpha, perdir); });
+  return 0;
+}
+int orc_redistance(int dtype, int D, const int64_t* Ng, void* phi, void* phi0, void* phi_ini, void* L, double d, double dtau, unsigned perdir) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, { redistance<T>(g, SF<T>{(T*)phi, &g}, SF<T>{(T*)phi0, &g}, SF<T>{(T*)phi_ini, &g}, SF<T>{(T*)L, &g}, d, dtau, perdir); });
+  return 0;
+}
+// per-cell metrics (I 1-based; i 1-based; NULL tuples are zeros) and their sums over inside(f): out = [Σρke, Σρgh, Σρu_1..D]
+int orc_metrics_cell(int dtype, int D, const int64_t* Ng, void* u, void* f, double lr, const double* U, const double* grav, const double* statWL,
+                     const int64_t* I, double* out) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, {
+    T UU[3] = {0, 0, 0}, G[3] = {0, 0, 0}, W[3] = {0, 0, 0};
+    for (int i = 0; i < D; ++i) { if (U) UU[i] = (T)U[i]; if (grav) G[i] = (T)grav[i]; if (statWL) W[i] = (T)statWL[i]; }
+    const I3 II = mkI(D, I);
+    out[0] = rhokeI<T>(g, II, VF<T>{(T*)u, &g}, SF<T>{(T*)f, &g}, (T)lr, UU);
+    out[1] = (double)rhogh<T>(g, II, G, SF<T>{(T*)f, &g}, (T)lr, W);
+    for (int i = 0; i < D; ++i) out[2 + i] = rhouI<T>(g, i, II, VF<T>{(T*)u, &g}, SF<T>{(T*)f, &g}, (T)lr, UU);
+  });
+  return 0;
+}
+int orc_metrics_sum(int dtype, int D, const int64_t* Ng, void* u, void* f, double lr, const double* U, const double* grav, const double* statWL,
+                    double* out) {
+  Grid g = make_grid(D, Ng);
+  for (int k = 0; k < 5; ++k) out[k] = 0;
+  Range r = r_inside(g);
+  DISPATCH(dtype, {
+    T UU[3] = {0, 0, 0}, G[3] = {0, 0, 0}, W[3] = {0, 0, 0};
+    for (int i = 0; i < D; ++i) { if (U) UU[i] = (T)U[i]; if (grav) G[i] = (T)grav[i]; if (statWL) W[i] = (T)statWL[i]; }
+    VF<T> uu{(T*)u, &g};
+    SF<T> ff{(T*)f, &g};
+    for (int64_t k = r.lo[2]; k <= r.hi[2]; ++k)
+      for (int64_t j = r.lo[1]; j <= r.hi[1]; ++j)
+        for (int64_t i = r.lo[0]; i <= r.hi[0]; ++i) {
+          const I3 II{{i, j, k}};
+          out[0] += rhokeI<T>(g, II, uu, ff, (T)lr, UU);
+          out[1] += (double)rhogh<T>(g, II, G, ff, (T)lr, W);
+          for (int c = 0; c < D; ++c) out[2 + c] += rhouI<T>(g, c, II, uu, ff, (T)lr, UU);
+        }
+  });
+  return 0;
+}
+int orc_enstrophy(int dtype, int D, const int64_t* Ng, void* omega, const int64_t* I, double* cell, double* sum) {
+  Grid g = make_grid(D, Ng);
+  Range r = r_inside(g);
+  DISPATCH(dtype, {
+    if (I && cell) *cell = EnsI<T>(g, mkI(D, I), (const T*)omega);
+    if (sum) {
+      double s = 0;
+      for (int64_t k = r.lo[2]; k <= r.hi[2]; ++k)
+        for (int64_t j = r.lo[1]; j <= r.hi[1]; ++j)
+          for (int64_t i = r.lo[0]; i <= r.hi[0]; ++i) s += EnsI<T>(g, I3{{i, j, k}}, (const T*)omega);
+      *sum = s;
+    }
+  });
   return 0;
 }
 

@@ -90,6 +90,12 @@ inline Range r_slice(const Grid& g, int64_t i, int j, int64_t low = 1) {  // Wat
   return r;
 }
 
+inline bool inside_others(const Grid& g, const I3& I, int j) {  // I ∈ 2:n-1 in every dimension but j (slice(N,·,j,2) runs to n)
+  for (int d = 0; d < g.D; ++d)
+    if (d != j && I.i[d] > g.n[d] - 1) return false;
+  return true;
+}
+
 // `@loop body over I ∈ R` : every index independent (that is what lets the reference run the same
 // body as a GPU kernel), so the OpenMP build may parallelise each pass.
 template <class F>

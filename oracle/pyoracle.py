@@ -28,7 +28,7 @@ def build(force: bool = False) -> None:
     """Compile liboracle.so / liboracle_omp.so with the committed Makefile (g++ only, a few seconds)."""
     need = force or not all(os.path.exists(os.path.join(_HERE, n)) for n in ("liboracle.so", "liboracle_omp.so"))
     if not need:
-        srcs = [os.path.join(_HERE, n) for n in ("oracle.cpp", "oracle_core.hpp", "oracle_fields.hpp", "oracle_flow.hpp", "oracle_forcing.hpp")]
+        srcs = [os.path.join(_HERE, n) for n in ("oracle.cpp", "oracle_core.hpp", "oracle_fields.hpp", "oracle_flow.hpp", "oracle_forcing.hpp", "oracle_post.hpp")]
         newest = max(os.path.getmtime(s) for s in srcs)
         need = any(os.path.getmtime(os.path.join(_HERE, n)) < newest for n in ("liboracle.so", "liboracle_omp.so"))
     if need:
@@ -299,6 +299,60 @@ def updateL(mu0, f, lam_rho, perdir=(), omp=False):
     """updateL!(μ₀,f,λρ;perdir) (flow.jl:254-259)."""
     D, ng = _ng(f)
     lib(omp).orc_update_l(_dt(f), D, ng, _p(mu0), _p(f), C.c_double(lam_rho), mask(perdir))
+
+
+# ---- post-processing (SURVEY §8f row 4): level-set redistancing and metrics ------------------------------------------------------------
+def gradphi2(a, b, c, d, e, s, dtype=np.float64) -> float:
+    """𝛁ϕᵢ²(a,b,c,d,e,s) (redistaning.jl:119-143)."""
+    out = C.c_double()
+    lib().orc_gradphi2(0 if np.dtype(dtype) == np.float32 else 1, *(C.c_double(float(v)) for v in (a, b, c, d, e, s)), C.byref(out))
+    return out.value
+
+
+def computeL(L, phi, phi_ini, perdir=()):
+    """computeL!(L,ϕ,ϕini;perdir) (redistaning.jl:67-87)."""
+    D, ng = _ng(phi)
+    lib().orc_compute_l(_dt(phi), D, ng, _p(L), _p(phi), _p(phi_ini), mask(perdir))
+
+
+def redistaningStage(phi, phi0, phi_ini, L, dtau, alpha, perdir=()):
+    """_redistaningStage!(ϕ,ϕ⁰,ϕini,L,dτ,α;perdir) (redistaning.jl:31-34)."""
+    D, ng = _ng(phi)
+    lib().orc_redist_stage(_dt(phi), D, ng, _p(phi), _p(phi0), _p(phi_ini), _p(L), C.c_double(dtau), C.c_double(alpha), mask(perdir))
+
+
+def redistaning(phi, phi0, phi_ini, L, d=5, dtau=0.5, perdir=(), omp=False):
+    """redistaning!(ls; d, dτ, perdir) (redistaning.jl:44-57) on the LevelSet arrays."""
+    D, ng = _ng(phi)
+    lib(omp).orc_redistance(_dt(phi), D, ng, _p(phi), _p(phi0), _p(phi_ini), _p(L), C.c_double(d), C.c_double(dtau), mask(perdir))
+
+
+def _t3(v, D):
+    return None if v is None else (C.c_double * 3)(*(list(map(float, v))[:D] + [0.0] * (3 - D)))
+
+
+def metrics_cell(I, u, f, lam_rho, U=None, g=None, statWL=None):
+    """(ρkeI, ρgh, [ρuI(i) for i in 1:D]) at cell I (metrics.jl:15,25,49)."""
+    D, ng = _ng(f)
+    out = (C.c_double * 5)()
+    lib().orc_metrics_cell(_dt(f), D, ng, _p(u), _p(f), C.c_double(lam_rho), _t3(U, D), _t3(g, D), _t3(statWL, D), _i3(I), out)
+    return out[0], out[1], [out[2 + i] for i in range(D)]
+
+
+def metrics_sum(u, f, lam_rho, U=None, g=None, statWL=None):
+    """Σ over inside(f) of ρkeI, ρgh, ρuI(i)."""
+    D, ng = _ng(f)
+    out = (C.c_double * 5)()
+    lib().orc_metrics_sum(_dt(f), D, ng, _p(u), _p(f), C.c_double(lam_rho), _t3(U, D), _t3(g, D), _t3(statWL, D), out)
+    return out[0], out[1], [out[2 + i] for i in range(D)]
+
+
+def enstrophy(omega, D, I=None):
+    """EnsI at cell I (if given) and Σ EnsI over the inside cells (metrics.jl:34-41); ω: (…,3) in 3-D, scalar field in 2-D."""
+    ng = (C.c_int64 * 3)(*(list(omega.shape[:D]) + [1] * (3 - D)))
+    cell, tot = C.c_double(), C.c_double()
+    lib().orc_enstrophy(_dt(omega), D, ng, _p(omega), _i3(I) if I is not None else None, C.byref(cell), C.byref(tot))
+    return (cell.value if I is not None else None), tot.value
 
 
 def num_threads(omp=True) -> int:
