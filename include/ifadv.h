@@ -159,6 +159,24 @@ int ifadv_update_u(ifadv_ctx* ctx, void* stream, void* u, void* rhou, const void
  *   fill_one != 0 folds the fill!(a.μ₀,1) that precedes it in MPFMomStep! (flow.jl:73,96) into the same pass. */
 int ifadv_update_l(ifadv_ctx* ctx, void* stream, void* mu0, const void* f, double lambda_rho, unsigned perdir_mask, int fill_one);
 
+/* ---- post-processing (single-GPU contexts) ---------------------------------------------------------------
+ * LevelSet(sim): ϕ = 2f-1, ϕini = ϕ over all entries                               src/redistaning.jl:8-29 (ϕ≡f⁰, ϕ⁰≡α, ϕini≡fᶠ, L≡σ) */
+int ifadv_levelset_init(ifadv_ctx* ctx, void* stream, void* phi, void* phi_ini, const void* f);
+/* computeL!(L,ϕ,ϕini;perdir): L = ϕini·(1-|∇ϕ|) on inside(ϕ), second-order ENO one-sided differences    src/redistaning.jl:67-143 */
+int ifadv_redist_compute_l(ifadv_ctx* ctx, void* stream, void* L, const void* phi, const void* phi_ini, unsigned perdir_mask);
+/* _redistaningStage!(ϕ,ϕ⁰,ϕini,L,dτ,α;perdir): computeL!; ϕ ← αϕ⁰+(1-α)(ϕ+dτL) on inside(ϕ)              src/redistaning.jl:31-34 */
+int ifadv_redist_stage(ifadv_ctx* ctx, void* stream, void* phi, const void* phi0, const void* phi_ini, void* L, double dtau, double alpha,
+                       unsigned perdir_mask);
+/* redistaning!(ls; d, dτ, perdir): round(d/dτ) third-order SSP Runge-Kutta steps, BCf! after every stage       src/redistaning.jl:44-57 */
+int ifadv_redistance(ifadv_ctx* ctx, void* stream, void* phi, void* phi0, const void* phi_ini, void* L, double d, double dtau,
+                     unsigned perdir_mask);
+/* Σ over inside(f) of ρkeI (out[0]), ρgh (out[1]) and ρuI(i) (out[2..]) accumulated in Float64                 src/metrics.jl:15-17,25,49-51
+ * U (background flow), g (gravity tuple), statWL: constant tuples, NULL = zeros.  Synchronises the stream. */
+int ifadv_metrics(ifadv_ctx* ctx, void* stream, const void* u, const void* f, double lambda_rho, const double U[3], const double g[3],
+                  const double statWL[3], double out[5]);
+/* Σ EnsI(I,ω) over the inside cells; ω: vector field in 3-D, scalar field in 2-D                              src/metrics.jl:34-41 */
+int ifadv_enstrophy(ifadv_ctx* ctx, void* stream, const void* omega, double* out);
+
 /* Stream overlap aid for MPFMomStep! (src/flow.jl:74,89): the midpoint f⁰=(f⁰+f)/2 and the copy f⁰<-f only READ the f that the
  * corrector's advectfq! is about to advance, and that call does not write f before its last directional sweep.  A caller that
  * runs those two field operations on a second stream records an event behind them and passes it here; the NEXT

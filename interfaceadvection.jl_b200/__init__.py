@@ -10,4 +10,5 @@ from .api import (  # noqa: F401
     BC, BCf, MPCFL, MPFMomStep, Flow, TwoPhaseSimulation, advect, advectVOF, advectVOFrhouu, advectfq, applyVOF, cVOF,
     from_numpy, jl_empty, mom_advect_step, u2rhou_advectfq, jl_zeros, rhou2u, sim_step, sim_time, sum_inside, to_numpy, u2rhou, context_for,
     viscSurfTenrhou, updateU, updateL, mom_step_forcing,
+    LevelSet, computeL, redistaningStage, redistaning, metrics, enstrophy,
 )

@@ -64,6 +64,12 @@ def lib():
         L.ifadv_visc_surften_rhou.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, dbl, dbl, dbl, u32]
         L.ifadv_update_u.argtypes = [vp, vp, vp, vp, vp, vp, dbl, vp, dbl, dblp, dbl]
         L.ifadv_update_l.argtypes = [vp, vp, vp, vp, dbl, u32, i32]
+        L.ifadv_levelset_init.argtypes = [vp, vp, vp, vp, vp]
+        L.ifadv_redist_compute_l.argtypes = [vp, vp, vp, vp, vp, u32]
+        L.ifadv_redist_stage.argtypes = [vp, vp, vp, vp, vp, vp, dbl, dbl, u32]
+        L.ifadv_redistance.argtypes = [vp, vp, vp, vp, vp, vp, dbl, dbl, u32]
+        L.ifadv_metrics.argtypes = [vp, vp, vp, vp, dbl, dblp, dblp, dblp, dblp]
+        L.ifadv_enstrophy.argtypes = [vp, vp, vp, dblp]
         L.ifadv_check_nan.argtypes = [vp, vp]
         L.ifadv_create_slab.argtypes = [C.POINTER(vp), i64p, i32, i32, vp, i32, i32, i32, i32]
         L.ifadv_slab_info.argtypes = [vp, i32p, i32p, i32p, i32p, i64p]
@@ -224,6 +230,30 @@ class Context:
 
     def update_l(self, stream, mu0, f, lam_rho, perdir, fill_one=False):
         return self._chk(lib().ifadv_update_l(self._h, stream, mu0, f, float(lam_rho), perdir_mask(perdir), int(bool(fill_one))))
+
+    def levelset_init(self, stream, phi, phi_ini, f):
+        return self._chk(lib().ifadv_levelset_init(self._h, stream, phi, phi_ini, f))
+
+    def redist_compute_l(self, stream, L, phi, phi_ini, perdir):
+        return self._chk(lib().ifadv_redist_compute_l(self._h, stream, L, phi, phi_ini, perdir_mask(perdir)))
+
+    def redist_stage(self, stream, phi, phi0, phi_ini, L, dtau, alpha, perdir):
+        return self._chk(lib().ifadv_redist_stage(self._h, stream, phi, phi0, phi_ini, L, float(dtau), float(alpha), perdir_mask(perdir)))
+
+    def redistance(self, stream, phi, phi0, phi_ini, L, d, dtau, perdir):
+        return self._chk(lib().ifadv_redistance(self._h, stream, phi, phi0, phi_ini, L, float(d), float(dtau), perdir_mask(perdir)))
+
+    def metrics(self, stream, u, f, lam_rho, U=None, g=None, statWL=None):
+        """(Σρke, Σρgh, [Σρu_i]) over inside(f) (ifadv_metrics)."""
+        out = (C.c_double * 5)()
+        t3 = lambda v: None if v is None else _d3(v, self.D)
+        self._chk(lib().ifadv_metrics(self._h, stream, u, f, float(lam_rho), t3(U), t3(g), t3(statWL), out))
+        return out[0], out[1], [out[2 + i] for i in range(self.D)]
+
+    def enstrophy(self, stream, omega) -> float:
+        out = C.c_double()
+        self._chk(lib().ifadv_enstrophy(self._h, stream, omega, C.byref(out)))
+        return out.value
 
     def defer_f_writes_until(self, event):
         """One-shot: the next CMOM advect call waits for `event` (cudaEvent_t handle) before its first write to f."""

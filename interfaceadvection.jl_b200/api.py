@@ -463,6 +463,41 @@ def mom_step_forcing(a: Flow, c: cVOF, dt=None, project: Optional[Callable] = No
         BC(a.u, a.uBC, a.exitBC, a.perdir)
 
 
+# ---- post-processing --------------------------------------------------------------------------------------------
+class LevelSet:
+    """LevelSet(sim) (src/redistaning.jl:8-29): ϕ = 2f-1 in sim.intf.f⁰'s storage, ϕ⁰ ≡ α, ϕini ≡ fᶠ, L ≡ flow.σ -- no extra memory."""
+
+    def __init__(self, sim: TwoPhaseSimulation):
+        c, a = sim.intf, sim.flow
+        self.phi, self.phi0, self.phi_ini, self.L, self.perdir = c.f0, c.alpha, c.ff, a.sigma, tuple(c.perdir)
+        context_for(c.f).levelset_init(_stream(c.f), _p(self.phi), _p(self.phi_ini), _p(c.f))
+
+
+def computeL(L, phi, phi_ini, perdir=()):
+    """computeL!(L,ϕ,ϕini;perdir) (src/redistaning.jl:67-87)."""
+    return context_for(phi).redist_compute_l(_stream(phi), _p(L), _p(phi), _p(phi_ini), perdir)
+
+
+def redistaningStage(phi, phi0, phi_ini, L, dtau, alpha, perdir=()):
+    """_redistaningStage!(ϕ,ϕ⁰,ϕini,L,dτ,α;perdir) (src/redistaning.jl:31-34)."""
+    return context_for(phi).redist_stage(_stream(phi), _p(phi), _p(phi0), _p(phi_ini), _p(L), dtau, alpha, perdir)
+
+
+def redistaning(ls: LevelSet, d=5, dtau=0.5, perdir=()):
+    """redistaning!(ls; d, dτ, perdir) (src/redistaning.jl:44-57)."""
+    return context_for(ls.phi).redistance(_stream(ls.phi), _p(ls.phi), _p(ls.phi0), _p(ls.phi_ini), _p(ls.L), d, dtau, perdir)
+
+
+def metrics(u, f, lam_rho, U=None, g=None, statWL=None):
+    """Σ over inside(f) of ρkeI, ρgh and ρuI(i) (src/metrics.jl:15-17,25,49-51): (kinetic energy, potential energy, momentum[D])."""
+    return context_for(f).metrics(_stream(f), _p(u), _p(f), lam_rho, U, g, statWL)
+
+
+def enstrophy(omega, f):
+    """Σ EnsI(I,ω) over the inside cells (src/metrics.jl:34-41); f only selects the context (grid, dtype)."""
+    return context_for(f).enstrophy(_stream(f), _p(omega))
+
+
 def MPFMomStep(a: Flow, b, c: cVOF, d=None, dt=None, project: Optional[Callable] = None, check=False, forcing=False):
     """Transport part of MPFMomStep!(a,b,c,d)  (src/flow.jl:60-109).
 

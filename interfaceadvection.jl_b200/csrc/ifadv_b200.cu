@@ -17,6 +17,7 @@
 #include "../../include/ifadv.h"
 #include "ifadv_ctx.hpp"
 #include "ifadv_forcing.cuh"
+#include "ifadv_post.cuh"
 
 using namespace ifadv;
 
@@ -1537,3 +1538,134 @@ int ifadv_host_step_bytes(const ifadv_ctx* c, int64_t* h2d, int64_t* d2h, int* s
 }
 
 }  // extern "C"
+
+// ---- post-processing (ifadv_post.cuh) ------------------------------------------------------------------------------------------------
+template <class T> static int redist_l_t(ifadv_ctx* c, cudaStream_t st, T* L, const T* phi, const T* pini, unsigned per) {
+  Geo g = c->g;
+  g.per = per;
+  const int bx = 128;
+  const dim3 gi = row_grid(g, c->D, bx);
+  if (c->D == 2) redist_l_kernel<T, 2><<<gi, bx, 0, st>>>(L, phi, pini, g);
+  else redist_l_kernel<T, 3><<<gi, bx, 0, st>>>(L, phi, pini, g);
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+template <class T>
+static int redist_stage_t(ifadv_ctx* c, cudaStream_t st, T* phi, const T* phi0, const T* pini, T* L, double dtau, double alpha, unsigned per) {
+  int rc = redist_l_t<T>(c, st, L, phi, pini, per);
+  if (rc) return rc;
+  const int bx = 128;
+  const dim3 gi = row_grid(c->g, c->D, bx);
+  if (c->D == 2) redist_stage_kernel<T, 2><<<gi, bx, 0, st>>>(phi, phi0, L, c->g, (T)dtau, (T)alpha);
+  else redist_stage_kernel<T, 3><<<gi, bx, 0, st>>>(phi, phi0, L, c->g, (T)dtau, (T)alpha);
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+template <class T>
+static int redistance_t(ifadv_ctx* c, cudaStream_t st, T* phi, T* phi0, const T* pini, T* L, double d, double dtau, unsigned per) {
+  const int itmx = (int)std::nearbyint(d / dtau);  // round(T, d/dτ), redistaning.jl:46
+  const double al[3] = {0.0, 3.0 / 4, 1.0 / 3};    // third-order SSP Runge-Kutta (Shu-Osher), :49-54
+  for (int it = 0; it < itmx; ++it) {
+    CU_CHECK(c, cudaMemcpyAsync(phi0, phi, sizeof(T) * (size_t)c->g.S, cudaMemcpyDeviceToDevice, st));
+    for (int s = 0; s < 3; ++s) {
+      int rc = redist_stage_t<T>(c, st, phi, phi0, pini, L, dtau, (double)(T)al[s], per);
+      if (rc) return rc;
+      if ((rc = launch_bcf<T>(c, st, phi, per))) return rc;
+    }
+  }
+  return 0;
+}
+
+extern "C" {
+int ifadv_levelset_init(ifadv_ctx* c, void* stream, void* phi, void* phi_ini, const void* f) {
+  if (!c) return -2;
+  if (!phi || !phi_ini || !f) return fail(c, -2, "null array");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = c->g.S;
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  if (c->dtype == IFADV_F32) levelset_kernel<float><<<nb, 256, 0, st>>>((float*)phi, (float*)phi_ini, (const float*)f, n);
+  else levelset_kernel<double><<<nb, 256, 0, st>>>((double*)phi, (double*)phi_ini, (const double*)f, n);
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+int ifadv_redist_compute_l(ifadv_ctx* c, void* stream, void* L, const void* phi, const void* phi_ini, unsigned perdir_mask) {
+  if (!c) return -2;
+  if (c->slab.nranks > 1) return fail(c, -2, "the post-processing entry points are single-GPU");
+  if (!L || !phi || !phi_ini) return fail(c, -2, "null array");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->dtype == IFADV_F32) return redist_l_t<float>(c, st, (float*)L, (const float*)phi, (const float*)phi_ini, perdir_mask);
+  return redist_l_t<double>(c, st, (double*)L, (const double*)phi, (const double*)phi_ini, perdir_mask);
+}
+int ifadv_redist_stage(ifadv_ctx* c, void* stream, void* phi, const void* phi0, const void* phi_ini, void* L, double dtau, double alpha,
+                       unsigned perdir_mask) {
+  if (!c) return -2;
+  if (c->slab.nranks > 1) return fail(c, -2, "the post-processing entry points are single-GPU");
+  if (!L || !phi || !phi0 || !phi_ini) return fail(c, -2, "null array");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->dtype == IFADV_F32)
+    return redist_stage_t<float>(c, st, (float*)phi, (const float*)phi0, (const float*)phi_ini, (float*)L, dtau, alpha, perdir_mask);
+  return redist_stage_t<double>(c, st, (double*)phi, (const double*)phi0, (const double*)phi_ini, (double*)L, dtau, alpha, perdir_mask);
+}
+int ifadv_redistance(ifadv_ctx* c, void* stream, void* phi, void* phi0, const void* phi_ini, void* L, double d, double dtau,
+                     unsigned perdir_mask) {
+  if (!c) return -2;
+  if (c->slab.nranks > 1) return fail(c, -2, "the post-processing entry points are single-GPU");
+  if (!L || !phi || !phi0 || !phi_ini) return fail(c, -2, "null array");
+  if (!(dtau > 0.0) || !(d >= 0.0)) return fail(c, -2, "invalid pseudo-time step");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->dtype == IFADV_F32) return redistance_t<float>(c, st, (float*)phi, (float*)phi0, (const float*)phi_ini, (float*)L, d, dtau, perdir_mask);
+  return redistance_t<double>(c, st, (double*)phi, (double*)phi0, (const double*)phi_ini, (double*)L, d, dtau, perdir_mask);
+}
+int ifadv_metrics(ifadv_ctx* c, void* stream, const void* u, const void* f, double lambda_rho, const double U[3], const double g[3],
+                  const double statWL[3], double out[5]) {
+  if (!c || !out) return -2;
+  if (c->slab.nranks > 1) return fail(c, -2, "the post-processing entry points are single-GPU");
+  if (!u || !f) return fail(c, -2, "null array");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU_CHECK(c, cudaMemsetAsync(c->misc_dev, 0, sizeof(unsigned long long) * 8, st));
+  const long long rows_ = (long long)(c->g.n[1] - 2) * (c->D == 3 ? c->g.n[2] - 2 : 1);
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((rows_ + 7) / 8, 148LL * 8));
+  double* acc = reinterpret_cast<double*>(c->misc_dev);
+  double UU[3] = {0, 0, 0}, G[3] = {0, 0, 0}, W[3] = {0, 0, 0};
+  for (int i = 0; i < c->D; ++i) { if (U) UU[i] = U[i]; if (g) G[i] = g[i]; if (statWL) W[i] = statWL[i]; }
+  if (c->dtype == IFADV_F32) {
+    if (c->D == 2) metrics_kernel<float, 2><<<grid, 256, 0, st>>>((const float*)u, (const float*)f, c->g, (float)lambda_rho, (float)UU[0], (float)UU[1], (float)UU[2], (float)G[0], (float)G[1], (float)G[2], (float)W[0], (float)W[1], (float)W[2], acc);
+    else metrics_kernel<float, 3><<<grid, 256, 0, st>>>((const float*)u, (const float*)f, c->g, (float)lambda_rho, (float)UU[0], (float)UU[1], (float)UU[2], (float)G[0], (float)G[1], (float)G[2], (float)W[0], (float)W[1], (float)W[2], acc);
+  } else {
+    if (c->D == 2) metrics_kernel<double, 2><<<grid, 256, 0, st>>>((const double*)u, (const double*)f, c->g, lambda_rho, UU[0], UU[1], UU[2], G[0], G[1], G[2], W[0], W[1], W[2], acc);
+    else metrics_kernel<double, 3><<<grid, 256, 0, st>>>((const double*)u, (const double*)f, c->g, lambda_rho, UU[0], UU[1], UU[2], G[0], G[1], G[2], W[0], W[1], W[2], acc);
+  }
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  CU_CHECK(c, cudaMemcpyAsync(c->misc_host, c->misc_dev, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
+  CU_CHECK(c, cudaStreamSynchronize(st));
+  memcpy(out, c->misc_host, sizeof(double) * 5);
+  return 0;
+}
+int ifadv_enstrophy(ifadv_ctx* c, void* stream, const void* omega, double* out) {
+  if (!c || !out) return -2;
+  if (c->slab.nranks > 1) return fail(c, -2, "the post-processing entry points are single-GPU");
+  if (!omega) return fail(c, -2, "null array");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU_CHECK(c, cudaMemsetAsync(c->misc_dev, 0, sizeof(unsigned long long) * 8, st));
+  const long long rows_ = (long long)(c->g.n[1] - 2) * (c->D == 3 ? c->g.n[2] - 2 : 1);
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((rows_ + 7) / 8, 148LL * 8));
+  double* acc = reinterpret_cast<double*>(c->misc_dev);
+  if (c->dtype == IFADV_F32) {
+    if (c->D == 2) enstrophy_kernel<float, 2><<<grid, 256, 0, st>>>((const float*)omega, c->g, acc);
+    else enstrophy_kernel<float, 3><<<grid, 256, 0, st>>>((const float*)omega, c->g, acc);
+  } else {
+    if (c->D == 2) enstrophy_kernel<double, 2><<<grid, 256, 0, st>>>((const double*)omega, c->g, acc);
+    else enstrophy_kernel<double, 3><<<grid, 256, 0, st>>>((const double*)omega, c->g, acc);
+  }
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  CU_CHECK(c, cudaMemcpyAsync(c->misc_host, c->misc_dev, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
+  CU_CHECK(c, cudaStreamSynchronize(st));
+  memcpy(out, c->misc_host, sizeof(double));
+  return 0;
+}
+}  // extern "C" (post-processing)

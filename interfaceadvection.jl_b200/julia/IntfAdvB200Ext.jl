@@ -20,6 +20,7 @@ using InterfaceAdvection
 import Random
 import InterfaceAdvection: advectVOF!, advectVOFρuu!, u2ρu!, ρu2u!, MPCFL, _scalar_op, cVOF
 import InterfaceAdvection: viscSurfTenρu!, updateU!, updateL!
+import InterfaceAdvection: LevelSet, redistaning!, computeL!, _redistaningStage!
 import InterfaceAdvection: getInterfaceNormal_WH!, getInterfaceNormal_WY!, getInterfaceNormal_Column!, getInterfaceNormal_PCD!,
                            getInterfaceNormal_SLIC!, getInterfaceNormal_MYC!, getInterfaceNormal_Y!, getInterfaceNormal_CD!,
                            getInterfaceNormal_XYLIC!
@@ -168,6 +169,35 @@ function updateL!(μ₀::CuArray{T}, f::CuArray{T}, λρ; perdir=()) where {T<:U
     ctx = context(f)
     check(ctx, ccall((:ifadv_update_l, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cuint, Cint),
                      ctx, stream_ptr(), dptr(μ₀), dptr(f), λρ, perdir_mask(perdir), 0)); nothing
+end
+
+# ---- post-processing: level-set redistancing (src/redistaning.jl:31-87) and metric sums (src/metrics.jl) ---------------------------
+function computeL!(L::CuArray{T}, ϕ::CuArray{T}, ϕini; perdir=()) where {T<:Union{Float32,Float64}}
+    ctx = context(ϕ)
+    check(ctx, ccall((:ifadv_redist_compute_l, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cuint),
+                     ctx, stream_ptr(), dptr(L), dptr(ϕ), dptr(ϕini), perdir_mask(perdir))); nothing
+end
+function _redistaningStage!(ϕ::CuArray{T}, ϕ⁰, ϕini, L, dτ, α; perdir=()) where {T<:Union{Float32,Float64}}
+    ctx = context(ϕ)
+    check(ctx, ccall((:ifadv_redist_stage, LIB), Cint,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Cuint),
+                     ctx, stream_ptr(), dptr(ϕ), dptr(ϕ⁰), dptr(ϕini), dptr(L), dτ, α, perdir_mask(perdir))); nothing
+end
+function redistaning!(ls::LevelSet{D,T,<:CuArray}; d=5, dτ=0.5, perdir=()) where {D,T<:Union{Float32,Float64}}
+    ctx = context(ls.ϕ)
+    check(ctx, ccall((:ifadv_redistance, LIB), Cint,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Cuint),
+                     ctx, stream_ptr(), dptr(ls.ϕ), dptr(ls.ϕ⁰), dptr(ls.ϕini), dptr(ls.L), d, dτ, perdir_mask(perdir))); nothing
+end
+"""Σ over inside(f) of ρkeI, ρgh, ρuI(i) (src/metrics.jl:15-17,25,49-51) in one device pass: (ke, pe, momentum::NTuple{D})."""
+function metric_sums(u::CuArray{T}, f::CuArray{T,D}, λρ; U=ntuple(_ -> 0.0, D), g=ntuple(_ -> 0.0, D), StatWL=ntuple(_ -> 0.0, D)) where {T<:Union{Float32,Float64},D}
+    ctx = context(f)
+    out = zeros(Cdouble, 5)
+    pad(v) = Cdouble[v...; zeros(3 - D)]
+    check(ctx, ccall((:ifadv_metrics, LIB), Cint,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                     ctx, stream_ptr(), dptr(u), dptr(f), λρ, pad(U), pad(g), pad(StatWL), out))
+    out[1], out[2], ntuple(i -> out[2 + i], D)
 end
 
 # ---- MPFMomStep!  (src/flow.jl:60-109) with the transport half on the fused entry points ---------------------------------------
