@@ -12,3 +12,4 @@ from .api import (  # noqa: F401
     viscSurfTenrhou, updateU, updateL, mom_step_forcing,
     LevelSet, computeL, redistaningStage, redistaning, metrics, enstrophy,
 )
+from . import vtkio  # noqa: F401,E402  (load! / save of VTK restart files, ext/IntfAdvReadVTKExt.jl)

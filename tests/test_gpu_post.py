@@ -99,3 +99,36 @@ def test_metrics_reference_kat_on_the_device(ia):  # test/maintests.jl:321-345 w
     assert ke == pytest.approx(ke_o) and mom == pytest.approx(mom_o)
     kc, _, mc = O.metrics_cell((2, 2), u, f, 0.2)
     assert kc == pytest.approx(4.5) and mc[0] == pytest.approx(0.9) and mc[1] == pytest.approx(2.1)
+
+
+@pytest.mark.parametrize("T,N,perdir", [(torch.float32, (20, 14, 10), (1,)), (torch.float64, (24, 16), ())])
+def test_vtk_restart_round_trip(ia, tmp_path, T, N, perdir):
+    """load!(sim, Val(:pvd)) (ext/IntfAdvReadVTKExt.jl:29-50) through the mirror: a run is saved as a `.pvd` collection of `.vti`
+    datasets (WriteVTK's default layout) and a fresh simulation restarted from the LAST dataset continues bit-identically."""
+    D = len(N)
+    sdf = lambda x: 0.3 * N[0] - ((x - 0.45 * N[0]) ** 2).sum(-1).sqrt()
+    mk = lambda: ia.TwoPhaseSimulation(N, (0,) * D, float(N[0]), T=T, InterfaceSDF=sdf, perdir=perdir, U=1.0, dt=0.3)
+    sim = mk()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    sim.flow.u.copy_(0.2 * torch.randn(sim.flow.u.shape, generator=g, device="cuda", dtype=T).to(sim.flow.u.dtype))
+    ia.BC(sim.flow.u, sim.flow.uBC, False, perdir)
+    fn = str(tmp_path / "WaterLily.pvd")
+    ia.vtkio.save(sim, fn, t=0.0)
+    ia.mom_advect_step(sim.flow, sim.intf, 0.3); sim.flow.dt.append(0.3)
+    ia.vtkio.save(sim, fn, t=0.3)
+    f1, u1 = ia.to_numpy(sim.intf.f).copy(), ia.to_numpy(sim.flow.u).copy()
+    ts, files = ia.vtkio.read_pvd(fn)
+    assert ts == [0.0, 0.3] and len(files) == 2
+    sim2 = mk()
+    t = ia.vtkio.load(sim2, fn)
+    assert t == pytest.approx(0.3 * sim2.L / sim2.U)
+    assert np.array_equal(ia.to_numpy(sim2.intf.f), f1) and np.array_equal(ia.to_numpy(sim2.flow.u), u1)
+    assert sim2.flow.dt[-2] == pytest.approx(t)
+    # the restarted simulation steps on exactly like the original (same sweep order: give both the same Δt history length)
+    sim2.flow.dt[:] = list(sim.flow.dt)
+    ia.mom_advect_step(sim.flow, sim.intf, 0.3); ia.mom_advect_step(sim2.flow, sim2.intf, 0.3)
+    assert np.array_equal(ia.to_numpy(sim2.intf.f), ia.to_numpy(sim.intf.f))
+    # a file of another size is refused like the reference's @assert
+    other = ia.TwoPhaseSimulation(tuple(n + 2 for n in N), (0,) * D, float(N[0]), T=T, perdir=perdir)
+    with pytest.raises(ValueError):
+        ia.vtkio.load(other, fn)
