@@ -597,8 +597,8 @@ static int advect_vof_t(ifadv_ctx* c, cudaStream_t st, T* f, T* ff, T* al, const
   const int D = c->D;
   c->g.per = per;
   const bool want_rhouf = !(flags & IFADV_NO_RHOUF) && rhouf != nullptr;
-  if (D == 2 && c->use_march != 0 && (long long)(c->g.n[0] - 2) * (c->g.n[1] - 2) <= (1ll << 20)) {
-    // small 2-D grids (BASELINE config 1): the whole step -- slot reset, fill!(ρuf,0), both sweeps, BCf! -- in one cooperative launch
+  if (D == 2 && c->use_march != 0) {
+    // 2-D grids (BASELINE config 1): the whole step -- slot reset, fill!(ρuf,0), both cell-parallel sweeps, BCf! -- in one cooperative launch
     SweepCfg<T> q[2];
     T* bufs2[3] = {f, ff, f};
     for (int s = 0; s < 2; ++s) {

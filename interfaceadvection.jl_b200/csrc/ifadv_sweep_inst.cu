@@ -17,6 +17,9 @@
 #endif
 #if IFADV_FAM == 0
 #include "ifadv_sweep.cuh"
+#if IFADV_D == 2 && IFADV_MOM == 0
+#include "ifadv_vofcell.cuh"
+#endif
 #elif IFADV_FAM == 1
 #include "ifadv_march.cuh"
 #elif IFADV_FAM == 2
@@ -174,9 +177,23 @@ static int launch_along2_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) 
   const int nzo = c->kz1 - c->kz0;  // planes of dimension 3 to update (all of them on one GPU, the owned ones of a z-slab)
   const int nx = c->g.n[0] - 2, ncc = (DCC == 2) ? nzo : c->g.n[DCC] - 2, na = (J == 2) ? nzo : c->g.n[J] - 2;
   const long long tiles = (long long)((nx + 31) / 32) * ((ncc + TC - 1) / TC);
-  int chunk = 128;  // a multiple of 4 (4 warm-up planes per chunk)
-  while (chunk > 16 && tiles * ((na + chunk - 1) / chunk) < 148 * 8) chunk >>= 1;
+  // march length (a multiple of 4; 4 warm-up planes per chunk): the largest candidate that still gives >= 8 CTAs per SM.  Not a power of
+  // two: at 512³ chunks of 96..120 planes run 2 % faster than 128 (equal-length CTAs that start in lockstep keep alternating between their
+  // load and arithmetic phases together; a shorter last chunk desynchronises them) -- tools/runs/gpurun_run39.sh, gpurun_run40.sh
+  int chunk = 16;
+  if (na <= 128 && tiles >= 148 * 8) chunk = (na + 3) / 4 * 4;  // thin slabs with plenty of tiles: one chunk
+  else {
+    static const int cand[] = {120, 88, 56, 40, 24, 16};
+    for (int cc : cand)
+      if (tiles * ((na + cc - 1) / cc) >= 148 * 8) { chunk = cc; break; }
+    const int n = (na + chunk - 1) / chunk, last = na - (n - 1) * chunk;
+    if (n > 1 && last * 4 < chunk) chunk = ((na + n - 1) / n + 3) / 4 * 4;  // no sliver at the end
+  }
   if (const char* e = getenv("IFADV_CHUNK")) chunk = std::max(16, (atoi(e) / 4) * 4);  // measurement override
+  {  // per kernel form: IFADV_CHUNK_Y / _YF / _Z / _ZF (F = fused first sweep)
+    static const char* names[4] = {"IFADV_CHUNK_Y", "IFADV_CHUNK_YF", "IFADV_CHUNK_Z", "IFADV_CHUNK_ZF"};
+    if (const char* e = getenv(names[(J - 1) * 2 + (FUSED ? 1 : 0)])) chunk = std::max(16, (atoi(e) / 4) * 4);
+  }
   dim3 grid((unsigned)((nx + 31) / 32), (unsigned)((ncc + TC - 1) / TC), (unsigned)((na + chunk - 1) / chunk));
   const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
   if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
@@ -245,9 +262,16 @@ static int launch_xrow_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   }
   const int nx = c->g.n[0] - 2, ny = c->g.n[1] - 2, nz = c->kz1 - c->kz0;
   const unsigned gx = (unsigned)((nx + TL::TX) / TL::TX), gy = (unsigned)((ny + TL::TY - 1) / TL::TY);  // elements 1..nx in tiles [60b, 60b+59]
-  int chunk = 128;  // one warm-up plane per chunk
-  while (chunk > 16 && (long long)gx * gy * ((nz + chunk - 1) / chunk) < 148 * 8) chunk >>= 1;
+  // march length (one warm-up plane per chunk): 20..48 planes run 4 % faster than 64 or 128 at 512³, 12..20 are the best at
+  // 512x256x256 (tools/runs/gpurun_run39.sh, gpurun_run40.sh)
+  int chunk = 12;
+  {
+    static const int cand[] = {20, 12};
+    for (int cc : cand)
+      if ((long long)gx * gy * ((nz + cc - 1) / cc) >= 148 * 8) { chunk = cc; break; }
+  }
   if (const char* e = getenv("IFADV_CHUNK")) chunk = std::max(4, atoi(e));  // measurement override
+  if (const char* e = getenv(FUSED ? "IFADV_CHUNK_XF" : "IFADV_CHUNK_X")) chunk = std::max(4, atoi(e));
   dim3 grid(gx, gy, (unsigned)((nz + chunk - 1) / chunk));
   const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
   if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
@@ -346,14 +370,13 @@ template int launch_sweep_dim<IFADV_T, IFADV_D, (IFADV_MOM != 0)>(ifadv_ctx*, cu
 
 #if IFADV_D == 2 && IFADV_MOM == 0
 // The whole 2-D pure-VOF step (advectVOF!, advection.jl:34-78) as ONE cooperative launch: reduction-slot reset, fill!(ρuf,0), the two
-// directional sweeps and the final BCf!, separated by grid-wide barriers.  Small 2-D grids (BASELINE config 1: 128², 16 k cells) are
-// launch-latency bound: five launches of ~13 µs each become one.
+// directional sweeps (cell-parallel + lane-dense fix-up of the interface cells, ifadv_vofcell.cuh) and the final BCf!, separated by
+// grid-wide barriers.  Small 2-D grids (BASELINE config 1: 128², 16 k cells) are launch-latency bound.
 namespace cg = cooperative_groups;
-constexpr int V2_NT = 128, V2_TX = 32, V2_TY = 4;  // small tiles: the step is latency bound, so spread it over as many SMs as there are tiles
-template <class T, int JA, int JB>
+constexpr int V2_NT = 128;
+template <class T, int JA, int JB, bool SAMEU, bool LOCAL>
 __global__ void __launch_bounds__(V2_NT) vof2d_step_kernel(const SweepP<T> PA, const SweepP<T> PB, T* f_final, T* rhouf, const long long nruf,
-                                                          unsigned long long* red, const unsigned per) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+                                                          unsigned long long* red, const unsigned per, int* list, unsigned* cnt, const unsigned cap) {
   cg::grid_group grid = cg::this_grid();
   const Geo g = PA.g;
   const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x, gs = (long long)gridDim.x * blockDim.x;
@@ -362,22 +385,12 @@ __global__ void __launch_bounds__(V2_NT) vof2d_step_kernel(const SweepP<T> PA, c
     if (r[4] != 0ull) atomicOr(red + 24, 1ull);
     r[0] = 0ull; r[1] = ~0ull; r[2] = 0ull; r[3] = ~0ull; r[4] = 0ull; r[5] = 0ull; r[6] = 0ull; r[7] = 0ull;
   }
+  if (gt == 0) { cnt[0] = 0u; cnt[1] = 0u; }
   if (rhouf != nullptr)
     for (long long i = gt; i < nruf; i += gs) rhouf[i] = T(0);  // fill!(ρuf,0), advection.jl:37
   grid.sync();
-  auto sweep = [&](auto ja, const SweepP<T>& P) {
-    constexpr int J = decltype(ja)::value;
-    constexpr int TX = V2_TX, TY = V2_TY;
-    const int gx = (g.n[0] - 2 + TX - 1) / TX, gy = (g.n[1] - 2 + TY - 1) / TY;
-    for (int t = blockIdx.x; t < gx * gy; t += gridDim.x) {
-      sweep_tile<T, 2, J, TX, TY, 1, false, V2_NT>(P, t % gx, t / gx, 0, smem_raw);
-      __syncthreads();  // the next tile reuses the shared planes
-    }
-  };
-  sweep(std::integral_constant<int, JA>{}, PA);
-  grid.sync();
-  sweep(std::integral_constant<int, JB>{}, PB);
-  grid.sync();
+  vof2d_cell_sweep<T, JA, SAMEU, LOCAL>(PA, grid, list, cnt, cap);
+  vof2d_cell_sweep<T, JB, SAMEU, LOCAL>(PB, grid, list + cap, cnt + 1, cap);
   // BCf!(f;perdir), VOFutil.jl:64-75: every ghost cell takes the value of its interior-equivalent cell
   const long long n0 = g.n[0], n1 = g.n[1], c0 = 2 * n1, c1 = 2 * n0;
   for (long long t = gt; t < c0 + c1; t += gs) {
@@ -393,21 +406,34 @@ template <class T> int launch_vof2d_step(ifadv_ctx* c, cudaStream_t st, const Sw
   SweepP<T> PA, PB;
   fill_params<T>(c, qa, qa.j, PA);
   fill_params<T>(c, qb, qb.j, PB);
-  const size_t smem = std::max(Tile<2, 0, V2_TX, V2_TY, 1>::template smem_bytes<T>(false), Tile<2, 1, V2_TX, V2_TY, 1>::template smem_bytes<T>(false));
-  void* kern = (qa.j == 0) ? (void*)vof2d_step_kernel<T, 0, 1> : (void*)vof2d_step_kernel<T, 1, 0>;
+  if ((unsigned long long)c->g.S >= 0x7fffffffull) { c->err = "grid too large for 32-bit element offsets"; return -2; }
+  if (!c->st_list) {  // list of deferred (interface) cells, shared with the surface-tension kernels
+    const unsigned cap = (unsigned)std::min<long long>(std::max<long long>(c->g.S / 8, 1 << 16), 1ll << 27);
+    CU_CHECK(c, cudaMalloc(&c->st_list, sizeof(int) * (size_t)cap * 3));
+    CU_CHECK(c, cudaMalloc(&c->st_cnt, sizeof(unsigned) * 4));
+    c->st_cap = cap;
+  }
+  const bool same = qa.u == qa.u0;
+  const long long ncell = (long long)(c->g.n[0] - 2) * (c->g.n[1] - 2);
+  const bool local = ncell <= (1ll << 17) && !getenv("IFADV_VOF2D_LIST");  // latency bound: in-line reconstruction, one grid barrier per sweep
+  void* kern;
+  if (local) kern = (qa.j == 0) ? (same ? (void*)vof2d_step_kernel<T, 0, 1, true, true> : (void*)vof2d_step_kernel<T, 0, 1, false, true>)
+                                : (same ? (void*)vof2d_step_kernel<T, 1, 0, true, true> : (void*)vof2d_step_kernel<T, 1, 0, false, true>);
+  else kern = (qa.j == 0) ? (same ? (void*)vof2d_step_kernel<T, 0, 1, true, false> : (void*)vof2d_step_kernel<T, 0, 1, false, false>)
+                          : (same ? (void*)vof2d_step_kernel<T, 1, 0, true, false> : (void*)vof2d_step_kernel<T, 1, 0, false, false>);
   int per_sm = 0, sms = 0;
-  CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CU_CHECK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, V2_NT, smem));
+  CU_CHECK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, V2_NT, 0));
   CU_CHECK(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-  const int nx = c->g.n[0] - 2, ny = c->g.n[1] - 2;
-  const int tiles = ((nx + V2_TX - 1) / V2_TX) * ((ny + V2_TY - 1) / V2_TY);
-  const int grid = std::max(1, std::min(tiles, per_sm * sms));
+  // latency bound for small grids: one cell per thread, spread over as many SMs as there are CTAs; persistent grid for large ones
+  const int grid = (int)std::max<long long>(1, std::min<long long>((ncell + V2_NT - 1) / V2_NT, (long long)std::min(per_sm, 8) * sms));
   T* ruf = rhouf;
   long long nruf = (long long)c->g.S * 2;
   unsigned long long* red = c->red_dev;
-  unsigned per = c->g.per;
-  void* args[] = {&PA, &PB, &f_final, &ruf, &nruf, &red, &per};
-  CU_CHECK(c, cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(V2_NT), args, smem, st));
+  unsigned per = c->g.per, cap = c->st_cap;
+  int* list = c->st_list;
+  unsigned* cnt = c->st_cnt;
+  void* args[] = {&PA, &PB, &f_final, &ruf, &nruf, &red, &per, &list, &cnt, &cap};
+  CU_CHECK(c, cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(V2_NT), args, 0, st));
   c->launches++;
   return 0;
 }

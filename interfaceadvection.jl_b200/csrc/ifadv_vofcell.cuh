@@ -26,10 +26,14 @@ template <class T> struct Box27 {  // 3^3 box held by the thread
   T v[27];
   IFADV_DI T operator()(int dx, int dy, int dz) const { return v[(dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)]; }
 };
+template <class T> struct Box9 {  // 3^2 box (2-D grids)
+  T v[9];
+  IFADV_DI T operator()(int dx, int dy, int) const { return v[(dx + 1) + 3 * (dy + 1)]; }
+};
 
 // VOF flux through the lower face of the cell with index v along J (cells v-1 | v), advection.jl:108-137.  PLIC = false: a face that
 // needs the reconstruction is only flagged.
-template <class T, int J, bool PLIC>
+template <class T, int J, bool PLIC, int D = 3>
 IFADV_DI VFace<T> vof_face(const SweepP<T>& P, T usum, T flo, T fhi, int v, int cx, int cy, int cz) {
   const int nA = P.g.n[J];
   const bool perA = (P.g.per >> J) & 1u;
@@ -43,24 +47,33 @@ IFADV_DI VFace<T> vof_face(const SweepP<T>& P, T usum, T flo, T fhi, int v, int 
   T ff = fc * dl;
   if (PLIC && need) {
     const int m = map1(cu, nA, perA);
-    // the 3^3 box around the upwind cell: 27 independent loads in flight (the normal schemes would otherwise pull them in one by one
-    // through data-dependent branches), ghost rules folded into three index maps per axis
-    Box27<T> B;
+    // the 3^D box around the upwind cell: all loads independent and in flight together (the normal schemes would otherwise pull them in
+    // one by one through data-dependent branches), ghost rules folded into three index maps per axis
     const int bx = (J == 0) ? m : cx, by = (J == 1) ? m : cy, bz = (J == 2) ? m : cz;
     long long ox[3], oy[3], oz[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       ox[a] = mapc(bx + a - 1, P.g.n[0], P.g.per & 1u) - 1;
       oy[a] = (long long)(mapc(by + a - 1, P.g.n[1], P.g.per & 2u) - 1) * P.g.s1;
-      oz[a] = (long long)(mapc(bz + a - 1, P.g.n[2], P.g.per & 4u) - 1) * P.g.s2;
+      oz[a] = (D == 3) ? (long long)(mapc(bz + a - 1, P.g.n[2], P.g.per & 4u) - 1) * P.g.s2 : 0;
     }
+    if (D == 3) {
+      Box27<T> B;
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+          for (int a = 0; a < 3; ++a) B.v[a + 3 * b + 9 * c] = __ldg(P.f_in + ox[a] + oy[b] + oz[c]);
+      ff = plic_face_flux_inl<T, D>(P.scheme, B, fc, J, dl);
+    } else {
+      Box9<T> B;
 #pragma unroll
       for (int b = 0; b < 3; ++b)
 #pragma unroll
-        for (int a = 0; a < 3; ++a) B.v[a + 3 * b + 9 * c] = __ldg(P.f_in + ox[a] + oy[b] + oz[c]);
-    ff = plic_face_flux_inl<T, 3>(P.scheme, B, fc, J, dl);
+        for (int a = 0; a < 3; ++a) B.v[a + 3 * b] = __ldg(P.f_in + ox[a] + oy[b]);
+      ff = plic_face_flux_inl<T, D>(P.scheme, B, fc, J, dl);
+    }
   }
   return VFace<T>{ff, dl, need};
 }
@@ -274,6 +287,72 @@ __global__ void __launch_bounds__(128) vofcell_fix_kernel(const SweepP<T> P, con
     vof_cell_finish<T, J>(P, l, cJ, fc, lo, hi, dv, rmax, rmin, amax, amin);
   }
   vof_reduce<T>(P, rmax, rmin, amax, amin);
+}
+
+// One directional sweep of a 2-D grid inside a cooperative kernel (the whole advect! step of small grids is ONE launch): phase 1 = every
+// cell the cell-parallel way, cells next to an interface face go to `list`; grid barrier; phase 2 = the listed cells lane-dense with the
+// PLIC reconstruction; grid barrier.  The grid-stride loops are warp-uniform (blockDim and gridDim·blockDim are multiples of 32).
+// LOCAL (small grids, where the step is bound by latency and grid barriers, not by issue slots): a flagged cell is reconstructed in line
+// by its own thread right away -- no list, one grid barrier less per sweep.
+template <class T, int J, bool SAMEU, bool LOCAL, class GRID>
+IFADV_DI void vof2d_cell_sweep(const SweepP<T>& P, GRID& grid, int* __restrict__ list, unsigned* cnt, const unsigned cap) {
+  const Geo& g = P.g;
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x, gs = (long long)gridDim.x * blockDim.x;
+  const int nx = g.n[0] - 2, ny = g.n[1] - 2, nA = g.n[J], lane = threadIdx.x & 31;
+  const bool perA = (g.per >> J) & 1u, first = P.first != 0;
+  const long long ncell = (long long)nx * ny, nround = (ncell + 31) / 32 * 32, sA = (J == 0) ? 1 : g.s1;
+  T rmax = -INFINITY, rmin = INFINITY;
+  unsigned int amax = 0, amin = 0;
+  auto cell = [&](long long c, bool plic_pass, bool ok) -> bool {  // returns: the cell is deferred (phase 1)
+    const int x = 2 + (int)(c % nx), y = 2 + (int)(c / nx);
+    const long long l = lin3(g, x, y, 1);
+    const int cJ = (J == 0) ? x : y;
+    const T fc = __ldg(P.f_in + l);
+    const T fm = __ldg(P.f_in + l + (long long)(map1(cJ - 1, nA, perA) - cJ) * sA);
+    const T fp = __ldg(P.f_in + l + (long long)(map1(cJ + 1, nA, perA) - cJ) * sA);
+    const T ulo = __ldg(P.uj + l), uhi = __ldg(P.uj + l + sA);
+    const T u0lo = SAMEU ? ulo : __ldg(P.u0j + l), u0hi = SAMEU ? uhi : __ldg(P.u0j + l + sA);
+    VFace<T> lo, hi;
+    if (plic_pass) { lo = vof_face<T, J, true, 2>(P, ulo + u0lo, fm, fc, cJ, x, y, 1); hi = vof_face<T, J, true, 2>(P, uhi + u0hi, fc, fp, cJ + 1, x, y, 1); }
+    else { lo = vof_face<T, J, false, 2>(P, ulo + u0lo, fm, fc, cJ, x, y, 1); hi = vof_face<T, J, false, 2>(P, uhi + u0hi, fc, fp, cJ + 1, x, y, 1); }
+    const bool flagged = lo.plic || hi.plic;
+    const int cb = first ? ((fc < T(0.5)) ? 0 : 1) : (int)P.cbar[l];
+    if (!plic_pass && first && ok) P.cbar[l] = (int8_t)cb;
+    if (ok && (plic_pass ? flagged : !flagged)) {
+      const T div = (uhi - ulo) + (u0hi - u0lo);
+      const T dv = ((cb ? div : T(0)) * P.dt) / T(2);
+      vof_cell_finish<T, J>(P, l, cJ, fc, lo, hi, dv, rmax, rmin, amax, amin);
+    }
+    return ok && flagged;
+  };
+  for (long long c = gt; c < nround; c += gs) {
+    const bool ok = c < ncell;
+    const bool defer = cell(ok ? c : 0, false, ok);
+    if (LOCAL) {
+      if (defer) cell(c, true, true);
+      continue;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, defer);
+    if (m) {
+      const int leader = __ffs(m) - 1;
+      unsigned base = 0;
+      if (lane == leader) base = atomicAdd(cnt, (unsigned)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      const unsigned q = base + (unsigned)__popc(m & ((1u << lane) - 1u));
+      if (defer && q < cap) list[q] = (int)(ok ? c : 0);
+    }
+  }
+  if (!LOCAL) {
+    grid.sync();
+    const unsigned n = *(volatile unsigned*)cnt;
+    if (n <= cap) {
+      for (long long q = gt; q < (long long)n; q += gs) cell(list[q], true, true);
+    } else {  // the list overflowed: examine every cell again
+      for (long long c = gt; c < ncell; c += gs) cell(c, true, true);
+    }
+  }
+  vof_reduce<T>(P, rmax, rmin, amax, amin);
+  grid.sync();
 }
 
 }  // namespace ifadv

@@ -526,3 +526,42 @@ def test_pure_vof_cell_kernel_matches_oracle_and_marching_kernels(ia, T, N, kind
         for j in range(3):
             sl = [slice(1, -1)] * 3; sl[j] = slice(1, None)
             assert np.array_equal(res[None][2][tuple(sl) + (j,)], res["lean"][2][tuple(sl) + (j,)])
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("N,kind,perdir", [((48, 40), "C1", ()), ((37, 29), "C3", (1,)), ((64, 24), "C1", (1, 2))])
+def test_pure_vof_2d_both_fixup_variants_match_oracle(ia, T, N, kind, perdir, monkeypatch):
+    """2-D advectVOF! is one cooperative launch of the cell-parallel sweeps (ifadv_vofcell.cuh): small grids reconstruct a flagged cell in
+    line, large ones go through the deferred list (forced here with IFADV_VOF2D_LIST).  Both against the oracle, and bit-identical to
+    each other and to the v1 tile kernel in Float64."""
+    from interfaceadvection.jl_b200 import api
+    st = make_state(N, kind, T, perdir=perdir)
+    u0 = second_velocity(st, 5, 0.9, 0.04)
+    a = alloc_cmom(st)
+    f_o = st["f"].copy(order="F")
+    res = {}
+    for dirO in [(1, 2), (2, 1)]:
+        f_o = st["f"].copy(order="F"); a = alloc_cmom(st)
+        so, rep = O.advectVOF(f_o, a["ff"], a["alpha"], a["nhat"], u0, st["u"], 1.0, a["cbar"], a["rhouf"], st["lam_rho"], "WH", perdir, dirO)
+        for var in ("local", "list", "tile"):
+            monkeypatch.delenv("IFADV_VOF2D_LIST", raising=False); monkeypatch.delenv("IFADV_KERNEL", raising=False)
+            if var == "list":
+                monkeypatch.setenv("IFADV_VOF2D_LIST", "1")
+            if var == "tile":
+                monkeypatch.setenv("IFADV_KERNEL", "tile")
+            api._contexts.clear()
+            d = _dev(ia, alloc_cmom(st))
+            fd, ud, u0d = ia.from_numpy(st["f"]), ia.from_numpy(st["u"]), ia.from_numpy(u0)
+            sc = ia.advectVOF(fd, d["ff"], d["alpha"], d["nhat"], u0d, ud, 1.0, d["cbar"], d["rhouf"], st["lam_rho"], "WH", perdir, dirO)
+            res[var] = (ia.to_numpy(fd), ia.to_numpy(d["rhouf"]))
+            assert sc == so, (var, dirO)
+            assert np.abs(res[var][0] - f_o).max() <= TOL[T], (var, dirO)
+            for j in range(2):
+                sl = [slice(1, -1)] * 2; sl[j] = slice(1, None)
+                assert np.abs(res[var][1][tuple(sl) + (j,)] - a["rhouf"][tuple(sl) + (j,)]).max() <= TOL[T], (var, dirO, j)
+            assert np.array_equal(inside(ia.to_numpy(d["cbar"]), 2), inside(a["cbar"], 2))
+        monkeypatch.delenv("IFADV_VOF2D_LIST", raising=False); monkeypatch.delenv("IFADV_KERNEL", raising=False)
+        api._contexts.clear()
+        assert np.array_equal(res["local"][0], res["list"][0])
+        if T == np.float64:
+            assert np.array_equal(res["local"][0], res["tile"][0])
