@@ -7,6 +7,7 @@
 #include "oracle_flow.hpp"
 #include "oracle_forcing.hpp"
 #include "oracle_post.hpp"
+#include "oracle_poisson.hpp"
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -328,6 +329,52 @@ int orc_enstrophy(int dtype, int D, const int64_t* Ng, void* omega, const int64_
     }
   });
   return 0;
+}
+
+// ---- pressure projection: src/flow.jl:300-347 on WaterLily's Poisson struct ---------------------------------------
+#define ORC_POIS(T, g) Pois<T>{VF<T>{(T*)L, &g}, SF<T>{(T*)Dg, &g}, SF<T>{(T*)iD, &g}, SF<T>{(T*)x, &g}, SF<T>{(T*)eps, &g}, SF<T>{(T*)r, &g}, SF<T>{(T*)z, &g}, perdir}
+int orc_pois_update(int dtype, int D, const int64_t* Ng, void* Dg, void* iD, void* L) {
+  Grid g = make_grid(D, Ng);
+  void *x = nullptr, *eps = nullptr, *r = nullptr, *z = nullptr;
+  const unsigned perdir = 0;
+  DISPATCH(dtype, { pois_update<T>(g, ORC_POIS(T, g)); });
+  return 0;
+}
+// mult!(p,x): perBC!(x); z = A x on inside(x) (ghost entries of z zeroed)
+int orc_pois_mult(int dtype, int D, const int64_t* Ng, void* z, void* x, void* L, void* Dg, unsigned perdir) {
+  Grid g = make_grid(D, Ng);
+  DISPATCH(dtype, {
+    SF<T> zz{(T*)z, &g}, xx{(T*)x, &g}, dd{(T*)Dg, &g};
+    VF<T> ll{(T*)L, &g};
+    perBC<T>(g, xx, perdir);
+    for (int64_t k = 0; k < g.S; ++k) zz.p[k] = 0;
+    loop(r_inside(g), [&](I3 I) { zz(I) = pois_mult<T>(g, I, ll, dd, xx); });
+  });
+  return 0;
+}
+int orc_pois_residual(int dtype, int D, const int64_t* Ng, void* x, void* r, void* z, void* L, void* Dg, void* iD, unsigned perdir) {
+  Grid g = make_grid(D, Ng);
+  void* eps = nullptr;
+  DISPATCH(dtype, { pois_residual<T>(g, ORC_POIS(T, g)); });
+  return 0;
+}
+// tol < 0: 50eps(T); itmx <= 0: 6000 (the defaults of flow.jl:300).  Returns the iteration count (>= 0)
+int orc_psolver(int dtype, int D, const int64_t* Ng, void* x, void* eps, void* r, void* z, void* L, void* Dg, void* iD, unsigned perdir,
+                double tol, int itmx, double* r2) {
+  Grid g = make_grid(D, Ng);
+  int np = 0;
+  DISPATCH(dtype, {
+    const T t = tol < 0 ? T(50) * std::numeric_limits<T>::epsilon() : (T)tol;
+    np = psolver<T>(g, ORC_POIS(T, g), t, itmx <= 0 ? 6000 : itmx, r2);
+  });
+  return np;
+}
+int orc_myproject(int dtype, int D, const int64_t* Ng, void* u, void* x, void* eps, void* r, void* z, void* L, void* Dg, void* iD,
+                  unsigned perdir, double dt, double* r2) {
+  Grid g = make_grid(D, Ng);
+  int np = 0;
+  DISPATCH(dtype, { np = myproject<T>(g, VF<T>{(T*)u, &g}, ORC_POIS(T, g), (T)dt, r2); });
+  return np;
 }
 
 }  // extern "C"

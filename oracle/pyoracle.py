@@ -28,7 +28,7 @@ def build(force: bool = False) -> None:
     """Compile liboracle.so / liboracle_omp.so with the committed Makefile (g++ only, a few seconds)."""
     need = force or not all(os.path.exists(os.path.join(_HERE, n)) for n in ("liboracle.so", "liboracle_omp.so"))
     if not need:
-        srcs = [os.path.join(_HERE, n) for n in ("oracle.cpp", "oracle_core.hpp", "oracle_fields.hpp", "oracle_flow.hpp", "oracle_forcing.hpp", "oracle_post.hpp")]
+        srcs = [os.path.join(_HERE, n) for n in ("oracle.cpp", "oracle_core.hpp", "oracle_fields.hpp", "oracle_flow.hpp", "oracle_forcing.hpp", "oracle_post.hpp", "oracle_poisson.hpp")]
         newest = max(os.path.getmtime(s) for s in srcs)
         need = any(os.path.getmtime(os.path.join(_HERE, n)) < newest for n in ("liboracle.so", "liboracle_omp.so"))
     if need:
@@ -353,6 +353,55 @@ def enstrophy(omega, D, I=None):
     cell, tot = C.c_double(), C.c_double()
     lib().orc_enstrophy(_dt(omega), D, ng, _p(omega), _i3(I) if I is not None else None, C.byref(cell), C.byref(tot))
     return (cell.value if I is not None else None), tot.value
+
+
+# ---- pressure projection: psolver!, inproject!, myproject! on WaterLily's Poisson arrays ------------------------------
+class Poisson:
+    """WaterLily.Poisson(x,L,z;perdir): x (pressure), L (face coefficients, Flow.μ₀), z (source, Flow.σ) are the caller's arrays;
+    D, iD, ϵ, r are its own; update() = set_diag!."""
+
+    def __init__(self, x, L, z, perdir=()):
+        self.x, self.L, self.z, self.perdir = x, L, z, tuple(perdir)
+        self.D, self.iD, self.eps, self.r = (zeros(x.shape, x.dtype) for _ in range(4))
+        self.n = []
+        self.update()
+
+    def update(self):
+        D, ng = _ng(self.x)
+        lib().orc_pois_update(_dt(self.x), D, ng, _p(self.D), _p(self.iD), _p(self.L))
+
+
+def pois_mult(p: Poisson, x):
+    """mult!(p,x): perBC!(x); p.z = A·x on inside(x)."""
+    D, ng = _ng(x)
+    lib().orc_pois_mult(_dt(x), D, ng, _p(p.z), _p(x), _p(p.L), _p(p.D), mask(p.perdir))
+    return p.z
+
+
+def pois_residual(p: Poisson):
+    """residual!(p): r = z - A·x with the mean removed."""
+    D, ng = _ng(p.x)
+    lib().orc_pois_residual(_dt(p.x), D, ng, _p(p.x), _p(p.r), _p(p.z), _p(p.L), _p(p.D), _p(p.iD), mask(p.perdir))
+
+
+def psolver(p: Poisson, tol=None, itmx=6000, omp=False):
+    """psolver!(p;tol=50eps(T),itmx) (flow.jl:300-326) -> (iterations, last r₂)."""
+    D, ng = _ng(p.x)
+    r2 = C.c_double()
+    n = lib(omp).orc_psolver(_dt(p.x), D, ng, _p(p.x), _p(p.eps), _p(p.r), _p(p.z), _p(p.L), _p(p.D), _p(p.iD), mask(p.perdir),
+                             C.c_double(-1.0 if tol is None else tol), int(itmx), C.byref(r2))
+    p.n.append(n)
+    return n, r2.value
+
+
+def myproject(u, p: Poisson, dt, omp=False):
+    """myproject!(a,b,w) with dt = T(w)·last(a.Δt) (flow.jl:328-347) -> (iterations, last r₂)."""
+    D, ng = _ng(p.x)
+    r2 = C.c_double()
+    n = lib(omp).orc_myproject(_dt(p.x), D, ng, _p(u), _p(p.x), _p(p.eps), _p(p.r), _p(p.z), _p(p.L), _p(p.D), _p(p.iD),
+                               mask(p.perdir), C.c_double(float(p.x.dtype.type(dt))), C.byref(r2))
+    p.n.append(n)
+    return n, r2.value
 
 
 def num_threads(omp=True) -> int:
