@@ -177,6 +177,23 @@ int ifadv_metrics(ifadv_ctx* ctx, void* stream, const void* u, const void* f, do
 /* Σ EnsI(I,ω) over the inside cells; ω: vector field in 3-D, scalar field in 2-D                              src/metrics.jl:34-41 */
 int ifadv_enstrophy(ifadv_ctx* ctx, void* stream, const void* omega, double* out);
 
+/* ---- pressure projection (single-GPU contexts) -------------------------------------------------------------
+ * On WaterLily's Poisson arrays: L ≡ Flow.μ₀ (face coefficients, (Ng...,D)), x ≡ Flow.p, z ≡ Flow.σ, and the solver's own D, iD, ϵ, r
+ * (scalar fields).  WaterLily's primitives (set_diag!, mult, perBC!, residual!, L₂) are restated from its published 1.x source.
+ * update!(p::Poisson) = set_diag!(D,iD,L): D = -Σᵢ(L[I,i]+L[I+δᵢ,i]), iD = D² < 2eps ? 0 : 1/D on inside(x)     flow.jl:81,105 */
+int ifadv_poisson_update(ifadv_ctx* ctx, void* stream, void* D, void* iD, const void* L);
+/* psolver!(p::Poisson; tol=50eps(T), itmx=6e3): Jacobi-preconditioned conjugate gradients on A x = z                src/flow.jl:300-326
+ *   tol < 0 and itmx <= 0 select the reference's defaults.  z is the source on entry and scratch afterwards, as in the reference.
+ *   Every scalar of the recurrence and the loop condition stay on the device; the host polls the iteration state one batch of queued
+ *   iterations behind.  Returns the iteration count nᵖ and the last r₂ = r·r; synchronises the stream.  -1: NaN residual. */
+int ifadv_psolver(ifadv_ctx* ctx, void* stream, void* x, void* eps, void* r, void* z, const void* L, const void* D, const void* iD,
+                  unsigned perdir_mask, double tol, int itmx, int* iters, double* r2);
+/* myproject!(a,b,w) with inproject!(a,b::Poisson,dt), dt = T(w)·last(a.Δt) formed by the caller                     src/flow.jl:328-347
+ *   z ← ∇·u; ϵ, r ← 0; x ← x·dt; psolver!(tol=50eps(T), itmx=2000); u[I,i] -= L[I,i]·∂ᵢx on inside(x); x ← x/dt.
+ *   The caller applies BC!(u, ...) afterwards (flow.jl:82,106 -> ifadv_bc_vec). */
+int ifadv_myproject(ifadv_ctx* ctx, void* stream, void* u, void* x, void* eps, void* r, void* z, const void* L, const void* D,
+                    const void* iD, double dt, unsigned perdir_mask, int* iters, double* r2);
+
 /* Stream overlap aid for MPFMomStep! (src/flow.jl:74,89): the midpoint f⁰=(f⁰+f)/2 and the copy f⁰<-f only READ the f that the
  * corrector's advectfq! is about to advance, and that call does not write f before its last directional sweep.  A caller that
  * runs those two field operations on a second stream records an event behind them and passes it here; the NEXT

@@ -11,5 +11,6 @@ from .api import (  # noqa: F401
     from_numpy, jl_empty, mom_advect_step, u2rhou_advectfq, jl_zeros, rhou2u, sim_step, sim_time, sum_inside, to_numpy, u2rhou, context_for,
     viscSurfTenrhou, updateU, updateL, mom_step_forcing,
     LevelSet, computeL, redistaningStage, redistaning, metrics, enstrophy,
+    Poisson, update, psolver, myproject, project_with,
 )
 from . import vtkio  # noqa: F401,E402  (load! / save of VTK restart files, ext/IntfAdvReadVTKExt.jl)

@@ -71,6 +71,9 @@ def lib():
         L.ifadv_metrics.argtypes = [vp, vp, vp, vp, dbl, dblp, dblp, dblp, dblp]
         L.ifadv_enstrophy.argtypes = [vp, vp, vp, dblp]
         L.ifadv_check_nan.argtypes = [vp, vp]
+        L.ifadv_poisson_update.argtypes = [vp, vp, vp, vp, vp]
+        L.ifadv_psolver.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, u32, dbl, i32, i32p, dblp]
+        L.ifadv_myproject.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, u32, i32p, dblp]
         L.ifadv_create_slab.argtypes = [C.POINTER(vp), i64p, i32, i32, vp, i32, i32, i32, i32]
         L.ifadv_slab_info.argtypes = [vp, i32p, i32p, i32p, i32p, i64p]
         L.ifadv_exchange_planes.argtypes = [vp, vp, vp, i32, i32]
@@ -254,6 +257,22 @@ class Context:
         out = C.c_double()
         self._chk(lib().ifadv_enstrophy(self._h, stream, omega, C.byref(out)))
         return out.value
+
+    def poisson_update(self, stream, D, iD, L):
+        return self._chk(lib().ifadv_poisson_update(self._h, stream, D, iD, L))
+
+    def psolver(self, stream, x, eps, r, z, L, D, iD, perdir, tol=None, itmx=6000):
+        """(iterations, last r₂) of psolver!(p;tol,itmx) (ifadv_psolver); tol=None: 50eps(T)."""
+        n, r2 = C.c_int(0), C.c_double(0.0)
+        self._chk(lib().ifadv_psolver(self._h, stream, x, eps, r, z, L, D, iD, perdir_mask(perdir), -1.0 if tol is None else float(tol),
+                                      int(itmx), C.byref(n), C.byref(r2)))
+        return n.value, r2.value
+
+    def myproject(self, stream, u, x, eps, r, z, L, D, iD, dt, perdir):
+        """(iterations, last r₂) of myproject!(a,b,w), dt = T(w)·last(a.Δt) (ifadv_myproject)."""
+        n, r2 = C.c_int(0), C.c_double(0.0)
+        self._chk(lib().ifadv_myproject(self._h, stream, u, x, eps, r, z, L, D, iD, float(dt), perdir_mask(perdir), C.byref(n), C.byref(r2)))
+        return n.value, r2.value
 
     def defer_f_writes_until(self, event):
         """One-shot: the next CMOM advect call waits for `event` (cudaEvent_t handle) before its first write to f."""

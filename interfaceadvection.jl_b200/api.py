@@ -220,6 +220,7 @@ class Flow:
         self.u0 = self.u.clone(memory_format=torch.preserve_format)
         self.f = jl_zeros(Ng + (D,), T, device)
         self.sigma = jl_zeros(Ng, T, device)
+        self.p = jl_zeros(Ng, T, device)
         self.mu0 = jl_zeros(Ng + (D,), T, device)  # μ₀: the projection's face coefficients (updateL!, flow.jl:254-259)
         self.mu0.fill_(1)
         self.dt = [float(dt)]  # Δt
@@ -231,14 +232,17 @@ class TwoPhaseSimulation:
     (src/InterfaceAdvection.jl:64-85).  The Poisson solver and body stay with WaterLily (out of scope)."""
 
     def __init__(self, dims, u_BC, L, T=torch.float32, lam_mu=1e-2, lam_rho=1e-3, eta=None, InterfaceSDF=None, lam="Koren",
-                 normalScheme="WH", U=None, dt=0.25, nu=0.0, g=None, u0=None, perdir=(), exitBC=False, device="cuda"):
+                 normalScheme="WH", U=None, dt=0.25, nu=0.0, g=None, u0=None, perdir=(), exitBC=False, device="cuda", psolver=None):
         self.L = L
         self.U = U if U is not None else math.sqrt(sum(float(x) ** 2 for x in u_BC))
         self.flow = Flow(dims, u_BC, T=T, u0fn=u0, dt=dt, nu=nu, g=g, exitBC=exitBC, perdir=perdir, lam=lam, device=device)
         self.intf = cVOF(dims, T=T, InterfaceSDF=InterfaceSDF, mu=nu, lam_mu=lam_mu, lam_rho=lam_rho, eta=eta,
                          normalScheme=normalScheme, perdir=perdir, device=device)
         self.flow.dt[-1] = min(self.flow.dt[-1], MPCFL(self.flow, self.intf))  # InterfaceAdvection.jl:81
-        self.pois, self.body = None, None
+        # psolver=Poisson: WaterLily's Simulation(...; psolver=Poisson) -- the solver the reference's psolver! is written for
+        # (flow.jl:300); MultiLevelPoisson (WaterLily's default) is not built: pass a `project` hook instead
+        self.pois = Poisson(self.flow.p, self.flow.mu0, self.flow.sigma, perdir=perdir) if psolver in ("Poisson", Poisson) else None
+        self.body = None
 
 
 # ---- the hot path ------------------------------------------------------------------------------------------------------
@@ -463,6 +467,49 @@ def mom_step_forcing(a: Flow, c: cVOF, dt=None, project: Optional[Callable] = No
         BC(a.u, a.uBC, a.exitBC, a.perdir)
 
 
+# ---- pressure projection ----------------------------------------------------------------------------------------
+class Poisson:
+    """WaterLily.Poisson(x,L,z;perdir): x ≡ Flow.p, L ≡ Flow.μ₀, z ≡ Flow.σ are the caller's arrays; D, iD, ϵ, r its own; n collects
+    the iteration counts like the reference's `p.n`."""
+
+    def __init__(self, x, L, z, perdir=()):
+        self.x, self.L, self.z, self.perdir = x, L, z, tuple(perdir)
+        Ng, T, dev = tuple(x.shape), x.dtype, x.device
+        self.D, self.iD, self.eps, self.r = (jl_zeros(Ng, T, dev) for _ in range(4))
+        self.n, self.r2 = [], []
+        update(self)
+
+
+def update(b: Poisson):
+    """update!(b::Poisson) = set_diag!(D,iD,L) (flow.jl:81,105)."""
+    return context_for(b.x).poisson_update(_stream(b.x), _p(b.D), _p(b.iD), _p(b.L))
+
+
+def psolver(b: Poisson, tol=None, itmx=6000):
+    """psolver!(p;tol=50eps(T),itmx=6e3) (src/flow.jl:300-326) -> iterations."""
+    n, r2 = context_for(b.x).psolver(_stream(b.x), _p(b.x), _p(b.eps), _p(b.r), _p(b.z), _p(b.L), _p(b.D), _p(b.iD), b.perdir, tol, itmx)
+    b.n.append(n); b.r2.append(r2)
+    return n
+
+
+def myproject(a: Flow, b: Poisson, w=1.0):
+    """myproject!(a,b,w) (src/flow.jl:328-347): dt = T(w)·last(a.Δt); z ← ∇·u, x ← x·dt, psolver!, u -= L ∂x, x ← x/dt."""
+    T = a.u.dtype
+    dt = float(torch.tensor(w, dtype=T) * torch.tensor(a.dt[-1], dtype=T))
+    n, r2 = context_for(b.x).myproject(_stream(b.x), _p(a.u), _p(b.x), _p(b.eps), _p(b.r), _p(b.z), _p(b.L), _p(b.D), _p(b.iD), dt, b.perdir)
+    b.n.append(n); b.r2.append(r2)
+    return n
+
+
+def project_with(b: Poisson) -> Callable:
+    """The `project(a, c, stage)` hook of MPFMomStep / mom_step_forcing for a Poisson: update!(b); myproject!(a,b[,1/2])
+    (flow.jl:81-82,105-106)."""
+    def hook(a, c, stage):
+        update(b)
+        myproject(a, b, 0.5 if stage == "predictor" else 1.0)
+    return hook
+
+
 # ---- post-processing (SURVEY §8f row 4) --------------------------------------------------------------------------------------------
 class LevelSet:
     """LevelSet(sim) (src/redistaning.jl:8-29): ϕ = 2f-1 in sim.intf.f⁰'s storage, ϕ⁰ ≡ α, ϕini ≡ fᶠ, L ≡ flow.σ -- no extra memory."""
@@ -507,6 +554,8 @@ def MPFMomStep(a: Flow, b, c: cVOF, d=None, dt=None, project: Optional[Callable]
     forcing=True runs the reference's whole sequence except the Poisson solve -- viscSurfTenρu!, updateU!, BC!, updateL! on the B200
     kernels too (mom_step_forcing) -- and `project` then stands for update!(b); myproject! only."""
     dt = a.dt[-1] if dt is None else dt
+    if project is None and forcing and isinstance(b, Poisson):
+        project = project_with(b)  # the reference's own projection on the B200 kernels (SURVEY §8f row 2)
     if forcing:
         mom_step_forcing(a, c, dt, project=project, check=check)
     else:

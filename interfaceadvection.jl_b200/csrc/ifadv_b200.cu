@@ -874,6 +874,7 @@ int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int dev
   c->st_list = nullptr; c->st_cnt = nullptr; c->st_cap = 0;
   c->pipe = nullptr;
   c->wait_f = nullptr;
+  c->pois_ctl = c->pois_host = nullptr; c->pois_ev[0] = c->pois_ev[1] = nullptr;
   c->host_h2d = c->host_d2h = 0; c->host_slabs = 0;
   c->prof_on = 0; c->prof_n = 0; c->prof_ev = nullptr; c->prof_tag = nullptr;
   for (int k = 0; k < 8; ++k) { c->prof_dir_ms[k] = 0.0; c->prof_dir_n[k] = 0; }
@@ -912,6 +913,7 @@ int ifadv_destroy(ifadv_ctx* c) {
   slab_p2p_free(c);
   if (c->slab_stream) { cudaStreamDestroy(c->slab_stream); cudaEventDestroy(c->slab_ev[0]); cudaEventDestroy(c->slab_ev[1]); }
   host_pipe_free(c);
+  ifadv_poisson_free(c);
   if (c->prof_ev) { for (int k = 0; k < 2 * IFADV_PROF_MAX; ++k) cudaEventDestroy(c->prof_ev[k]); delete[] c->prof_ev; delete[] c->prof_tag; }
   delete c;
   return 0;

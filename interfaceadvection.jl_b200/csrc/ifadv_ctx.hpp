@@ -69,7 +69,12 @@ struct ifadv_ctx {
   unsigned char* prof_tag;  // per launch: bit 0 = fused first sweep (10s+1 B/cell) / standard sweep (13s+1 B/cell); bits 1.. = 2*j + fused
   double prof_dir_ms[8];    // accumulated by ifadv_profile_read: index 2*j + fused
   int64_t prof_dir_n[8];
+  // pressure solver (ifadv_poisson.cu), allocated lazily: control block in device memory, pinned mirror of two polls, their events
+  void* pois_ctl;
+  void* pois_host;
+  cudaEvent_t pois_ev[2];
 };
+void ifadv_poisson_free(ifadv_ctx* c);  // ifadv_poisson.cu
 #define IFADV_PROF_MAX 4096
 
 #define CU_CHECK(ctx, call)                                                                 \

@@ -1,0 +1,179 @@
+// ifadv_poisson.cu -- C ABI of the pressure projection (include/ifadv.h: ifadv_poisson_update, ifadv_psolver, ifadv_myproject);
+// kernels in ifadv_poisson.cuh.  Compiled -fmad=false with IEEE division in both precisions.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <limits>
+
+#include "../../include/ifadv.h"
+#include "ifadv_ctx.hpp"
+#include "ifadv_poisson.cuh"
+
+using namespace ifadv;
+
+namespace {
+int pfail(ifadv_ctx* c, int code, const char* msg) {
+  if (c) c->err = msg;
+  return code;
+}
+// control block (device), its pinned mirror for two polls in flight, and their events
+int pois_alloc(ifadv_ctx* c) {
+  if (c->pois_ctl) return 0;
+  CU_CHECK(c, cudaMalloc(&c->pois_ctl, sizeof(PoisCtl)));
+  CU_CHECK(c, cudaMemset(c->pois_ctl, 0, sizeof(PoisCtl)));
+  CU_CHECK(c, cudaMallocHost(&c->pois_host, 2 * 256));
+  CU_CHECK(c, cudaEventCreateWithFlags(&c->pois_ev[0], cudaEventDisableTiming));
+  CU_CHECK(c, cudaEventCreateWithFlags(&c->pois_ev[1], cudaEventDisableTiming));
+  return 0;
+}
+inline unsigned row_blocks(const ifadv_ctx* c) {
+  const long long rows = (long long)(c->g.n[1] - 2) * (c->D == 3 ? c->g.n[2] - 2 : 1);
+  return (unsigned)std::max<long long>(1, std::min<long long>((rows + 7) / 8, std::min(148LL * 6, (long long)IFADV_POIS_MAXB)));
+}
+template <class T, int D> int perbc_launch(ifadv_ctx* c, cudaStream_t st, T* a, unsigned per) {
+  Geo g = c->g;
+  g.per = per & ((1u << D) - 1u);
+  if (!g.per) return 0;
+  const long long n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
+  const long long tot = ((g.per & 1u) ? 2 * n1 * n2 : 0) + ((g.per & 2u) ? 2 * n0 * n2 : 0) + ((D == 3 && (g.per & 4u)) ? 2 * n0 * n1 : 0);
+  perbc_kernel<T, D><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a, g);
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+template <class T, int D> int update_t(ifadv_ctx* c, cudaStream_t st, T* Dg, T* iD, const T* L) {
+  pois_diag_kernel<T, D><<<row_blocks(c), 256, 0, st>>>(Dg, iD, L, c->g);
+  c->launches++;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+
+// psolver!(p;tol,itmx), src/flow.jl:300-326
+template <class T, int D>
+int psolver_t(ifadv_ctx* c, cudaStream_t st, T* x, T* eps, T* r, T* z, const T* L, const T* Dg, const T* iD, unsigned per, double tol, int itmx,
+              int* iters, double* r2_out) {
+  int rc = pois_alloc(c);
+  if (rc) return rc;
+  PoisCtl* ctl = (PoisCtl*)c->pois_ctl;
+  const unsigned nb = row_blocks(c);
+  const Geo g = c->g;
+  const double tolT = tol < 0 ? (double)(T(50) * std::numeric_limits<T>::epsilon()) : (double)(T)tol;
+  if (itmx <= 0) itmx = 6000;
+  if ((rc = perbc_launch<T, D>(c, st, x, per))) return rc;                                        // :301 (and residual!'s own)
+  pois_residual_kernel<T, D><<<nb, 256, 0, st>>>(r, z, x, L, Dg, iD, g, ctl, tolT, itmx);          // :302
+  pois_start_kernel<T, D><<<nb, 256, 0, st>>>(r, z, eps, iD, g, ctl);                              // :302-307
+  c->launches += 2;
+  CU_CHECK(c, cudaGetLastError());
+  // Iterations are enqueued in batches; the control block of batch k is read back while batch k+1 is already queued, so the device
+  // never waits for the host.  Kernels past convergence return immediately.
+  struct Poll { double rho, zeps, beta, r2, mean, tol, r2_0; int n, itmx, done, sub_mean; };
+  static_assert(sizeof(Poll) <= 256, "poll mirror");
+  char* host = (char*)c->pois_host;
+  auto poll = [&](int slot) -> int {
+    CU_CHECK(c, cudaMemcpyAsync(host + 256 * slot, ctl, sizeof(Poll), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(c, cudaEventRecord(c->pois_ev[slot], st));
+    return 0;
+  };
+  int it = 0, last = 0, batch = 8;
+  Poll res{};
+  if ((rc = poll(last))) return rc;  // behind the start kernel
+  for (;;) {
+    bool queued = false;
+    if (it < itmx) {
+      const int end = std::min(itmx, it + batch);
+      for (; it < end; ++it) {
+        if ((rc = perbc_launch<T, D>(c, st, eps, per))) return rc;                                 // :311
+        pois_mult_kernel<T, D><<<nb, 256, 0, st>>>(z, eps, L, Dg, g, ctl);                         // :312-313
+        pois_update_kernel<T, D><<<nb, 256, 0, st>>>(x, r, z, eps, iD, g, ctl);                    // :313-321
+        pois_dir_kernel<T, D><<<nb, 256, 0, st>>>(eps, z, g, ctl, it);                             // :319
+        c->launches += 3;
+      }
+      CU_CHECK(c, cudaGetLastError());
+      if ((rc = poll(last ^ 1))) return rc;
+      queued = true;
+      batch = std::min(64, batch * 2);
+    }
+    CU_CHECK(c, cudaEventSynchronize(c->pois_ev[last]));
+    memcpy(&res, host + 256 * last, sizeof(Poll));
+    if (res.done || !queued) break;  // converged (what is still queued returns at once), or all itmx iterations were behind this poll
+    last ^= 1;
+  }
+  if ((rc = perbc_launch<T, D>(c, st, x, per))) return rc;                                          // :325
+  if (iters) *iters = res.n;
+  if (r2_out) *r2_out = res.r2;
+  if (res.r2 != res.r2) return pfail(c, -1, "NaN in the pressure solver");
+  return 0;
+}
+
+// myproject!(a,b,w) with dt = T(w)·last(a.Δt), src/flow.jl:328-347
+template <class T, int D>
+int myproject_t(ifadv_ctx* c, cudaStream_t st, T* u, T* x, T* eps, T* r, T* z, const T* L, const T* Dg, const T* iD, double dt, unsigned per,
+                int* iters, double* r2_out) {
+  const Geo g = c->g;
+  const T dtT = (T)dt;
+  {
+    const int bx = 128;
+    const dim3 gi((unsigned)((g.n[0] + bx - 1) / bx), (unsigned)g.n[1], (unsigned)g.n[2]);
+    pois_setup_kernel<T, D><<<gi, bx, 0, st>>>(x, eps, r, z, u, g, dtT);                            // :344-345
+    c->launches++;
+    CU_CHECK(c, cudaGetLastError());
+  }
+  int rc = psolver_t<T, D>(c, st, x, eps, r, z, L, Dg, iD, per, -1.0, 2000, iters, r2_out);         // :346
+  if (rc) return rc;
+  pois_apply_kernel<T, D><<<row_blocks(c), 256, 0, st>>>(u, L, x, g);                               // :331-333
+  scale_kernel<T><<<(unsigned)((g.S + 255) / 256), 256, 0, st>>>(x, T(1) / dtT, g.S);                // :334
+  c->launches += 2;
+  CU_CHECK(c, cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
+void ifadv_poisson_free(ifadv_ctx* c) {
+  if (!c || !c->pois_ctl) return;
+  cudaFree(c->pois_ctl);
+  cudaFreeHost(c->pois_host);
+  cudaEventDestroy(c->pois_ev[0]);
+  cudaEventDestroy(c->pois_ev[1]);
+  c->pois_ctl = nullptr;
+}
+
+#define POIS_DISPATCH(call2f, call3f, call2d, call3d)            \
+  if (c->dtype == IFADV_F32) return c->D == 2 ? call2f : call3f; \
+  return c->D == 2 ? call2d : call3d;
+
+extern "C" {
+int ifadv_poisson_update(ifadv_ctx* c, void* stream, void* Dg, void* iD, const void* L) {
+  if (!c) return -2;
+  if (!Dg || !iD || !L) return pfail(c, -2, "null array");
+  cudaStream_t st = (cudaStream_t)stream;
+  POIS_DISPATCH((update_t<float, 2>(c, st, (float*)Dg, (float*)iD, (const float*)L)), (update_t<float, 3>(c, st, (float*)Dg, (float*)iD, (const float*)L)),
+                (update_t<double, 2>(c, st, (double*)Dg, (double*)iD, (const double*)L)),
+                (update_t<double, 3>(c, st, (double*)Dg, (double*)iD, (const double*)L)))
+}
+
+int ifadv_psolver(ifadv_ctx* c, void* stream, void* x, void* eps, void* r, void* z, const void* L, const void* Dg, const void* iD,
+                  unsigned perdir_mask, double tol, int itmx, int* iters, double* r2) {
+  if (!c) return -2;
+  if (c->slab.nranks > 1) return pfail(c, -2, "the pressure solver is single-GPU");
+  if (!x || !eps || !r || !z || !L || !Dg || !iD) return pfail(c, -2, "null array");
+  cudaStream_t st = (cudaStream_t)stream;
+#define A_(T) (T*)x, (T*)eps, (T*)r, (T*)z, (const T*)L, (const T*)Dg, (const T*)iD, perdir_mask, tol, itmx, iters, r2
+  POIS_DISPATCH((psolver_t<float, 2>(c, st, A_(float))), (psolver_t<float, 3>(c, st, A_(float))), (psolver_t<double, 2>(c, st, A_(double))),
+                (psolver_t<double, 3>(c, st, A_(double))))
+#undef A_
+}
+
+int ifadv_myproject(ifadv_ctx* c, void* stream, void* u, void* x, void* eps, void* r, void* z, const void* L, const void* Dg, const void* iD,
+                    double dt, unsigned perdir_mask, int* iters, double* r2) {
+  if (!c) return -2;
+  if (c->slab.nranks > 1) return pfail(c, -2, "the pressure solver is single-GPU");
+  if (!u || !x || !eps || !r || !z || !L || !Dg || !iD) return pfail(c, -2, "null array");
+  if (!(dt != 0.0) || dt != dt) return pfail(c, -2, "invalid time step");
+  cudaStream_t st = (cudaStream_t)stream;
+#define A_(T) (T*)u, (T*)x, (T*)eps, (T*)r, (T*)z, (const T*)L, (const T*)Dg, (const T*)iD, dt, perdir_mask, iters, r2
+  POIS_DISPATCH((myproject_t<float, 2>(c, st, A_(float))), (myproject_t<float, 3>(c, st, A_(float))), (myproject_t<double, 2>(c, st, A_(double))),
+                (myproject_t<double, 3>(c, st, A_(double))))
+#undef A_
+}
+}  // extern "C"

@@ -1,0 +1,284 @@
+// ifadv_poisson.cuh -- variable-coefficient pressure projection: the reference's Jacobi-preconditioned
+// conjugate-gradient solver psolver! (src/flow.jl:300-326), inproject! (:343-347) and myproject! (:328-341) on WaterLily's Poisson
+// arrays (L ≡ Flow.μ₀, x ≡ Flow.p, z ≡ Flow.σ; D, iD, ϵ, r).
+//
+// The reference runs, per iteration, 2·|perdir| ghost-plane copies + 5 field passes + 3 dot products, each dot product a device ->
+// host synchronisation (alpha, beta and the loop condition are host scalars).  Here an iteration is three kernels and NO host round
+// trip: every scalar of the recurrence (rho, z·ϵ, beta, r₂, the iteration count, the loop condition) lives in a control block in
+// device memory, written by the LAST CTA of the kernel that completes the corresponding reduction:
+//   pois_mult_kernel    z = A ϵ on inside(x);                            Σ z·ϵ                                   (:312-313)   6 s B/cell
+//   pois_update_kernel  alpha = rho / (z·ϵ); x += alpha ϵ; r -= alpha z; z = r·iD;   Σ r·z, Σ r·r               (:313-317,321) 8 s B/cell
+//                       last CTA: beta = rho2/rho, rho = rho2, r₂, n += 1, done = !(r₂ > tol && n < itmx)        (:309,318,320)
+//   pois_dir_kernel     ϵ = beta ϵ + z                                                                           (:319)       3 s B/cell
+// (+ one launch for perBC!(ϵ) when a direction is periodic) = 17 s B per cell and iteration.  Kernels of iterations past convergence
+// return at once (they read `done`), so the host enqueues iterations in batches and polls the control block one batch behind.
+// Reductions: Float64 partial sums per CTA in a fixed order, summed by the last CTA in a fixed order (deterministic for a grid
+// size), rounded to T -- the reference's `⋅` is BLAS / CUBLAS dot with an unspecified order, so comparisons carry a tolerance.
+// Per-cell arithmetic follows the reference expression by expression (-fmad=false, IEEE division).
+#pragma once
+#include "ifadv_math.cuh"
+#include "ifadv_sweep.cuh"
+
+namespace ifadv {
+
+#define IFADV_POIS_MAXB 2048  // upper bound of the reduction grids
+
+struct PoisCtl {
+  double rho, zeps, beta, r2, mean, tol, r2_0;
+  int n, itmx, done, sub_mean;
+  unsigned ticket[4];
+  double part[3][IFADV_POIS_MAXB];
+};
+
+template <class T> struct teps;
+template <> struct teps<float> { static constexpr float v = 1.1920928955078125e-07f; };
+template <> struct teps<double> { static constexpr double v = 2.220446049250313e-16; };
+
+// CTA partial sums -> part[q][blockIdx.x]; returns true in every thread of the last CTA to arrive, with tot[q] the grid totals
+// (valid in thread 0).  NQ <= 2.
+template <int NQ> IFADV_DI bool grid_reduce(double (&v)[NQ], PoisCtl* ctl, int tk, double (&tot)[NQ]) {
+  __shared__ double ws[8][NQ];
+  __shared__ int last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    double t = v[q];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    if (lane == 0) ws[wid][q] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      double t = 0.0;
+      for (int w = 0; w < wpb; ++w) t += ws[w][q];
+      ctl->part[q][blockIdx.x] = t;
+    }
+    __threadfence();
+    last = (atomicAdd(&ctl->ticket[tk], 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return false;
+  __threadfence();
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    double t = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += __ldcg(&ctl->part[q][b]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    __syncthreads();
+    if (lane == 0) ws[wid][q] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      double t = 0.0;
+      for (int w = 0; w < wpb; ++w) t += ws[w][q];
+      tot[q] = t;
+    }
+    ctl->ticket[tk] = 0u;
+  }
+  return true;
+}
+
+// mult(I,L,D,x) = x[I]·D[I] + Σᵢ L[I,i]·x[I-δᵢ] + Σᵢ L[I+δᵢ,i]·x[I+δᵢ]   (WaterLily Poisson.jl, restated)
+template <class T, int D> IFADV_DI T pois_mult(const T* __restrict__ L, const T* __restrict__ Dg, const T* __restrict__ x, const Geo& g, long long l) {
+  T lo = T(0), up = T(0);
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const long long st = (i == 0) ? 1 : ((i == 1) ? g.s1 : g.s2);
+    lo = lo + __ldg(L + (long long)i * g.S + l) * __ldg(x + l - st);
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const long long st = (i == 0) ? 1 : ((i == 1) ? g.s1 : g.s2);
+    up = up + __ldg(L + (long long)i * g.S + l + st) * __ldg(x + l + st);
+  }
+  return __ldg(x + l) * __ldg(Dg + l) + lo + up;
+}
+
+// rows of inside(x) walked by warps, lanes along the contiguous dimension
+#define IFADV_POIS_ROWS(...)                                                                                   \
+  const int ny = g.n[1] - 2, nz = (D == 3) ? g.n[2] - 2 : 1;                                                   \
+  const long long rows = (long long)ny * nz;                                                                   \
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wid = threadIdx.x >> 5;                            \
+  for (long long rw = (long long)blockIdx.x * wpb + wid; rw < rows; rw += (long long)gridDim.x * wpb) {        \
+    const int y = 2 + (int)(rw % ny), zc = (D == 3) ? 2 + (int)(rw / ny) : 1;                                  \
+    const long long l0 = lin3(g, 0, y, zc);                                                                    \
+    for (int xc = 2 + lane; xc <= g.n[0] - 1; xc += 32) {                                                      \
+      const long long l = l0 + xc;                                                                             \
+      __VA_ARGS__                                                                                                  \
+    }                                                                                                          \
+  }
+
+// set_diag!(D,iD,L) = update!(p::Poisson): D = -Σᵢ (L[I,i] + L[I+δᵢ,i]); iD = D² < 2eps ? 0 : 1/D on inside
+template <class T, int D> __global__ void __launch_bounds__(256) pois_diag_kernel(T* __restrict__ Dg, T* __restrict__ iD, const T* __restrict__ L, const Geo g) {
+  IFADV_POIS_ROWS({
+    T s = T(0);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const long long st = (i == 0) ? 1 : ((i == 1) ? g.s1 : g.s2);
+      s = s - (__ldg(L + (long long)i * g.S + l) + __ldg(L + (long long)i * g.S + l + st));
+    }
+    Dg[l] = s;
+    iD[l] = (s * s < T(2) * teps<T>::v) ? T(0) : T(1) / s;
+  })
+}
+
+// perBC!(a,perdir): every cell with a ghost coordinate in a periodic direction takes the value of the cell with those coordinates
+// wrapped (closed form of the sequential plane copies; coordinates of non-periodic directions stay as they are)
+template <class T, int D> __global__ void perbc_kernel(T* a, const Geo g) {
+  const long long n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
+  const long long c0 = (g.per & 1u) ? 2 * n1 * n2 : 0, c1 = (g.per & 2u) ? 2 * n0 * n2 : 0, c2 = (D == 3 && (g.per & 4u)) ? 2 * n0 * n1 : 0;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= c0 + c1 + c2) return;
+  int x, y, z;
+  if (t < c0) { const long long r = t >> 1; x = (t & 1) ? (int)n0 : 1; y = (int)(r % n1) + 1; z = (int)(r / n1) + 1; }
+  else if (t < c0 + c1) { const long long q = t - c0, r = q >> 1; y = (q & 1) ? (int)n1 : 1; x = (int)(r % n0) + 1; z = (int)(r / n0) + 1; }
+  else { const long long q = t - c0 - c1, r = q >> 1; z = (q & 1) ? (int)n2 : 1; x = (int)(r % n0) + 1; y = (int)(r / n0) + 1; }
+  const int mx = (g.per & 1u) ? wrapc(x, g.n[0]) : x, my = (g.per & 2u) ? wrapc(y, g.n[1]) : y, mz = (D == 3 && (g.per & 4u)) ? wrapc(z, g.n[2]) : z;
+  a[lin3(g, x, y, z)] = a[lin3(g, mx, my, mz)];
+}
+
+// inproject!: z = div(I,u) on inside(z), 0 elsewhere; ϵ = r = 0; x *= dt over all entries        (flow.jl:344-345)
+template <class T, int D> __global__ void pois_setup_kernel(T* __restrict__ x, T* __restrict__ eps, T* __restrict__ r, T* __restrict__ z,
+                                                            const T* __restrict__ u, const Geo g, T dt) {
+  const int xc = 1 + blockIdx.x * blockDim.x + threadIdx.x, y = 1 + blockIdx.y, zc = 1 + blockIdx.z;
+  if (xc > g.n[0]) return;
+  const long long l = lin3(g, xc, y, zc);
+  const bool in = xc >= 2 && xc <= g.n[0] - 1 && y >= 2 && y <= g.n[1] - 1 && (D == 2 || (zc >= 2 && zc <= g.n[2] - 1));
+  T s = T(0);
+  if (in) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const long long st = (i == 0) ? 1 : ((i == 1) ? g.s1 : g.s2);
+      s = s + (__ldg(u + (long long)i * g.S + l + st) - __ldg(u + (long long)i * g.S + l));
+    }
+  }
+  z[l] = s;
+  eps[l] = T(0);
+  r[l] = T(0);
+  x[l] = x[l] * dt;
+}
+
+// residual!(p), first half: r = iD == 0 ? 0 : z - A x on inside;  Σ r -> mean s = Σr / |inside|, dropped when |s| <= 2eps
+template <class T, int D> __global__ void __launch_bounds__(256) pois_residual_kernel(T* __restrict__ r, const T* __restrict__ z, const T* __restrict__ x,
+                                                                                      const T* __restrict__ L, const T* __restrict__ Dg,
+                                                                                      const T* __restrict__ iD, const Geo g, PoisCtl* ctl,
+                                                                                      double tol, int itmx) {
+  double acc[1] = {0.0};
+  IFADV_POIS_ROWS({
+    const T v = (__ldg(iD + l) == T(0)) ? T(0) : __ldg(z + l) - pois_mult<T, D>(L, Dg, x, g, l);
+    r[l] = v;
+    acc[0] += (double)v;
+  })
+  double tot[1];
+  if (grid_reduce<1>(acc, ctl, 0, tot) && threadIdx.x == 0) {
+    const T s = (T)tot[0] / (T)(rows * (long long)(g.n[0] - 2));
+    const bool sub = !(t_abs(s) <= T(2) * teps<T>::v);
+    ctl->mean = (double)s;
+    ctl->sub_mean = sub ? 1 : 0;
+    ctl->tol = tol;
+    ctl->itmx = itmx;
+    ctl->n = 0;
+    ctl->done = 0;
+  }
+}
+
+// residual!, second half (r -= s) fused with psolver!'s start: z = ϵ = r·iD; r₂ = r·r, rho = r·z          (flow.jl:302-307)
+template <class T, int D> __global__ void __launch_bounds__(256) pois_start_kernel(T* __restrict__ r, T* __restrict__ z, T* __restrict__ eps,
+                                                                                   const T* __restrict__ iD, const Geo g, PoisCtl* ctl) {
+  const bool sub = ctl->sub_mean != 0;
+  const T s = (T)ctl->mean;
+  double acc[2] = {0.0, 0.0};
+  IFADV_POIS_ROWS({
+    T rv = r[l];
+    if (sub) { rv = rv - s; r[l] = rv; }
+    const T zv = rv * __ldg(iD + l);
+    z[l] = zv;
+    eps[l] = zv;
+    acc[0] += (double)rv * (double)rv;
+    acc[1] += (double)rv * (double)zv;
+  })
+  double tot[2];
+  if (grid_reduce<2>(acc, ctl, 1, tot) && threadIdx.x == 0) {
+    const T r2 = (T)tot[0], tol = (T)ctl->tol;
+    ctl->r2 = (double)r2;
+    ctl->r2_0 = (double)r2;
+    ctl->rho = (double)(T)tot[1];
+    ctl->done = ((r2 > tol || r2 > tol / T(4)) && 0 < ctl->itmx) ? 0 : 1;  // :309 with nᵖ == 0
+  }
+}
+
+// z = A ϵ on inside;  Σ z·ϵ                                                                              (flow.jl:312-313)
+template <class T, int D> __global__ void __launch_bounds__(256) pois_mult_kernel(T* __restrict__ z, const T* __restrict__ eps, const T* __restrict__ L,
+                                                                                  const T* __restrict__ Dg, const Geo g, PoisCtl* ctl) {
+  if (ctl->done) return;
+  double acc[1] = {0.0};
+  IFADV_POIS_ROWS({
+    const T v = pois_mult<T, D>(L, Dg, eps, g, l);
+    z[l] = v;
+    acc[0] += (double)v * (double)__ldg(eps + l);
+  })
+  double tot[1];
+  if (grid_reduce<1>(acc, ctl, 2, tot) && threadIdx.x == 0) ctl->zeps = (double)(T)tot[0];
+}
+
+// x += alpha ϵ; r -= alpha z; z = r·iD;  Σ r·z, Σ r·r; last CTA: the scalar recurrence and the loop condition   (flow.jl:313-321)
+template <class T, int D> __global__ void __launch_bounds__(256) pois_update_kernel(T* __restrict__ x, T* __restrict__ r, T* __restrict__ z,
+                                                                                    const T* __restrict__ eps, const T* __restrict__ iD, const Geo g,
+                                                                                    PoisCtl* ctl) {
+  if (ctl->done) return;
+  const T alpha = (T)ctl->rho / (T)ctl->zeps;
+  double acc[2] = {0.0, 0.0};
+  IFADV_POIS_ROWS({
+    x[l] = x[l] + alpha * __ldg(eps + l);
+    const T rv = r[l] - alpha * z[l];
+    r[l] = rv;
+    const T zv = rv * __ldg(iD + l);
+    z[l] = zv;
+    acc[0] += (double)rv * (double)zv;
+    acc[1] += (double)rv * (double)rv;
+  })
+  double tot[2];
+  if (grid_reduce<2>(acc, ctl, 3, tot) && threadIdx.x == 0) {
+    const T rho2 = (T)tot[0], r2 = (T)tot[1];
+    ctl->beta = (double)(rho2 / (T)ctl->rho);
+    ctl->rho = (double)rho2;
+    ctl->r2 = (double)r2;
+    const int n = ctl->n + 1;
+    ctl->n = n;
+    ctl->done = (r2 > (T)ctl->tol && n < ctl->itmx) ? 0 : 1;
+  }
+}
+
+// ϵ = beta ϵ + z on inside; runs iff the update kernel of iteration `it` ran (n == it + 1)                 (flow.jl:319)
+template <class T, int D> __global__ void __launch_bounds__(256) pois_dir_kernel(T* __restrict__ eps, const T* __restrict__ z, const Geo g,
+                                                                                 const PoisCtl* ctl, int it) {
+  if (ctl->n != it + 1) return;
+  const T beta = (T)ctl->beta;
+  IFADV_POIS_ROWS({ eps[l] = beta * eps[l] + __ldg(z + l); })
+}
+
+// myproject!: u[I,i] -= L[I,i]·∂(i,I,x) on inside(x)                                                      (flow.jl:331-333)
+template <class T, int D> __global__ void __launch_bounds__(256) pois_apply_kernel(T* __restrict__ u, const T* __restrict__ L, const T* __restrict__ x,
+                                                                                   const Geo g) {
+  IFADV_POIS_ROWS({
+    const T xc_ = __ldg(x + l);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const long long st = (i == 0) ? 1 : ((i == 1) ? g.s1 : g.s2);
+      const long long li = (long long)i * g.S + l;
+      u[li] = u[li] - __ldg(L + li) * (xc_ - __ldg(x + l - st));
+    }
+  })
+}
+
+template <class T> __global__ void scale_kernel(T* a, T s, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = a[i] * s;
+}
+
+}  // namespace ifadv

@@ -108,8 +108,9 @@ def oracle_mom_step_hook(st, f, u, dt, dirO, hook, lam="Koren", scheme="WH"):
     return a["rhou"]
 
 
-def oracle_mom_step_forcing(st, a, f, u, dt, dirO, mu, lam_mu, eta, g, lam="Koren", scheme="WH"):
-    """MPFMomStep! with its explicit forcing and without the Poisson solve (flow.jl:60-107 minus :81-82,:105-106) on the oracle.
+def oracle_mom_step_forcing(st, a, f, u, dt, dirO, mu, lam_mu, eta, g, lam="Koren", scheme="WH", pois=None):
+    """MPFMomStep! with its explicit forcing (flow.jl:60-107) on the oracle; pois=None leaves the Poisson solve out (:81-82,:105-106),
+    pois = O.Poisson(p, a["mu0"], a["Phi"]) runs update!(b); myproject!(a,b[,1/2]); BC! at its two places.
     `a` is the persistent array set of alloc_cmom (the reference's aliasing: uStar≡n̂, dilaU≡α, r≡flow.f, Φ≡flow.σ, fbuffer≡fᶠ) plus
     "mu0"; f and u are advanced in place.  Mirrors api.mom_step_forcing."""
     T = st["dtype"]
@@ -125,6 +126,8 @@ def oracle_mom_step_forcing(st, a, f, u, dt, dirO, mu, lam_mu, eta, g, lam="Kore
     O.updateU(u, a["rhou"], a["nhat"], a["r"], dt, f0, lr, g, 0.5)                                      # :77
     O.BC(u, uBC, False, pd)                                                                             # :79
     O.updateL(a["mu0"], f0, lr, pd)                                                                     # :80
+    if pois is not None:
+        pois.update(); O.myproject(u, pois, T(0.5) * T(dt)); O.BC(u, uBC, False, pd)                    # :81-82
     f0[...] = f                                                                                         # :89
     O.u2rhou(a["rhou"], u0, f, lr); O.BC(a["rhou"], uBC, False, pd)                                     # :91
     O.advectVOFrhouu(f, a["ff"], a["alpha"], a["nhat"], u, u, dt, a["cbar"], a["rhou"], a["r"], a["Phi"], a["rhouf"], a["nhat"], u0,
@@ -136,4 +139,6 @@ def oracle_mom_step_forcing(st, a, f, u, dt, dirO, mu, lam_mu, eta, g, lam="Kore
     O.updateU(u, a["rhou"], a["nhat"], a["r"], dt, f, lr, g, 1.0)                                       # :101
     O.BC(u, uBC, False, pd)                                                                             # :103
     O.updateL(a["mu0"], f, lr, pd)                                                                      # :104
+    if pois is not None:
+        pois.update(); O.myproject(u, pois, T(1) * T(dt)); O.BC(u, uBC, False, pd)                      # :105-106
     return a["rhou"]
