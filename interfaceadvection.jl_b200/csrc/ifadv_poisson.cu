@@ -31,6 +31,14 @@ inline unsigned row_blocks(const ifadv_ctx* c) {
   const long long rows = (long long)(c->g.n[1] - 2) * (c->D == 3 ? c->g.n[2] - 2 : 1);
   return (unsigned)std::max<long long>(1, std::min<long long>((rows + 7) / 8, std::min(148LL * 6, (long long)IFADV_POIS_MAXB)));
 }
+// persistent grids: as many CTAs as are resident at once for that kernel (its register count decides), never more than the rows give
+template <class K> unsigned resident_blocks(const ifadv_ctx* c, K kernel) {
+  int occ = 0, sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0) != cudaSuccess || occ < 1) occ = 2;
+  const long long rows = (long long)(c->g.n[1] - 2) * (c->D == 3 ? c->g.n[2] - 2 : 1);
+  return (unsigned)std::max<long long>(1, std::min<long long>((rows + 7) / 8, std::min<long long>((long long)sms * occ, IFADV_POIS_MAXB)));
+}
 template <class T, int D> int perbc_launch(ifadv_ctx* c, cudaStream_t st, T* a, unsigned per) {
   Geo g = c->g;
   g.per = per & ((1u << D) - 1u);
@@ -57,6 +65,8 @@ int psolver_t(ifadv_ctx* c, cudaStream_t st, T* x, T* eps, T* r, T* z, const T* 
   if (rc) return rc;
   PoisCtl* ctl = (PoisCtl*)c->pois_ctl;
   const unsigned nb = row_blocks(c);
+  const unsigned nb_mult = resident_blocks(c, pois_mult_kernel<T, D>), nb_upd = resident_blocks(c, pois_update_kernel<T, D>),
+                 nb_dir = resident_blocks(c, pois_dir_kernel<T, D>);
   const Geo g = c->g;
   const double tolT = tol < 0 ? (double)(T(50) * std::numeric_limits<T>::epsilon()) : (double)(T)tol;
   if (itmx <= 0) itmx = 6000;
@@ -84,9 +94,9 @@ int psolver_t(ifadv_ctx* c, cudaStream_t st, T* x, T* eps, T* r, T* z, const T* 
       const int end = std::min(itmx, it + batch);
       for (; it < end; ++it) {
         if ((rc = perbc_launch<T, D>(c, st, eps, per))) return rc;                                 // :311
-        pois_mult_kernel<T, D><<<nb, 256, 0, st>>>(z, eps, L, Dg, g, ctl);                         // :312-313
-        pois_update_kernel<T, D><<<nb, 256, 0, st>>>(x, r, z, eps, iD, g, ctl);                    // :313-321
-        pois_dir_kernel<T, D><<<nb, 256, 0, st>>>(eps, z, g, ctl, it);                             // :319
+        pois_mult_kernel<T, D><<<nb_mult, 256, 0, st>>>(z, eps, L, Dg, g, ctl);                         // :312-313
+        pois_update_kernel<T, D><<<nb_upd, 256, 0, st>>>(x, r, z, eps, iD, g, ctl);                    // :313-321
+        pois_dir_kernel<T, D><<<nb_dir, 256, 0, st>>>(eps, z, g, ctl, it);                             // :319
         c->launches += 3;
       }
       CU_CHECK(c, cudaGetLastError());

@@ -113,11 +113,26 @@ template <class T, int D> IFADV_DI T pois_mult(const T* __restrict__ L, const T*
     }                                                                                                          \
   }
 
+// The same walk with U cells per lane and trip: the kernels below load all U cells first, then compute, then store, so that a thread
+// keeps U times as many loads in flight (the solver is a pure streaming workload: latency x bandwidth needs ~40 KB in flight per SM).
+#define IFADV_POIS_ROWS_U(U, ...)                                                                              \
+  const int ny = g.n[1] - 2, nz = (D == 3) ? g.n[2] - 2 : 1;                                                   \
+  const long long rows = (long long)ny * nz;                                                                   \
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wid = threadIdx.x >> 5;                            \
+  const int xlast = g.n[0] - 1;                                                                                \
+  for (long long rw = (long long)blockIdx.x * wpb + wid; rw < rows; rw += (long long)gridDim.x * wpb) {        \
+    const int y = 2 + (int)(rw % ny), zc = (D == 3) ? 2 + (int)(rw / ny) : 1;                                  \
+    const long long l0 = lin3(g, 0, y, zc);                                                                    \
+    for (int xb = 2 + lane; xb <= xlast; xb += 32 * (U)) {                                                     \
+      __VA_ARGS__                                                                                              \
+    }                                                                                                          \
+  }
+
 // set_diag!(D,iD,L) = update!(p::Poisson): D = -Σᵢ (L[I,i] + L[I+δᵢ,i]); iD = D² < 2eps ? 0 : 1/D on inside
 template <class T, int D> __global__ void __launch_bounds__(256) pois_diag_kernel(T* __restrict__ Dg, T* __restrict__ iD, const T* __restrict__ L, const Geo g) {
   IFADV_POIS_ROWS({
     T s = T(0);
-#pragma unroll
+_Pragma("unroll")
     for (int i = 0; i < D; ++i) {
       const long long st = (i == 0) ? 1 : ((i == 1) ? g.s1 : g.s2);
       s = s - (__ldg(L + (long long)i * g.S + l) + __ldg(L + (long long)i * g.S + l + st));
@@ -216,11 +231,41 @@ template <class T, int D> __global__ void __launch_bounds__(256) pois_start_kern
 template <class T, int D> __global__ void __launch_bounds__(256) pois_mult_kernel(T* __restrict__ z, const T* __restrict__ eps, const T* __restrict__ L,
                                                                                   const T* __restrict__ Dg, const Geo g, PoisCtl* ctl) {
   if (ctl->done) return;
+  constexpr int U = (sizeof(T) == 4) ? 4 : 2;
   double acc[1] = {0.0};
-  IFADV_POIS_ROWS({
-    const T v = pois_mult<T, D>(L, Dg, eps, g, l);
-    z[l] = v;
-    acc[0] += (double)v * (double)__ldg(eps + l);
+  IFADV_POIS_ROWS_U(U, {
+    T ec[U], dg[U], ll[U][D], lu[U][D], em[U][D], ep[U][D];
+_Pragma("unroll")
+    for (int k = 0; k < U; ++k) {
+      const int xc = xb + 32 * k;
+      if (xc <= xlast) {
+        const long long l = l0 + xc;
+        ec[k] = __ldg(eps + l);
+        dg[k] = __ldg(Dg + l);
+_Pragma("unroll")
+        for (int i = 0; i < D; ++i) {
+          const long long st = (i == 0) ? 1 : ((i == 1) ? g.s1 : g.s2);
+          ll[k][i] = __ldg(L + (long long)i * g.S + l);
+          lu[k][i] = __ldg(L + (long long)i * g.S + l + st);
+          em[k][i] = __ldg(eps + l - st);
+          ep[k][i] = __ldg(eps + l + st);
+        }
+      }
+    }
+_Pragma("unroll")
+    for (int k = 0; k < U; ++k) {
+      const int xc = xb + 32 * k;
+      if (xc <= xlast) {
+        T lo = T(0), up = T(0);
+_Pragma("unroll")
+        for (int i = 0; i < D; ++i) lo = lo + ll[k][i] * em[k][i];
+_Pragma("unroll")
+        for (int i = 0; i < D; ++i) up = up + lu[k][i] * ep[k][i];
+        const T v = ec[k] * dg[k] + lo + up;
+        z[l0 + xc] = v;
+        acc[0] += (double)v * (double)ec[k];
+      }
+    }
   })
   double tot[1];
   if (grid_reduce<1>(acc, ctl, 2, tot) && threadIdx.x == 0) ctl->zeps = (double)(T)tot[0];
@@ -232,15 +277,32 @@ template <class T, int D> __global__ void __launch_bounds__(256) pois_update_ker
                                                                                     PoisCtl* ctl) {
   if (ctl->done) return;
   const T alpha = (T)ctl->rho / (T)ctl->zeps;
+  constexpr int U = (sizeof(T) == 4) ? 8 : 4;
   double acc[2] = {0.0, 0.0};
-  IFADV_POIS_ROWS({
-    x[l] = x[l] + alpha * __ldg(eps + l);
-    const T rv = r[l] - alpha * z[l];
-    r[l] = rv;
-    const T zv = rv * __ldg(iD + l);
-    z[l] = zv;
-    acc[0] += (double)rv * (double)zv;
-    acc[1] += (double)rv * (double)rv;
+  IFADV_POIS_ROWS_U(U, {
+    T xv[U], ev[U], rv[U], zv[U], dv[U];
+_Pragma("unroll")
+    for (int k = 0; k < U; ++k) {
+      const int xc = xb + 32 * k;
+      if (xc <= xlast) {
+        const long long l = l0 + xc;
+        xv[k] = x[l]; ev[k] = __ldg(eps + l); rv[k] = r[l]; zv[k] = z[l]; dv[k] = __ldg(iD + l);
+      }
+    }
+_Pragma("unroll")
+    for (int k = 0; k < U; ++k) {
+      const int xc = xb + 32 * k;
+      if (xc <= xlast) {
+        const long long l = l0 + xc;
+        x[l] = xv[k] + alpha * ev[k];
+        const T rn = rv[k] - alpha * zv[k];
+        r[l] = rn;
+        const T zn = rn * dv[k];
+        z[l] = zn;
+        acc[0] += (double)rn * (double)zn;
+        acc[1] += (double)rn * (double)rn;
+      }
+    }
   })
   double tot[2];
   if (grid_reduce<2>(acc, ctl, 3, tot) && threadIdx.x == 0) {
@@ -259,7 +321,20 @@ template <class T, int D> __global__ void __launch_bounds__(256) pois_dir_kernel
                                                                                  const PoisCtl* ctl, int it) {
   if (ctl->n != it + 1) return;
   const T beta = (T)ctl->beta;
-  IFADV_POIS_ROWS({ eps[l] = beta * eps[l] + __ldg(z + l); })
+  constexpr int U = (sizeof(T) == 4) ? 8 : 4;
+  IFADV_POIS_ROWS_U(U, {
+    T ev[U], zv[U];
+_Pragma("unroll")
+    for (int k = 0; k < U; ++k) {
+      const int xc = xb + 32 * k;
+      if (xc <= xlast) { ev[k] = eps[l0 + xc]; zv[k] = __ldg(z + l0 + xc); }
+    }
+_Pragma("unroll")
+    for (int k = 0; k < U; ++k) {
+      const int xc = xb + 32 * k;
+      if (xc <= xlast) eps[l0 + xc] = beta * ev[k] + zv[k];
+    }
+  })
 }
 
 // myproject!: u[I,i] -= L[I,i]·∂(i,I,x) on inside(x)                                                      (flow.jl:331-333)
@@ -267,7 +342,7 @@ template <class T, int D> __global__ void __launch_bounds__(256) pois_apply_kern
                                                                                    const Geo g) {
   IFADV_POIS_ROWS({
     const T xc_ = __ldg(x + l);
-#pragma unroll
+_Pragma("unroll")
     for (int i = 0; i < D; ++i) {
       const long long st = (i == 0) ? 1 : ((i == 1) ? g.s1 : g.s2);
       const long long li = (long long)i * g.S + l;

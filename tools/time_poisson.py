@@ -25,7 +25,7 @@ def run(N, T, itmx, perdir=()):
     # fixed number of iterations through psolver (the source is ∇·u)
     u0 = a.u.clone()
     res = []
-    for rep in range(3):
+    for rep in range(1 if len(sys.argv) > 1 else 3):
         a.u.copy_(u0); a.p.zero_()
         ia.myproject(a, b, 1.0) if rep == 0 and itmx is None else None
         b.z.zero_(); b.x.zero_()
@@ -51,9 +51,12 @@ def run(N, T, itmx, perdir=()):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:  # N dtype itmx: one configuration (for ncu)
+        n = int(sys.argv[1])
+        run((n, n, n), getattr(torch, sys.argv[2]), int(sys.argv[3]))
+        sys.exit(0)
     run((64, 64, 64), torch.float32, 200)
     run((256, 256, 256), torch.float32, 200)
     run((256, 256, 256), torch.float64, 200)
     run((512, 512, 512), torch.float32, 100)
     run((512, 512, 512), torch.float32, 100, perdir=(1, 2))
-    run((256, 256, 256), torch.float32, None)
