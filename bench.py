@@ -521,6 +521,19 @@ def run_b200(args):
         torch.cuda.empty_cache()
         forcing_line = tf.measure(w["N"][0], w["dtype"] == "float64", 5, dev)
 
+    # ---- next to the path: the reference's Jacobi-PCG pressure solver on the same grid, timed on its own ----
+    projection_line = None
+    if not args.no_extra and world == 1 and D == 3:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("time_poisson", os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "time_poisson.py"))
+        tp = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(tp)
+        ia.api._contexts.clear()
+        torch.cuda.empty_cache()
+        projection_line = tp.measure(w["N"][0], w["dtype"] == "float64", 50, dev, cpu_n=0 if args.no_cpu else 128)
+        ia.api._contexts.clear()
+        torch.cuda.empty_cache()
+
     # ---- e2e: the reference-facing C-ABI call with HOST buffers (H2D/D2H inside the timed region) ----
     e2e = None
     if not args.no_e2e:
@@ -555,7 +568,7 @@ def run_b200(args):
                        "nccl_bytes_sent_per_rank_per_step": int(sent / (args.steps + args.warmup)) if world > 1 else 0,
                        "mass_drift_rel": r["mass_drift_rel"]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": r["launches"], "clocks": r["clocks"],
-            "slab_check": bitwise, "tgv_line": tgv_line, "c5": c5_line, "forcing": forcing_line,
+            "slab_check": bitwise, "tgv_line": tgv_line, "c5": c5_line, "forcing": forcing_line, "projection": projection_line,
         }
         print(json.dumps(line))
     if dist is not None:

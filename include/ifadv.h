@@ -177,7 +177,10 @@ int ifadv_metrics(ifadv_ctx* ctx, void* stream, const void* u, const void* f, do
 /* Σ EnsI(I,ω) over the inside cells; ω: vector field in 3-D, scalar field in 2-D                              src/metrics.jl:34-41 */
 int ifadv_enstrophy(ifadv_ctx* ctx, void* stream, const void* omega, double* out);
 
-/* ---- pressure projection (single-GPU contexts) -------------------------------------------------------------
+/* ---- pressure projection ----------------------------------------------------------------------------------
+ * z-slab contexts: the dot products are all-reduced over the communicator, the ghost plane of ϵ (every iteration) and of x (at both
+ * ends) comes from the z-neighbours, only the owned planes are updated; the caller refreshes the ghost planes of u afterwards
+ * (ifadv_exchange_planes) and passes a perdir_mask without the z bit, as for the transport.
  * On WaterLily's Poisson arrays: L ≡ Flow.μ₀ (face coefficients, (Ng...,D)), x ≡ Flow.p, z ≡ Flow.σ, and the solver's own D, iD, ϵ, r
  * (scalar fields).  WaterLily's primitives (set_diag!, mult, perBC!, residual!, L₂) are restated from its published 1.x source.
  * update!(p::Poisson) = set_diag!(D,iD,L): D = -Σᵢ(L[I,i]+L[I+δᵢ,i]), iD = D² < 2eps ? 0 : 1/D on inside(x)     flow.jl:81,105 */

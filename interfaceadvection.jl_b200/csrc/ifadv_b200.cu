@@ -844,6 +844,17 @@ template <class T> static int update_l_t(ifadv_ctx* c, cudaStream_t st, T* mu0, 
 // ------------------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------------------
+// helpers of the slab-aware pressure solver (ifadv_poisson.cu): sum all-reduce of n doubles in device memory, exchange of `planes`
+// ghost planes of a scalar field with both z-neighbours
+int ifadv_slab_allreduce_sum(ifadv_ctx* c, cudaStream_t st, double* dev, int n) {
+  if (c->slab.nranks <= 1) return 0;
+  if (!nccl_api()->ok) return fail(c, -4, "NCCL is not available");
+  NCCL_CHECK(c, nccl_api()->AllReduce(dev, dev, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)c->slab.comm, st));
+  return 0;
+}
+int ifadv_slab_exchange_scalar(ifadv_ctx* c, cudaStream_t st, void* field, size_t esz, int planes) {
+  return slab_exchange(c, st, field, esz, 1, planes, planes);
+}
 namespace { void host_pipe_free(ifadv_ctx* c); }  // z-slab pipeline of the host-buffer entry point, defined below
 
 extern "C" {

@@ -73,6 +73,7 @@ struct ifadv_ctx {
   void* pois_ctl;
   void* pois_host;
   cudaEvent_t pois_ev[2];
+  int pois_slab_flag;  // what the control block's `slab` field holds
 };
 void ifadv_poisson_free(ifadv_ctx* c);  // ifadv_poisson.cu
 #define IFADV_PROF_MAX 4096

@@ -12,6 +12,10 @@
 
 using namespace ifadv;
 
+// ifadv_b200.cu: the z-slab transport (NCCL / CUDA-IPC copy engines) behind two small helpers
+int ifadv_slab_allreduce_sum(ifadv_ctx* c, cudaStream_t st, double* dev, int n);
+int ifadv_slab_exchange_scalar(ifadv_ctx* c, cudaStream_t st, void* field, size_t esz, int planes);
+
 namespace {
 int pfail(ifadv_ctx* c, int code, const char* msg) {
   if (c) c->err = msg;
@@ -22,13 +26,15 @@ int pois_alloc(ifadv_ctx* c) {
   if (c->pois_ctl) return 0;
   CU_CHECK(c, cudaMalloc(&c->pois_ctl, sizeof(PoisCtl)));
   CU_CHECK(c, cudaMemset(c->pois_ctl, 0, sizeof(PoisCtl)));
+  c->pois_slab_flag = 0;
   CU_CHECK(c, cudaMallocHost(&c->pois_host, 2 * 256));
   CU_CHECK(c, cudaEventCreateWithFlags(&c->pois_ev[0], cudaEventDisableTiming));
   CU_CHECK(c, cudaEventCreateWithFlags(&c->pois_ev[1], cudaEventDisableTiming));
   return 0;
 }
+inline long long owned_rows(const ifadv_ctx* c) { return (long long)(c->g.n[1] - 2) * (c->D == 3 ? c->kz1 - c->kz0 : 1); }
 inline unsigned row_blocks(const ifadv_ctx* c) {
-  const long long rows = (long long)(c->g.n[1] - 2) * (c->D == 3 ? c->g.n[2] - 2 : 1);
+  const long long rows = owned_rows(c);
   return (unsigned)std::max<long long>(1, std::min<long long>((rows + 7) / 8, std::min(148LL * 6, (long long)IFADV_POIS_MAXB)));
 }
 // persistent grids: as many CTAs as are resident at once for that kernel (its register count decides), never more than the rows give
@@ -36,7 +42,7 @@ template <class K> unsigned resident_blocks(const ifadv_ctx* c, K kernel) {
   int occ = 0, sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0) != cudaSuccess || occ < 1) occ = 2;
-  const long long rows = (long long)(c->g.n[1] - 2) * (c->D == 3 ? c->g.n[2] - 2 : 1);
+  const long long rows = owned_rows(c);
   return (unsigned)std::max<long long>(1, std::min<long long>((rows + 7) / 8, std::min<long long>((long long)sms * occ, IFADV_POIS_MAXB)));
 }
 template <class T, int D> int perbc_launch(ifadv_ctx* c, cudaStream_t st, T* a, unsigned per) {
@@ -51,28 +57,53 @@ template <class T, int D> int perbc_launch(ifadv_ctx* c, cudaStream_t st, T* a, 
   return 0;
 }
 template <class T, int D> int update_t(ifadv_ctx* c, cudaStream_t st, T* Dg, T* iD, const T* L) {
-  pois_diag_kernel<T, D><<<row_blocks(c), 256, 0, st>>>(Dg, iD, L, c->g);
+  pois_diag_kernel<T, D><<<row_blocks(c), 256, 0, st>>>(Dg, iD, L, c->g, c->kz0, c->kz1);
   c->launches++;
   CU_CHECK(c, cudaGetLastError());
   return 0;
 }
 
-// psolver!(p;tol,itmx), src/flow.jl:300-326
+// psolver!(p;tol,itmx), src/flow.jl:300-326.  z-slab contexts: every reduction is followed by an all-reduce of the ranks' sums and a
+// one-thread kernel that applies the scalar step (all ranks hold identical scalars, so they take identical decisions); the ghost
+// plane of ϵ (and of x at both ends) comes from the z-neighbours.
 template <class T, int D>
 int psolver_t(ifadv_ctx* c, cudaStream_t st, T* x, T* eps, T* r, T* z, const T* L, const T* Dg, const T* iD, unsigned per, double tol, int itmx,
               int* iters, double* r2_out) {
   int rc = pois_alloc(c);
   if (rc) return rc;
   PoisCtl* ctl = (PoisCtl*)c->pois_ctl;
+  const bool slab = c->slab.nranks > 1;
+  const int kz0 = c->kz0, kz1 = c->kz1;
   const unsigned nb = row_blocks(c);
   const unsigned nb_mult = resident_blocks(c, pois_mult_kernel<T, D>), nb_upd = resident_blocks(c, pois_update_kernel<T, D>),
                  nb_dir = resident_blocks(c, pois_dir_kernel<T, D>);
   const Geo g = c->g;
   const double tolT = tol < 0 ? (double)(T(50) * std::numeric_limits<T>::epsilon()) : (double)(T)tol;
   if (itmx <= 0) itmx = 6000;
-  if ((rc = perbc_launch<T, D>(c, st, x, per))) return rc;                                        // :301 (and residual!'s own)
-  pois_residual_kernel<T, D><<<nb, 256, 0, st>>>(r, z, x, L, Dg, iD, g, ctl, tolT, itmx);          // :302
-  pois_start_kernel<T, D><<<nb, 256, 0, st>>>(r, z, eps, iD, g, ctl);                              // :302-307
+  if (c->pois_slab_flag != (slab ? 1 : 0)) {
+    const int v = slab ? 1 : 0;
+    CU_CHECK(c, cudaMemcpyAsync(&ctl->slab, &v, sizeof(int), cudaMemcpyHostToDevice, st));
+    CU_CHECK(c, cudaStreamSynchronize(st));
+    c->pois_slab_flag = v;
+  }
+  auto reduce_fin = [&](int which, int nacc) -> int {  // z-slab: all-reduce the sums of the kernel just launched, then the scalar step
+    if (!slab) return 0;
+    int e = ifadv_slab_allreduce_sum(c, st, ctl->acc, nacc);
+    if (e) return e;
+    pois_fin_kernel<T><<<1, 1, 0, st>>>(ctl, which, tolT, itmx);
+    c->launches++;
+    return 0;
+  };
+  auto ghosts = [&](T* a) -> int {  // perBC! in x, y (and z on one GPU) + the z-neighbours' plane
+    int e = perbc_launch<T, D>(c, st, a, per);
+    if (e) return e;
+    return slab ? ifadv_slab_exchange_scalar(c, st, a, sizeof(T), 1) : 0;
+  };
+  if ((rc = ghosts(x))) return rc;                                                                  // :301 (and residual!'s own)
+  pois_residual_kernel<T, D><<<nb, 256, 0, st>>>(r, z, x, L, Dg, iD, g, ctl, tolT, itmx, kz0, kz1);  // :302
+  if ((rc = reduce_fin(0, 2))) return rc;
+  pois_start_kernel<T, D><<<nb, 256, 0, st>>>(r, z, eps, iD, g, ctl, kz0, kz1);                      // :302-307
+  if ((rc = reduce_fin(1, 2))) return rc;
   c->launches += 2;
   CU_CHECK(c, cudaGetLastError());
   // Iterations are enqueued in batches; the control block of batch k is read back while batch k+1 is already queued, so the device
@@ -85,7 +116,8 @@ int psolver_t(ifadv_ctx* c, cudaStream_t st, T* x, T* eps, T* r, T* z, const T* 
     CU_CHECK(c, cudaEventRecord(c->pois_ev[slot], st));
     return 0;
   };
-  int it = 0, last = 0, batch = 8;
+  const int batch_max = slab ? 8 : 64;  // the collectives of a z-slab run are not skipped past convergence: keep the overshoot short
+  int it = 0, last = 0, batch = slab ? 4 : 8;
   Poll res{};
   if ((rc = poll(last))) return rc;  // behind the start kernel
   for (;;) {
@@ -93,23 +125,25 @@ int psolver_t(ifadv_ctx* c, cudaStream_t st, T* x, T* eps, T* r, T* z, const T* 
     if (it < itmx) {
       const int end = std::min(itmx, it + batch);
       for (; it < end; ++it) {
-        if ((rc = perbc_launch<T, D>(c, st, eps, per))) return rc;                                 // :311
-        pois_mult_kernel<T, D><<<nb_mult, 256, 0, st>>>(z, eps, L, Dg, g, ctl);                         // :312-313
-        pois_update_kernel<T, D><<<nb_upd, 256, 0, st>>>(x, r, z, eps, iD, g, ctl);                    // :313-321
-        pois_dir_kernel<T, D><<<nb_dir, 256, 0, st>>>(eps, z, g, ctl, it);                             // :319
+        if ((rc = ghosts(eps))) return rc;                                                           // :311
+        pois_mult_kernel<T, D><<<nb_mult, 256, 0, st>>>(z, eps, L, Dg, g, ctl, kz0, kz1);            // :312-313
+        if ((rc = reduce_fin(2, 1))) return rc;
+        pois_update_kernel<T, D><<<nb_upd, 256, 0, st>>>(x, r, z, eps, iD, g, ctl, kz0, kz1);        // :313-321
+        if ((rc = reduce_fin(3, 2))) return rc;
+        pois_dir_kernel<T, D><<<nb_dir, 256, 0, st>>>(eps, z, g, ctl, it, kz0, kz1);                 // :319
         c->launches += 3;
       }
       CU_CHECK(c, cudaGetLastError());
       if ((rc = poll(last ^ 1))) return rc;
       queued = true;
-      batch = std::min(64, batch * 2);
+      batch = std::min(batch_max, batch * 2);
     }
     CU_CHECK(c, cudaEventSynchronize(c->pois_ev[last]));
     memcpy(&res, host + 256 * last, sizeof(Poll));
     if (res.done || !queued) break;  // converged (what is still queued returns at once), or all itmx iterations were behind this poll
     last ^= 1;
   }
-  if ((rc = perbc_launch<T, D>(c, st, x, per))) return rc;                                          // :325
+  if ((rc = ghosts(x))) return rc;                                                                  // :325
   if (iters) *iters = res.n;
   if (r2_out) *r2_out = res.r2;
   if (res.r2 != res.r2) return pfail(c, -1, "NaN in the pressure solver");
@@ -131,7 +165,7 @@ int myproject_t(ifadv_ctx* c, cudaStream_t st, T* u, T* x, T* eps, T* r, T* z, c
   }
   int rc = psolver_t<T, D>(c, st, x, eps, r, z, L, Dg, iD, per, -1.0, 2000, iters, r2_out);         // :346
   if (rc) return rc;
-  pois_apply_kernel<T, D><<<row_blocks(c), 256, 0, st>>>(u, L, x, g);                               // :331-333
+  pois_apply_kernel<T, D><<<row_blocks(c), 256, 0, st>>>(u, L, x, g, c->kz0, c->kz1);               // :331-333 (owned planes)
   scale_kernel<T><<<(unsigned)((g.S + 255) / 256), 256, 0, st>>>(x, T(1) / dtT, g.S);                // :334
   c->launches += 2;
   CU_CHECK(c, cudaGetLastError());
@@ -165,7 +199,6 @@ int ifadv_poisson_update(ifadv_ctx* c, void* stream, void* Dg, void* iD, const v
 int ifadv_psolver(ifadv_ctx* c, void* stream, void* x, void* eps, void* r, void* z, const void* L, const void* Dg, const void* iD,
                   unsigned perdir_mask, double tol, int itmx, int* iters, double* r2) {
   if (!c) return -2;
-  if (c->slab.nranks > 1) return pfail(c, -2, "the pressure solver is single-GPU");
   if (!x || !eps || !r || !z || !L || !Dg || !iD) return pfail(c, -2, "null array");
   cudaStream_t st = (cudaStream_t)stream;
 #define A_(T) (T*)x, (T*)eps, (T*)r, (T*)z, (const T*)L, (const T*)Dg, (const T*)iD, perdir_mask, tol, itmx, iters, r2
@@ -177,7 +210,6 @@ int ifadv_psolver(ifadv_ctx* c, void* stream, void* x, void* eps, void* r, void*
 int ifadv_myproject(ifadv_ctx* c, void* stream, void* u, void* x, void* eps, void* r, void* z, const void* L, const void* Dg, const void* iD,
                     double dt, unsigned perdir_mask, int* iters, double* r2) {
   if (!c) return -2;
-  if (c->slab.nranks > 1) return pfail(c, -2, "the pressure solver is single-GPU");
   if (!u || !x || !eps || !r || !z || !L || !Dg || !iD) return pfail(c, -2, "null array");
   if (!(dt != 0.0) || dt != dt) return pfail(c, -2, "invalid time step");
   cudaStream_t st = (cudaStream_t)stream;

@@ -26,6 +26,8 @@ namespace ifadv {
 struct PoisCtl {
   double rho, zeps, beta, r2, mean, tol, r2_0;
   int n, itmx, done, sub_mean;
+  int slab, pad_;   // slab != 0 (z-slab context): the last CTA only stores its rank's sums in acc[]; the host all-reduces them and
+  double acc[4];    // pois_fin_kernel applies the scalar step -- identical values, hence identical decisions, on every rank
   unsigned ticket[4];
   double part[3][IFADV_POIS_MAXB];
 };
@@ -99,13 +101,13 @@ template <class T, int D> IFADV_DI T pois_mult(const T* __restrict__ L, const T*
   return __ldg(x + l) * __ldg(Dg + l) + lo + up;
 }
 
-// rows of inside(x) walked by warps, lanes along the contiguous dimension
+// rows of inside(x) -- planes [kz0, kz1) of a z-slab -- walked by warps, lanes along the contiguous dimension
 #define IFADV_POIS_ROWS(...)                                                                                   \
-  const int ny = g.n[1] - 2, nz = (D == 3) ? g.n[2] - 2 : 1;                                                   \
+  const int ny = g.n[1] - 2, nz = (D == 3) ? kz1 - kz0 : 1;                                                    \
   const long long rows = (long long)ny * nz;                                                                   \
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wid = threadIdx.x >> 5;                            \
   for (long long rw = (long long)blockIdx.x * wpb + wid; rw < rows; rw += (long long)gridDim.x * wpb) {        \
-    const int y = 2 + (int)(rw % ny), zc = (D == 3) ? 2 + (int)(rw / ny) : 1;                                  \
+    const int y = 2 + (int)(rw % ny), zc = (D == 3) ? kz0 + (int)(rw / ny) : 1;                                \
     const long long l0 = lin3(g, 0, y, zc);                                                                    \
     for (int xc = 2 + lane; xc <= g.n[0] - 1; xc += 32) {                                                      \
       const long long l = l0 + xc;                                                                             \
@@ -116,12 +118,12 @@ template <class T, int D> IFADV_DI T pois_mult(const T* __restrict__ L, const T*
 // The same walk with U cells per lane and trip: the kernels below load all U cells first, then compute, then store, so that a thread
 // keeps U times as many loads in flight (the solver is a pure streaming workload: latency x bandwidth needs ~40 KB in flight per SM).
 #define IFADV_POIS_ROWS_U(U, ...)                                                                              \
-  const int ny = g.n[1] - 2, nz = (D == 3) ? g.n[2] - 2 : 1;                                                   \
+  const int ny = g.n[1] - 2, nz = (D == 3) ? kz1 - kz0 : 1;                                                    \
   const long long rows = (long long)ny * nz;                                                                   \
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wid = threadIdx.x >> 5;                            \
   const int xlast = g.n[0] - 1;                                                                                \
   for (long long rw = (long long)blockIdx.x * wpb + wid; rw < rows; rw += (long long)gridDim.x * wpb) {        \
-    const int y = 2 + (int)(rw % ny), zc = (D == 3) ? 2 + (int)(rw / ny) : 1;                                  \
+    const int y = 2 + (int)(rw % ny), zc = (D == 3) ? kz0 + (int)(rw / ny) : 1;                                \
     const long long l0 = lin3(g, 0, y, zc);                                                                    \
     for (int xb = 2 + lane; xb <= xlast; xb += 32 * (U)) {                                                     \
       __VA_ARGS__                                                                                              \
@@ -129,7 +131,7 @@ template <class T, int D> IFADV_DI T pois_mult(const T* __restrict__ L, const T*
   }
 
 // set_diag!(D,iD,L) = update!(p::Poisson): D = -Σᵢ (L[I,i] + L[I+δᵢ,i]); iD = D² < 2eps ? 0 : 1/D on inside
-template <class T, int D> __global__ void __launch_bounds__(256) pois_diag_kernel(T* __restrict__ Dg, T* __restrict__ iD, const T* __restrict__ L, const Geo g) {
+template <class T, int D> __global__ void __launch_bounds__(256) pois_diag_kernel(T* __restrict__ Dg, T* __restrict__ iD, const T* __restrict__ L, const Geo g, int kz0, int kz1) {
   IFADV_POIS_ROWS({
     T s = T(0);
 _Pragma("unroll")
@@ -178,11 +180,47 @@ template <class T, int D> __global__ void pois_setup_kernel(T* __restrict__ x, T
   x[l] = x[l] * dt;
 }
 
+// ---- the scalar steps behind the four reductions (last CTA of the kernel, or pois_fin_kernel after the all-reduce of a z-slab run) ----
+template <class T> IFADV_DI void fin_residual(PoisCtl* ctl, double sum, double cnt, double tol, int itmx) {
+  const T s = (T)sum / (T)cnt;                                     // sum(p.r)/length(inside(p.r))
+  ctl->mean = (double)s;
+  ctl->sub_mean = (t_abs(s) <= T(2) * teps<T>::v) ? 0 : 1;
+  ctl->tol = tol;
+  ctl->itmx = itmx;
+  ctl->n = 0;
+  ctl->done = 0;
+}
+template <class T> IFADV_DI void fin_start(PoisCtl* ctl, double rr, double rz) {
+  const T r2 = (T)rr, tol = (T)ctl->tol;
+  ctl->r2 = (double)r2;
+  ctl->r2_0 = (double)r2;
+  ctl->rho = (double)(T)rz;
+  ctl->done = ((r2 > tol || r2 > tol / T(4)) && 0 < ctl->itmx) ? 0 : 1;  // flow.jl:309 with nᵖ == 0
+}
+template <class T> IFADV_DI void fin_mult(PoisCtl* ctl, double ze) { ctl->zeps = (double)(T)ze; }
+template <class T> IFADV_DI void fin_update(PoisCtl* ctl, double rz, double rr) {
+  const T rho2 = (T)rz, r2 = (T)rr;
+  ctl->beta = (double)(rho2 / (T)ctl->rho);                        // :318
+  ctl->rho = (double)rho2;                                         // :320
+  ctl->r2 = (double)r2;                                            // :321
+  const int n = ctl->n + 1;
+  ctl->n = n;
+  ctl->done = (r2 > (T)ctl->tol && n < ctl->itmx) ? 0 : 1;         // :309 with nᵖ >= 1
+}
+// z-slab runs: acc[] holds the all-reduced sums.  `which`: 0 residual, 1 start, 2 mult, 3 update -- skipped like the kernel it follows
+template <class T> __global__ void pois_fin_kernel(PoisCtl* ctl, int which, double tol, int itmx) {
+  if (which == 0) fin_residual<T>(ctl, ctl->acc[0], ctl->acc[1], tol, itmx);
+  else if (which == 1) fin_start<T>(ctl, ctl->acc[0], ctl->acc[1]);
+  else if (ctl->done) return;
+  else if (which == 2) fin_mult<T>(ctl, ctl->acc[0]);
+  else fin_update<T>(ctl, ctl->acc[0], ctl->acc[1]);
+}
+
 // residual!(p), first half: r = iD == 0 ? 0 : z - A x on inside;  Σ r -> mean s = Σr / |inside|, dropped when |s| <= 2eps
 template <class T, int D> __global__ void __launch_bounds__(256) pois_residual_kernel(T* __restrict__ r, const T* __restrict__ z, const T* __restrict__ x,
                                                                                       const T* __restrict__ L, const T* __restrict__ Dg,
                                                                                       const T* __restrict__ iD, const Geo g, PoisCtl* ctl,
-                                                                                      double tol, int itmx) {
+                                                                                      double tol, int itmx, int kz0, int kz1) {
   double acc[1] = {0.0};
   IFADV_POIS_ROWS({
     const T v = (__ldg(iD + l) == T(0)) ? T(0) : __ldg(z + l) - pois_mult<T, D>(L, Dg, x, g, l);
@@ -191,20 +229,15 @@ template <class T, int D> __global__ void __launch_bounds__(256) pois_residual_k
   })
   double tot[1];
   if (grid_reduce<1>(acc, ctl, 0, tot) && threadIdx.x == 0) {
-    const T s = (T)tot[0] / (T)(rows * (long long)(g.n[0] - 2));
-    const bool sub = !(t_abs(s) <= T(2) * teps<T>::v);
-    ctl->mean = (double)s;
-    ctl->sub_mean = sub ? 1 : 0;
-    ctl->tol = tol;
-    ctl->itmx = itmx;
-    ctl->n = 0;
-    ctl->done = 0;
+    const double cnt = (double)(rows * (long long)(g.n[0] - 2));
+    if (ctl->slab) { ctl->acc[0] = tot[0]; ctl->acc[1] = cnt; }
+    else fin_residual<T>(ctl, tot[0], cnt, tol, itmx);
   }
 }
 
 // residual!, second half (r -= s) fused with psolver!'s start: z = ϵ = r·iD; r₂ = r·r, rho = r·z          (flow.jl:302-307)
 template <class T, int D> __global__ void __launch_bounds__(256) pois_start_kernel(T* __restrict__ r, T* __restrict__ z, T* __restrict__ eps,
-                                                                                   const T* __restrict__ iD, const Geo g, PoisCtl* ctl) {
+                                                                                   const T* __restrict__ iD, const Geo g, PoisCtl* ctl, int kz0, int kz1) {
   const bool sub = ctl->sub_mean != 0;
   const T s = (T)ctl->mean;
   double acc[2] = {0.0, 0.0};
@@ -219,17 +252,14 @@ template <class T, int D> __global__ void __launch_bounds__(256) pois_start_kern
   })
   double tot[2];
   if (grid_reduce<2>(acc, ctl, 1, tot) && threadIdx.x == 0) {
-    const T r2 = (T)tot[0], tol = (T)ctl->tol;
-    ctl->r2 = (double)r2;
-    ctl->r2_0 = (double)r2;
-    ctl->rho = (double)(T)tot[1];
-    ctl->done = ((r2 > tol || r2 > tol / T(4)) && 0 < ctl->itmx) ? 0 : 1;  // :309 with nᵖ == 0
+    if (ctl->slab) { ctl->acc[0] = tot[0]; ctl->acc[1] = tot[1]; }
+    else fin_start<T>(ctl, tot[0], tot[1]);
   }
 }
 
 // z = A ϵ on inside;  Σ z·ϵ                                                                              (flow.jl:312-313)
 template <class T, int D> __global__ void __launch_bounds__(256) pois_mult_kernel(T* __restrict__ z, const T* __restrict__ eps, const T* __restrict__ L,
-                                                                                  const T* __restrict__ Dg, const Geo g, PoisCtl* ctl) {
+                                                                                  const T* __restrict__ Dg, const Geo g, PoisCtl* ctl, int kz0, int kz1) {
   if (ctl->done) return;
   constexpr int U = (sizeof(T) == 4) ? 4 : 2;
   double acc[1] = {0.0};
@@ -268,13 +298,16 @@ _Pragma("unroll")
     }
   })
   double tot[1];
-  if (grid_reduce<1>(acc, ctl, 2, tot) && threadIdx.x == 0) ctl->zeps = (double)(T)tot[0];
+  if (grid_reduce<1>(acc, ctl, 2, tot) && threadIdx.x == 0) {
+    if (ctl->slab) ctl->acc[0] = tot[0];
+    else fin_mult<T>(ctl, tot[0]);
+  }
 }
 
 // x += alpha ϵ; r -= alpha z; z = r·iD;  Σ r·z, Σ r·r; last CTA: the scalar recurrence and the loop condition   (flow.jl:313-321)
 template <class T, int D> __global__ void __launch_bounds__(256) pois_update_kernel(T* __restrict__ x, T* __restrict__ r, T* __restrict__ z,
                                                                                     const T* __restrict__ eps, const T* __restrict__ iD, const Geo g,
-                                                                                    PoisCtl* ctl) {
+                                                                                    PoisCtl* ctl, int kz0, int kz1) {
   if (ctl->done) return;
   const T alpha = (T)ctl->rho / (T)ctl->zeps;
   constexpr int U = (sizeof(T) == 4) ? 8 : 4;
@@ -306,19 +339,14 @@ _Pragma("unroll")
   })
   double tot[2];
   if (grid_reduce<2>(acc, ctl, 3, tot) && threadIdx.x == 0) {
-    const T rho2 = (T)tot[0], r2 = (T)tot[1];
-    ctl->beta = (double)(rho2 / (T)ctl->rho);
-    ctl->rho = (double)rho2;
-    ctl->r2 = (double)r2;
-    const int n = ctl->n + 1;
-    ctl->n = n;
-    ctl->done = (r2 > (T)ctl->tol && n < ctl->itmx) ? 0 : 1;
+    if (ctl->slab) { ctl->acc[0] = tot[0]; ctl->acc[1] = tot[1]; }
+    else fin_update<T>(ctl, tot[0], tot[1]);
   }
 }
 
 // ϵ = beta ϵ + z on inside; runs iff the update kernel of iteration `it` ran (n == it + 1)                 (flow.jl:319)
 template <class T, int D> __global__ void __launch_bounds__(256) pois_dir_kernel(T* __restrict__ eps, const T* __restrict__ z, const Geo g,
-                                                                                 const PoisCtl* ctl, int it) {
+                                                                                 const PoisCtl* ctl, int it, int kz0, int kz1) {
   if (ctl->n != it + 1) return;
   const T beta = (T)ctl->beta;
   constexpr int U = (sizeof(T) == 4) ? 8 : 4;
@@ -339,7 +367,7 @@ _Pragma("unroll")
 
 // myproject!: u[I,i] -= L[I,i]·∂(i,I,x) on inside(x)                                                      (flow.jl:331-333)
 template <class T, int D> __global__ void __launch_bounds__(256) pois_apply_kernel(T* __restrict__ u, const T* __restrict__ L, const T* __restrict__ x,
-                                                                                   const Geo g) {
+                                                                                   const Geo g, int kz0, int kz1) {
   IFADV_POIS_ROWS({
     const T xc_ = __ldg(x + l);
 _Pragma("unroll")

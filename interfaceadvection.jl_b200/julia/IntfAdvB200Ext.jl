@@ -20,6 +20,7 @@ using InterfaceAdvection
 import Random
 import InterfaceAdvection: advectVOF!, advectVOFρuu!, u2ρu!, ρu2u!, MPCFL, _scalar_op, cVOF
 import InterfaceAdvection: viscSurfTenρu!, updateU!, updateL!
+import InterfaceAdvection: psolver!, myproject!
 import InterfaceAdvection: LevelSet, redistaning!, computeL!, _redistaningStage!
 import InterfaceAdvection: getInterfaceNormal_WH!, getInterfaceNormal_WY!, getInterfaceNormal_Column!, getInterfaceNormal_PCD!,
                            getInterfaceNormal_SLIC!, getInterfaceNormal_MYC!, getInterfaceNormal_Y!, getInterfaceNormal_CD!,
@@ -169,6 +170,35 @@ function updateL!(μ₀::CuArray{T}, f::CuArray{T}, λρ; perdir=()) where {T<:U
     ctx = context(f)
     check(ctx, ccall((:ifadv_update_l, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cuint, Cint),
                      ctx, stream_ptr(), dptr(μ₀), dptr(f), λρ, perdir_mask(perdir), 0)); nothing
+end
+
+# ---- pressure projection on WaterLily's Poisson (src/flow.jl:300-347): update!, psolver!, myproject! -------------------------------
+# b.L ≡ a.μ₀, b.x ≡ a.p, b.z ≡ a.σ; MultiLevelPoisson keeps WaterLily's own solver!.
+const CuPoisson{T} = WaterLily.Poisson{T,<:CuArray{T},<:CuArray{T}}
+function WaterLily.update!(b::CuPoisson{T}) where {T<:Union{Float32,Float64}}
+    ctx = context(b.x)
+    check(ctx, ccall((:ifadv_poisson_update, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                     ctx, stream_ptr(), dptr(b.D), dptr(b.iD), dptr(b.L))); nothing
+end
+function psolver!(b::CuPoisson{T}; log=false, tol=50eps(T), itmx=6e3) where {T<:Union{Float32,Float64}}
+    ctx = context(b.x)
+    it = Ref{Cint}(0); r₂ = Ref{Cdouble}(0)
+    check(ctx, ccall((:ifadv_psolver, LIB), Cint,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cuint, Cdouble, Cint,
+                      Ptr{Cint}, Ptr{Cdouble}),
+                     ctx, stream_ptr(), dptr(b.x), dptr(b.ϵ), dptr(b.r), dptr(b.z), dptr(b.L), dptr(b.D), dptr(b.iD), perdir_mask(b.perdir),
+                     Cdouble(tol), Cint(itmx), it, r₂))
+    push!(b.n, it[]); nothing
+end
+function myproject!(a::Flow{n,T}, b::CuPoisson{T}, w=1) where {n,T<:Union{Float32,Float64}}
+    ctx = context(b.x)
+    it = Ref{Cint}(0); r₂ = Ref{Cdouble}(0)
+    check(ctx, ccall((:ifadv_myproject, LIB), Cint,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble,
+                      Cuint, Ptr{Cint}, Ptr{Cdouble}),
+                     ctx, stream_ptr(), dptr(a.u), dptr(b.x), dptr(b.ϵ), dptr(b.r), dptr(b.z), dptr(b.L), dptr(b.D), dptr(b.iD),
+                     Cdouble(T(w) * last(a.Δt)), perdir_mask(b.perdir), it, r₂))
+    push!(b.n, it[]); nothing
 end
 
 # ---- post-processing: level-set redistancing (src/redistaning.jl:31-87) and metric sums (src/metrics.jl) ---------------------------

@@ -2,7 +2,10 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
 Every rank advances its z-slab with the CUDA path (ifadv_create_slab: per-sweep NCCL ghost-plane exchange inside the library) and
 also advances the whole grid on its own GPU.  Owned cells of f and ρu must be BIT-IDENTICAL ("N-GPU result == 1-GPU
-result") -- with prescribed velocities, and with a `project` hook that changes u between predictor and corrector."""
+result") -- with prescribed velocities, and with a `project` hook that changes u between predictor and corrector.
+Second part: the pressure projection (ifadv_myproject) on the slabs -- dot products all-reduced, ghost planes of ϵ and x from the
+z-neighbours -- against the single-GPU projection of the global problem: the summation order of the dot products differs, so the
+comparison carries the solver's tolerance (u, p of the owned planes; iteration count)."""
 import os
 import sys
 
@@ -68,8 +71,56 @@ def main():
             print(f"[mgpu_check] world={world} {dtype} per_z={per_z} hook={hook} N/gpu={N}: bitwise={'OK' if flag.item() else 'MISMATCH'} "
                   f"max|Δ(f,ρu)|(rank0)={err:.3e} mass={m:.6f} single-GPU mass={ia.sum_inside(sim.intf.f):.6f} bytes_sent/rank={run.bytes_sent}")
         ok_all = ok_all and bool(flag.item())
+    ok_all = projection_check(rank, world, dev) and ok_all
     dist.destroy_process_group()
     sys.exit(0 if ok_all else 1)
+
+
+def projection_check(rank, world, dev):
+    ok_all = True
+    for dtype, per_z, N in [("float64", False, (48, 40, 24)), ("float32", True, (64, 48, 16)), ("float64", True, (40, 32, 12))]:
+        perdir = (1, 3) if per_z else (2,)
+        T = getattr(torch, dtype)
+        N1, N2, nz = N
+        Ng = (N1, N2, nz * world)
+        sdf = configs.sdf_sphere([N1 / 2, N2 / 2, nz * 1.0], nz * 0.6, inside_dark=False)
+        sim = ia.TwoPhaseSimulation(Ng, (0, 0, 0), float(N1), T=T, lam_rho=1e-2, InterfaceSDF=sdf, perdir=perdir, U=1.0, dt=0.5,
+                                    device=dev, psolver="Poisson")
+        gen = torch.Generator(device=dev).manual_seed(7)  # the same global field on every rank
+        sim.flow.u.copy_(torch.randn(sim.flow.u.shape, generator=gen, device=dev, dtype=T))
+        ia.BC(sim.flow.u, (0, 0, 0), False, perdir)
+        g = slab.SlabGeom(rank, world, nz, slab.G_DEFAULT, per_z)
+        nzg = nz * world
+        zidx = torch.tensor([((g.z_origin + l - 1) % nzg) + 1 if per_z else min(max(g.z_origin + l, 0), nzg + 1)
+                             for l in range(g.nz_local + 2)], device=dev)
+        run = slab.SlabRunner(N, dtype, perdir, "C4", rank, world, dev, fields=(sim.intf.f.index_select(2, zidx), sim.flow.u.index_select(2, zidx)),
+                              lam_rho=1e-2)
+        a, c = run.flow, run.intf
+        a.dt[:] = [0.5]; sim.flow.dt[:] = [0.5]
+        # global problem on this rank's GPU
+        ia.updateL(sim.flow.mu0, sim.intf.f, 1e-2, perdir, fill_one=True)
+        ia.update(sim.pois)
+        n_ref = ia.myproject(sim.flow, sim.pois, 0.5)
+        # the slab
+        ia.updateL(a.mu0, c.f, 1e-2, run.perdir, fill_one=True)
+        b = ia.Poisson(a.p, a.mu0, a.sigma, run.perdir)
+        n_slab = ia.myproject(a, b, 0.5)
+        torch.cuda.synchronize()
+        own = g.owned
+        ref_u = sim.flow.u[1:-1, 1:-1, 1 + rank * nz: 1 + (rank + 1) * nz, :]
+        ref_p = sim.flow.p[1:-1, 1:-1, 1 + rank * nz: 1 + (rank + 1) * nz]
+        du = float((ref_u - a.u[1:-1, 1:-1, own, :]).abs().max())
+        dp = float((ref_p - a.p[1:-1, 1:-1, own]).abs().max())
+        tol = 1e-6 if dtype == "float64" else 5e-2
+        ok = du <= tol * max(1.0, float(ref_u.abs().max())) and dp <= tol * max(1.0, float(ref_p.abs().max())) and \
+            abs(n_slab - n_ref) <= max(2, n_ref // 10) and n_ref > 0
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"[mgpu_check] projection world={world} {dtype} per_z={per_z} N/gpu={N}: {'OK' if flag.item() else 'MISMATCH'} "
+                  f"iterations slab/1-GPU={n_slab}/{n_ref} max|Δu|={du:.3e} max|Δp|={dp:.3e} r2={b.r2[-1]:.3e}")
+        ok_all = ok_all and bool(flag.item())
+    return ok_all
 
 
 if __name__ == "__main__":
