@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -78,6 +79,24 @@ int psolver_t(ifadv_ctx* c, cudaStream_t st, T* x, T* eps, T* r, T* z, const T* 
   const unsigned nb_mult = resident_blocks(c, pois_mult_kernel<T, D>), nb_upd = resident_blocks(c, pois_update_kernel<T, D>),
                  nb_dir = resident_blocks(c, pois_dir_kernel<T, D>);
   const Geo g = c->g;
+  // very small grids (<= 100 k entries per field, e.g. 32^3 or BASELINE config 1's 128^2): batches of iterations as ONE cooperative
+  // launch -- 16.9 vs 27.8 us per iteration at 32^3; from 64^3 on the grid-wide barriers cost what the launches cost (24.0 vs 24.5 us)
+  // and at 128^3 more (53 vs 41 us), so larger grids keep the three-kernel form (IFADV_POIS_COOP=0/1 overrides)
+  bool coop = false;
+  unsigned nb_coop = 0;
+  Geo gp = g;
+  gp.per = per & ((1u << D) - 1u);
+  if (!slab) {
+    const char* e = getenv("IFADV_POIS_COOP");
+    int can = 0;
+    cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, c->device);
+    coop = can && (e ? atoi(e) != 0 : g.S <= 100000);
+    if (coop) {
+      nb_coop = resident_blocks(c, pois_pcg_coop_kernel<T, D>);
+      const char* eb = getenv("IFADV_POIS_COOP_CTAS");  // measurement knob: cap of the cooperative grid
+      if (eb && atoi(eb) > 0) nb_coop = std::min<unsigned>(nb_coop, (unsigned)atoi(eb));
+    }
+  }
   const double tolT = tol < 0 ? (double)(T(50) * std::numeric_limits<T>::epsilon()) : (double)(T)tol;
   if (itmx <= 0) itmx = 6000;
   if (c->pois_slab_flag != (slab ? 1 : 0)) {
@@ -124,6 +143,14 @@ int psolver_t(ifadv_ctx* c, cudaStream_t st, T* x, T* eps, T* r, T* z, const T* 
     bool queued = false;
     if (it < itmx) {
       const int end = std::min(itmx, it + batch);
+      if (coop) {
+        int it0 = it, it1 = end, k0 = kz0, k1 = kz1;
+        void* args[] = {(void*)&x, (void*)&r, (void*)&z, (void*)&eps, (void*)&L, (void*)&Dg, (void*)&iD, (void*)&gp, (void*)&ctl, (void*)&it0,
+                        (void*)&it1, (void*)&k0, (void*)&k1};
+        CU_CHECK(c, cudaLaunchCooperativeKernel((void*)pois_pcg_coop_kernel<T, D>, dim3(nb_coop), dim3(256), args, 0, st));
+        c->launches++;
+        it = end;
+      }
       for (; it < end; ++it) {
         if ((rc = ghosts(eps))) return rc;                                                           // :311
         pois_mult_kernel<T, D><<<nb_mult, 256, 0, st>>>(z, eps, L, Dg, g, ctl, kz0, kz1);            // :312-313

@@ -16,6 +16,8 @@
 // size), rounded to T -- the reference's `⋅` is BLAS / CUBLAS dot with an unspecified order, so comparisons carry a tolerance.
 // Per-cell arithmetic follows the reference expression by expression (-fmad=false, IEEE division).
 #pragma once
+#include <cooperative_groups.h>
+
 #include "ifadv_math.cuh"
 #include "ifadv_sweep.cuh"
 
@@ -363,6 +365,100 @@ _Pragma("unroll")
       if (xc <= xlast) eps[l0 + xc] = beta * ev[k] + zv[k];
     }
   })
+}
+
+// ---- very small grids: a batch of iterations in ONE cooperative launch -------------------------------------------------------------
+// On small grids an iteration of the three-kernel form is bound by launch latency (32³: 28 µs per iteration, 3 launches).  Here the
+// CTAs stay resident and meet at grid-wide barriers instead (32³: 17 µs; no gain from 64³ on, see ifadv_poisson.cu): perBC!(ϵ) | barrier | z = Aϵ, Σ z·ϵ |
+// barrier | x, r, z update, Σ r·z, Σ r·r, scalar step | barrier | ϵ = beta ϵ + z | barrier.  Same per-cell arithmetic and the same
+// last-CTA reductions (partial sums grouped by this launch's grid, so the dot products agree with the three-kernel form to round-off).
+// Arrays written inside the launch are read with plain loads (never through the read-only path).
+template <class T, int D> IFADV_DI T pois_mult_plain(const T* __restrict__ L, const T* __restrict__ Dg, const T* x, const Geo& g, long long l) {
+  T lo = T(0), up = T(0);
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const long long st = (i == 0) ? 1 : ((i == 1) ? g.s1 : g.s2);
+    lo = lo + __ldg(L + (long long)i * g.S + l) * x[l - st];
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const long long st = (i == 0) ? 1 : ((i == 1) ? g.s1 : g.s2);
+    up = up + __ldg(L + (long long)i * g.S + l + st) * x[l + st];
+  }
+  return x[l] * __ldg(Dg + l) + lo + up;
+}
+template <class T, int D> __global__ void __launch_bounds__(256) pois_pcg_coop_kernel(T* x, T* r, T* z, T* eps, const T* __restrict__ L,
+                                                                                      const T* __restrict__ Dg, const T* __restrict__ iD, const Geo g,
+                                                                                      PoisCtl* ctl, int it0, int it1, int kz0, int kz1) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  volatile PoisCtl* vc = ctl;
+  const int ny = g.n[1] - 2, nz = (D == 3) ? kz1 - kz0 : 1;
+  const long long rows = (long long)ny * nz;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wid = threadIdx.x >> 5;
+  const long long n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
+  const long long c0 = (g.per & 1u) ? 2 * n1 * n2 : 0, c1 = (g.per & 2u) ? 2 * n0 * n2 : 0, c2 = (D == 3 && (g.per & 4u)) ? 2 * n0 * n1 : 0;
+  for (int it = it0; it < it1; ++it) {
+    if (vc->done) break;  // uniform: written before the last barrier of the previous iteration (or by an earlier launch)
+    if (g.per) {          // perBC!(ϵ), flow.jl:311
+      for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < c0 + c1 + c2; t += (long long)gridDim.x * blockDim.x) {
+        int xx, yy, zz;
+        if (t < c0) { const long long q = t >> 1; xx = (t & 1) ? (int)n0 : 1; yy = (int)(q % n1) + 1; zz = (int)(q / n1) + 1; }
+        else if (t < c0 + c1) { const long long u_ = t - c0, q = u_ >> 1; yy = (u_ & 1) ? (int)n1 : 1; xx = (int)(q % n0) + 1; zz = (int)(q / n0) + 1; }
+        else { const long long u_ = t - c0 - c1, q = u_ >> 1; zz = (u_ & 1) ? (int)n2 : 1; xx = (int)(q % n0) + 1; yy = (int)(q / n0) + 1; }
+        const int mx = (g.per & 1u) ? wrapc(xx, g.n[0]) : xx, my = (g.per & 2u) ? wrapc(yy, g.n[1]) : yy,
+                  mz = (D == 3 && (g.per & 4u)) ? wrapc(zz, g.n[2]) : zz;
+        eps[lin3(g, xx, yy, zz)] = eps[lin3(g, mx, my, mz)];
+      }
+      grid.sync();
+    }
+    {  // z = A ϵ, Σ z·ϵ   (:312-313)
+      double acc[1] = {0.0};
+      for (long long rw = (long long)blockIdx.x * wpb + wid; rw < rows; rw += (long long)gridDim.x * wpb) {
+        const long long l0 = lin3(g, 0, 2 + (int)(rw % ny), (D == 3) ? kz0 + (int)(rw / ny) : 1);
+        for (int xc = 2 + lane; xc <= g.n[0] - 1; xc += 32) {
+          const long long l = l0 + xc;
+          const T v = pois_mult_plain<T, D>(L, Dg, eps, g, l);
+          z[l] = v;
+          acc[0] += (double)v * (double)eps[l];
+        }
+      }
+      double tot[1];
+      if (grid_reduce<1>(acc, ctl, 2, tot) && threadIdx.x == 0) fin_mult<T>(ctl, tot[0]);
+    }
+    grid.sync();
+    {  // x, r, z update, Σ r·z, Σ r·r, scalar step   (:313-321)
+      const T alpha = (T)vc->rho / (T)vc->zeps;
+      double acc[2] = {0.0, 0.0};
+      for (long long rw = (long long)blockIdx.x * wpb + wid; rw < rows; rw += (long long)gridDim.x * wpb) {
+        const long long l0 = lin3(g, 0, 2 + (int)(rw % ny), (D == 3) ? kz0 + (int)(rw / ny) : 1);
+        for (int xc = 2 + lane; xc <= g.n[0] - 1; xc += 32) {
+          const long long l = l0 + xc;
+          x[l] = x[l] + alpha * eps[l];
+          const T rn = r[l] - alpha * z[l];
+          r[l] = rn;
+          const T zn = rn * __ldg(iD + l);
+          z[l] = zn;
+          acc[0] += (double)rn * (double)zn;
+          acc[1] += (double)rn * (double)rn;
+        }
+      }
+      double tot[2];
+      if (grid_reduce<2>(acc, ctl, 3, tot) && threadIdx.x == 0) fin_update<T>(ctl, tot[0], tot[1]);
+    }
+    grid.sync();
+    {  // ϵ = beta ϵ + z   (:319)
+      const T beta = (T)vc->beta;
+      for (long long rw = (long long)blockIdx.x * wpb + wid; rw < rows; rw += (long long)gridDim.x * wpb) {
+        const long long l0 = lin3(g, 0, 2 + (int)(rw % ny), (D == 3) ? kz0 + (int)(rw / ny) : 1);
+        for (int xc = 2 + lane; xc <= g.n[0] - 1; xc += 32) {
+          const long long l = l0 + xc;
+          eps[l] = beta * eps[l] + z[l];
+        }
+      }
+    }
+    grid.sync();
+  }
 }
 
 // myproject!: u[I,i] -= L[I,i]·∂(i,I,x) on inside(x)                                                      (flow.jl:331-333)
