@@ -98,7 +98,63 @@ def measure_cpu(n, f64, itmx):
             "Gcell_iterations_per_s": n ** 3 * it / dt / 1e9, "kind": "port (C++/OpenMP restatement, un-fused pass structure)"}
 
 
+def measure_slab(N=(512, 512, 256), f64=False, itmx=50, reps=3):
+    """Weak scaling of the solver over z-slabs (one process per GPU, torchrun): N per GPU, fixed iteration count, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import interfaceadvection.jl_b200 as ia
+    from interfaceadvection.jl_b200 import slab
+
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = "float64" if f64 else "float32"
+    T = getattr(torch, dtype)
+    run = slab.SlabRunner(N, dtype, (), "C4", rank, world, dev, lam_rho=1e-3)
+    a, c = run.flow, run.intf
+    gen = torch.Generator(device=dev).manual_seed(5 + rank)
+    a.u.copy_(0.1 * torch.randn(a.u.shape, generator=gen, device=dev, dtype=T))
+    ia.BC(a.u, a.uBC, False, run.perdir)
+    run.exchange(a.u)
+    ia.updateL(a.mu0, c.f, c.lam_rho, run.perdir, fill_one=True)
+    b = ia.Poisson(a.p, a.mu0, a.sigma, run.perdir)
+    src = torch.zeros_like(b.z)
+    ins = (slice(1, -1),) * 3
+    for i in range(3):
+        hi = tuple(slice(2, None) if d == i else slice(1, -1) for d in range(3)) + (i,)
+        src[ins] += a.u[hi] - a.u[ins + (i,)]
+    best = None
+    for _ in range(reps):
+        b.z.copy_(src); b.x.zero_()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        it = ia.psolver(b, itmx=itmx)
+        e1.record(); torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        best = float(ms) if best is None else min(best, float(ms))
+    cells = float(np.prod(N)) * world
+    s = 8 if f64 else 4
+    if rank == 0:
+        print(json.dumps({"what": "psolver on z-slabs, weak scaling", "n_gpus": world, "grid_per_gpu": list(N), "dtype": "f64" if f64 else "f32",
+                          "iterations": it, "ms_per_iteration": best / max(it, 1), "Gcell_iterations_per_s": cells * it / (best * 1e-3) / 1e9,
+                          "algorithmic_GBps_per_gpu": 17 * s * cells / world * it / (best * 1e-3) / 1e9,
+                          "transport": run.transport, "r2": b.r2[-1]}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "slab":
+        measure_slab()
+        sys.exit(0)
     if len(sys.argv) > 1:  # n dtype itmx: one configuration (for ncu)
         print(json.dumps(measure(int(sys.argv[1]), sys.argv[2] == "float64", int(sys.argv[3]), reps=1)), flush=True)
         sys.exit(0)
