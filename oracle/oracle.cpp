@@ -377,4 +377,83 @@ int orc_myproject(int dtype, int D, const int64_t* Ng, void* u, void* x, void* e
   return np;
 }
 
+// ---- WaterLily.MultiLevelPoisson: opaque handle (levels >= 2 and level 1's D, iD, ϵ, r are owned by the handle) -------------------------
+struct OrcML { int dtype; void* h; };
+void* orc_ml_create(int dtype, int D, const int64_t* Ng, void* x, void* L, void* z, unsigned perdir, int maxlevels) {
+  if (dtype == 0) return new OrcML{0, ml_create<float>(D, Ng, (float*)x, (float*)L, (float*)z, perdir, maxlevels)};
+  if (dtype == 1) return new OrcML{1, ml_create<double>(D, Ng, (double*)x, (double*)L, (double*)z, perdir, maxlevels)};
+  return nullptr;
+}
+#define ML_DISPATCH(m, ...)                          \
+  do {                                               \
+    if ((m)->dtype == 0) {                           \
+      using T = float;                               \
+      auto& ml = *(MLPois<float>*)(m)->h;            \
+      __VA_ARGS__;                                   \
+    } else {                                         \
+      using T = double;                              \
+      auto& ml = *(MLPois<double>*)(m)->h;           \
+      __VA_ARGS__;                                   \
+    }                                                \
+  } while (0)
+int orc_ml_destroy(void* m_) {
+  OrcML* m = (OrcML*)m_;
+  if (!m) return 0;
+  if (m->dtype == 0) delete (MLPois<float>*)m->h; else delete (MLPois<double>*)m->h;
+  delete m;
+  return 0;
+}
+int orc_ml_levels(void* m_) {
+  OrcML* m = (OrcML*)m_;
+  int n = 0;
+  ML_DISPATCH(m, { (void)sizeof(T); n = (int)ml.lv.size(); });
+  return n;
+}
+// which: 0 L, 1 D, 2 iD, 3 x, 4 ϵ, 5 r, 6 z; level 0-based
+int orc_ml_level_array(void* m_, int level, int which, void** ptr, int64_t* Ng) {
+  OrcML* m = (OrcML*)m_;
+  ML_DISPATCH(m, {
+    (void)sizeof(T);
+    if (level < 0 || level >= (int)ml.lv.size()) return -2;
+    auto& lv = *ml.lv[level];
+    for (int d = 0; d < 3; ++d) Ng[d] = lv.g.n[d];
+    void* t[7] = {lv.p.L.p, lv.p.D.p, lv.p.iD.p, lv.p.x.p, lv.p.eps.p, lv.p.r.p, lv.p.z.p};
+    *ptr = t[which];
+  });
+  return 0;
+}
+int orc_ml_update(void* m_) {
+  OrcML* m = (OrcML*)m_;
+  ML_DISPATCH(m, { (void)sizeof(T); ml_update(ml); });
+  return 0;
+}
+int orc_ml_vcycle(void* m_) {
+  OrcML* m = (OrcML*)m_;
+  ML_DISPATCH(m, { (void)sizeof(T); ml_vcycle(ml); });
+  return 0;
+}
+int orc_ml_smooth(void* m_, int level) {
+  OrcML* m = (OrcML*)m_;
+  ML_DISPATCH(m, { (void)sizeof(T); pois_pcg_smooth(ml.lv[level]->g, ml.lv[level]->p); });
+  return 0;
+}
+int orc_ml_residual(void* m_) {
+  OrcML* m = (OrcML*)m_;
+  ML_DISPATCH(m, { (void)sizeof(T); pois_residual(ml.lv[0]->g, ml.lv[0]->p); });
+  return 0;
+}
+// solver!(ml;tol,itmx): tol < 0 -> 1e-4, itmx <= 0 -> 32 (WaterLily's defaults)
+int orc_ml_solver(void* m_, double tol, int itmx, double* r2) {
+  OrcML* m = (OrcML*)m_;
+  int np = 0;
+  ML_DISPATCH(m, { np = ml_solver<T>(ml, tol < 0 ? T(1e-4) : (T)tol, itmx <= 0 ? 32 : itmx, r2); });
+  return np;
+}
+int orc_ml_myproject(void* m_, void* u, double dt, double* r2) {
+  OrcML* m = (OrcML*)m_;
+  int np = 0;
+  ML_DISPATCH(m, { np = ml_myproject<T>(ml, VF<T>{(T*)u, &ml.lv[0]->g}, (T)dt, r2); });
+  return np;
+}
+
 }  // extern "C"

@@ -404,6 +404,66 @@ def myproject(u, p: Poisson, dt, omp=False):
     return n, r2.value
 
 
+class MultiLevelPoisson:
+    """WaterLily.MultiLevelPoisson(x,L,z;maxlevels=10,perdir): geometric multigrid on the caller's x, L, z (level 1); the coarser
+    levels and every level's D, iD, ϵ, r live in the oracle's handle.  level(l, name) returns a numpy view of a level's array."""
+    _NAMES = {"L": 0, "D": 1, "iD": 2, "x": 3, "eps": 4, "r": 5, "z": 6}
+
+    def __init__(self, x, L, z, perdir=(), maxlevels=10):
+        self.x, self.L, self.z, self.perdir = x, L, z, tuple(perdir)
+        D, ng = _ng(x)
+        self.D_ = D
+        lib().orc_ml_create.restype = C.c_void_p
+        self._h = C.c_void_p(lib().orc_ml_create(_dt(x), D, ng, _p(x), _p(L), _p(z), mask(perdir), int(maxlevels)))
+        self.n = []
+
+    def __del__(self):
+        try:
+            lib().orc_ml_destroy(self._h)
+        except Exception:
+            pass
+
+    @property
+    def levels(self) -> int:
+        return lib().orc_ml_levels(self._h)
+
+    def level(self, l, name):
+        ptr, ng = C.c_void_p(), (C.c_int64 * 3)()
+        assert lib().orc_ml_level_array(self._h, int(l), self._NAMES[name], C.byref(ptr), ng) == 0
+        shape = tuple(ng[:self.D_]) + ((self.D_,) if name == "L" else ())
+        n = int(np.prod(shape))
+        ct = C.c_float if self.x.dtype == np.float32 else C.c_double
+        buf = (ct * n).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=self.x.dtype).reshape(shape, order="F")
+
+    def update(self):
+        lib().orc_ml_update(self._h)
+
+    def vcycle(self):
+        lib().orc_ml_vcycle(self._h)
+
+    def smooth(self, level=0):
+        lib().orc_ml_smooth(self._h, int(level))
+
+    def residual(self):
+        lib().orc_ml_residual(self._h)
+
+    def solver(self, tol=1e-4, itmx=32):
+        """solver!(ml;tol,itmx) -> (V-cycles, last r₂)."""
+        r2 = C.c_double()
+        n = lib().orc_ml_solver(self._h, C.c_double(tol), int(itmx), C.byref(r2))
+        self.n.append(n)
+        return n, r2.value
+
+
+def ml_myproject(u, ml: MultiLevelPoisson, dt):
+    """myproject!(a,b::MultiLevelPoisson,w), dt = T(w)·last(a.Δt): solver!(b;tol=1e-4,itmx=200) inside -> (V-cycles, last r₂)."""
+    r2 = C.c_double()
+    n = lib().orc_ml_myproject(ml._h, _p(u), C.c_double(float(ml.x.dtype.type(dt))), C.byref(r2))
+    ml.n.append(n)
+    return n, r2.value
+
+
 def num_threads(omp=True) -> int:
     return lib(omp).orc_num_threads()
 
