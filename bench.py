@@ -533,6 +533,15 @@ def run_b200(args):
         projection_line = tp.measure(w["N"][0], w["dtype"] == "float64", 50, dev, cpu_n=0 if args.no_cpu else 128)
         ia.api._contexts.clear()
         torch.cuda.empty_cache()
+        try:  # WaterLily's default psolver (MultiLevelPoisson, inproject!'s second method flow.jl:343-347) on the same problem
+            spec = importlib.util.spec_from_file_location("time_mlpoisson", os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "time_mlpoisson.py"))
+            tm = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(tm)
+            projection_line["multigrid"] = tm.measure(w["N"][0], w["dtype"] == "float64", 4, dev)
+        except ia.IfadvError as e:  # grid without three multigrid levels (WaterLily's own constructor assertion)
+            projection_line["multigrid"] = {"unavailable": str(e)}
+        ia.api._contexts.clear()
+        torch.cuda.empty_cache()
 
     # ---- e2e: the reference-facing C-ABI call with HOST buffers (H2D/D2H inside the timed region) ----
     e2e = None

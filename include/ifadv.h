@@ -197,6 +197,33 @@ int ifadv_psolver(ifadv_ctx* ctx, void* stream, void* x, void* eps, void* r, voi
 int ifadv_myproject(ifadv_ctx* ctx, void* stream, void* u, void* x, void* eps, void* r, void* z, const void* L, const void* D,
                     const void* iD, double dt, unsigned perdir_mask, int* iters, double* r2);
 
+/* ---- WaterLily.MultiLevelPoisson: geometric multigrid, the solver of inproject!'s second method (src/flow.jl:343-347) ---------------
+ * and WaterLily's default `psolver`.  WaterLily is not under the reference tree; MultiLevelPoisson(x,L,z;maxlevels,perdir), update!,
+ * Vcycle!, smooth! (= pcg!(p;it=6)), residual!, solver! are restated from its published 1.x sources.  Level 1 works on the caller's
+ * x ≡ Flow.p, L ≡ Flow.μ₀, z ≡ Flow.σ (borrowed for the handle's lifetime); D, iD, ϵ, r of level 1 and all arrays of the coarser levels
+ * (extents 1 + N÷2 while every extent incl. ghosts is even and > 4, at most maxlevels restrictions; <= 0: 10) belong to the handle.
+ * One solver cycle (Vcycle!; smooth!; L₂) is replayed as one CUDA graph (IFADV_ML_GRAPH=0: plain launches); the smoother's scalars and
+ * early exits stay on the device, the host reads r₂ once per cycle as the reference's loop does.  Single-GPU contexts only (-2 on a
+ * z-slab context).  create runs update!(ml). */
+typedef struct ifadv_ml ifadv_ml;
+int ifadv_ml_create(ifadv_ctx* ctx, ifadv_ml** ml, void* stream, void* x, void* L, void* z, unsigned perdir_mask, int maxlevels);
+int ifadv_ml_destroy(ifadv_ml* ml);
+int ifadv_ml_levels(const ifadv_ml* ml);
+/* device pointer and extents (ghosts included) of a level's array: level 0-based; which: 0 L, 1 D, 2 iD, 3 x, 4 ϵ, 5 r, 6 z */
+int ifadv_ml_level_array(ifadv_ml* ml, int level, int which, void** dev_ptr, int64_t Ng[3]);
+/* update!(ml): set_diag! on level 1, then restrictL! + BC!(L,0,false,perdir) + set_diag! level by level */
+int ifadv_ml_update(ifadv_ml* ml, void* stream);
+/* residual!(ml) (level 1: r = z - A x, mean removed), Vcycle!(ml), smooth!(ml.levels[level]) -- the pieces of solver!, for tests */
+int ifadv_ml_residual(ifadv_ml* ml, void* stream);
+int ifadv_ml_vcycle(ifadv_ml* ml, void* stream);
+int ifadv_ml_smooth(ifadv_ml* ml, void* stream, int level);
+/* solver!(ml; tol=1e-4, itmx=32): tol < 0 and itmx <= 0 select WaterLily's defaults; returns the cycle count and the last r₂.
+ * Synchronises the stream once per cycle.  -1: NaN residual. */
+int ifadv_ml_solver(ifadv_ml* ml, void* stream, double tol, int itmx, int* cycles, double* r2);
+/* myproject!(a,b::MultiLevelPoisson,w), dt = T(w)·last(a.Δt): z ← ∇·u; x ← x·dt; solver!(b;tol=1e-4,itmx=200); u -= L ∂x; x ← x/dt
+ * (src/flow.jl:328-341,343-347).  The caller applies BC!(u,...) afterwards (flow.jl:82,106). */
+int ifadv_ml_myproject(ifadv_ml* ml, void* stream, void* u, double dt, int* cycles, double* r2);
+
 /* Stream overlap aid for MPFMomStep! (src/flow.jl:74,89): the midpoint f⁰=(f⁰+f)/2 and the copy f⁰<-f only READ the f that the
  * corrector's advectfq! is about to advance, and that call does not write f before its last directional sweep.  A caller that
  * runs those two field operations on a second stream records an event behind them and passes it here; the NEXT

@@ -12,5 +12,6 @@ from .api import (  # noqa: F401
     viscSurfTenrhou, updateU, updateL, mom_step_forcing,
     LevelSet, computeL, redistaningStage, redistaning, metrics, enstrophy,
     Poisson, update, psolver, myproject, project_with,
+    MultiLevelPoisson, Vcycle, smooth, residual, solver,
 )
 from . import vtkio  # noqa: F401,E402  (load! / save of VTK restart files, ext/IntfAdvReadVTKExt.jl)

@@ -74,6 +74,16 @@ def lib():
         L.ifadv_poisson_update.argtypes = [vp, vp, vp, vp, vp]
         L.ifadv_psolver.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, u32, dbl, i32, i32p, dblp]
         L.ifadv_myproject.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, u32, i32p, dblp]
+        L.ifadv_ml_create.argtypes = [vp, C.POINTER(vp), vp, vp, vp, vp, u32, i32]
+        L.ifadv_ml_destroy.argtypes = [vp]
+        L.ifadv_ml_levels.argtypes = [vp]
+        L.ifadv_ml_level_array.argtypes = [vp, i32, i32, C.POINTER(vp), i64p]
+        L.ifadv_ml_update.argtypes = [vp, vp]
+        L.ifadv_ml_residual.argtypes = [vp, vp]
+        L.ifadv_ml_vcycle.argtypes = [vp, vp]
+        L.ifadv_ml_smooth.argtypes = [vp, vp, i32]
+        L.ifadv_ml_solver.argtypes = [vp, vp, dbl, i32, i32p, dblp]
+        L.ifadv_ml_myproject.argtypes = [vp, vp, vp, dbl, i32p, dblp]
         L.ifadv_create_slab.argtypes = [C.POINTER(vp), i64p, i32, i32, vp, i32, i32, i32, i32]
         L.ifadv_slab_info.argtypes = [vp, i32p, i32p, i32p, i32p, i64p]
         L.ifadv_exchange_planes.argtypes = [vp, vp, vp, i32, i32]
@@ -272,6 +282,48 @@ class Context:
         """(iterations, last r₂) of myproject!(a,b,w), dt = T(w)·last(a.Δt) (ifadv_myproject)."""
         n, r2 = C.c_int(0), C.c_double(0.0)
         self._chk(lib().ifadv_myproject(self._h, stream, u, x, eps, r, z, L, D, iD, float(dt), perdir_mask(perdir), C.byref(n), C.byref(r2)))
+        return n.value, r2.value
+
+    # ---- WaterLily.MultiLevelPoisson (ifadv_ml_*): the handle is a plain integer owned by the caller (api.MultiLevelPoisson) ----
+    def ml_create(self, stream, x, L, z, perdir, maxlevels=10) -> int:
+        h = C.c_void_p()
+        self._chk(lib().ifadv_ml_create(self._h, C.byref(h), stream, x, L, z, perdir_mask(perdir), int(maxlevels)))
+        return h.value
+
+    def ml_destroy(self, h):
+        lib().ifadv_ml_destroy(C.c_void_p(h))
+
+    def ml_levels(self, h) -> int:
+        return lib().ifadv_ml_levels(C.c_void_p(h))
+
+    def ml_level_array(self, h, level, which):
+        """(device pointer, extents incl. ghosts) of a level's array; which: 0 L, 1 D, 2 iD, 3 x, 4 ϵ, 5 r, 6 z."""
+        ptr, ng = C.c_void_p(), (C.c_int64 * 3)()
+        self._chk(lib().ifadv_ml_level_array(C.c_void_p(h), int(level), int(which), C.byref(ptr), ng))
+        return ptr.value, tuple(ng)
+
+    def ml_update(self, h, stream):
+        return self._chk(lib().ifadv_ml_update(C.c_void_p(h), stream))
+
+    def ml_residual(self, h, stream):
+        return self._chk(lib().ifadv_ml_residual(C.c_void_p(h), stream))
+
+    def ml_vcycle(self, h, stream):
+        return self._chk(lib().ifadv_ml_vcycle(C.c_void_p(h), stream))
+
+    def ml_smooth(self, h, stream, level=0):
+        return self._chk(lib().ifadv_ml_smooth(C.c_void_p(h), stream, int(level)))
+
+    def ml_solver(self, h, stream, tol=1e-4, itmx=32):
+        """(cycles, last r₂) of solver!(ml;tol,itmx) (ifadv_ml_solver)."""
+        n, r2 = C.c_int(0), C.c_double(0.0)
+        self._chk(lib().ifadv_ml_solver(C.c_void_p(h), stream, float(tol), int(itmx), C.byref(n), C.byref(r2)))
+        return n.value, r2.value
+
+    def ml_myproject(self, h, stream, u, dt):
+        """(cycles, last r₂) of myproject!(a,b::MultiLevelPoisson,w), dt = T(w)·last(a.Δt) (ifadv_ml_myproject)."""
+        n, r2 = C.c_int(0), C.c_double(0.0)
+        self._chk(lib().ifadv_ml_myproject(C.c_void_p(h), stream, u, float(dt), C.byref(n), C.byref(r2)))
         return n.value, r2.value
 
     def defer_f_writes_until(self, event):

@@ -240,8 +240,14 @@ class TwoPhaseSimulation:
                          normalScheme=normalScheme, perdir=perdir, device=device)
         self.flow.dt[-1] = min(self.flow.dt[-1], MPCFL(self.flow, self.intf))  # InterfaceAdvection.jl:81
         # psolver=Poisson: WaterLily's Simulation(...; psolver=Poisson) -- the solver the reference's psolver! is written for
-        # (flow.jl:300); MultiLevelPoisson (WaterLily's default) is not built: pass a `project` hook instead
-        self.pois = Poisson(self.flow.p, self.flow.mu0, self.flow.sigma, perdir=perdir) if psolver in ("Poisson", Poisson) else None
+        # (flow.jl:300); psolver=MultiLevelPoisson: WaterLily's default, inproject!'s second method (flow.jl:343-347); None: no projection
+        # object (velocities prescribed, or a `project` hook of the caller's)
+        if psolver in ("Poisson", Poisson):
+            self.pois = Poisson(self.flow.p, self.flow.mu0, self.flow.sigma, perdir=perdir)
+        elif psolver in ("MultiLevelPoisson", MultiLevelPoisson):
+            self.pois = MultiLevelPoisson(self.flow.p, self.flow.mu0, self.flow.sigma, perdir=perdir)
+        else:
+            self.pois = None
         self.body = None
 
 
@@ -480,8 +486,10 @@ class Poisson:
         update(self)
 
 
-def update(b: Poisson):
-    """update!(b::Poisson) = set_diag!(D,iD,L) (flow.jl:81,105)."""
+def update(b):
+    """update!(b::Poisson) = set_diag!(D,iD,L); update!(b::MultiLevelPoisson) = set_diag! + restrictL! down the levels (flow.jl:81,105)."""
+    if isinstance(b, MultiLevelPoisson):
+        return b._ctx.ml_update(b._h, _stream(b.x))
     return context_for(b.x).poisson_update(_stream(b.x), _p(b.D), _p(b.iD), _p(b.L))
 
 
@@ -492,22 +500,93 @@ def psolver(b: Poisson, tol=None, itmx=6000):
     return n
 
 
-def myproject(a: Flow, b: Poisson, w=1.0):
-    """myproject!(a,b,w) (src/flow.jl:328-347): dt = T(w)·last(a.Δt); z ← ∇·u, x ← x·dt, psolver!, u -= L ∂x, x ← x/dt."""
+def myproject(a: Flow, b, w=1.0):
+    """myproject!(a,b,w) (src/flow.jl:328-347): dt = T(w)·last(a.Δt); z ← ∇·u, x ← x·dt, psolver! (b::Poisson) or
+    solver!(b;tol=1e-4,itmx=200) (b::MultiLevelPoisson), u -= L ∂x, x ← x/dt."""
     T = a.u.dtype
     dt = float(torch.tensor(w, dtype=T) * torch.tensor(a.dt[-1], dtype=T))
+    if isinstance(b, MultiLevelPoisson):
+        n, r2 = b._ctx.ml_myproject(b._h, _stream(b.x), _p(a.u), dt)
+        b.n.append(n); b.r2.append(r2)
+        return n
     n, r2 = context_for(b.x).myproject(_stream(b.x), _p(a.u), _p(b.x), _p(b.eps), _p(b.r), _p(b.z), _p(b.L), _p(b.D), _p(b.iD), dt, b.perdir)
     b.n.append(n); b.r2.append(r2)
     return n
 
 
-def project_with(b: Poisson) -> Callable:
-    """The `project(a, c, stage)` hook of MPFMomStep / mom_step_forcing for a Poisson: update!(b); myproject!(a,b[,1/2])
+def project_with(b) -> Callable:
+    """The `project(a, c, stage)` hook of MPFMomStep / mom_step_forcing for a Poisson / MultiLevelPoisson: update!(b); myproject!(a,b[,1/2])
     (flow.jl:81-82,105-106)."""
     def hook(a, c, stage):
         update(b)
         myproject(a, b, 0.5 if stage == "predictor" else 1.0)
     return hook
+
+
+class _DevView:
+    """A device array the library owns, exposed through __cuda_array_interface__ (no copy; valid while its owner lives)."""
+
+    def __init__(self, ptr, shape_c, dtype):
+        self.__cuda_array_interface__ = {"shape": tuple(shape_c), "typestr": "<f4" if dtype == torch.float32 else "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class MultiLevelPoisson:
+    """WaterLily.MultiLevelPoisson(x,L,z;maxlevels=10,perdir): geometric multigrid on the caller's x ≡ Flow.p, L ≡ Flow.μ₀, z ≡ Flow.σ
+    (level 1); the coarser levels and every level's D, iD, ϵ, r live in the library's handle (ifadv_ml_*).  The solver behind
+    inproject!(a,b::MultiLevelPoisson,dt) (src/flow.jl:343-347) and WaterLily's default `psolver`.  n collects the cycle counts like the
+    reference's `ml.n`.  level(l, name) is a column-major view of a level's array (name: L, D, iD, x, eps, r, z)."""
+    _NAMES = {"L": 0, "D": 1, "iD": 2, "x": 3, "eps": 4, "r": 5, "z": 6}
+
+    def __init__(self, x, L, z, perdir=(), maxlevels=10):
+        self.x, self.L, self.z, self.perdir = x, L, z, tuple(perdir)
+        self._ctx = context_for(x)
+        self._h = self._ctx.ml_create(_stream(x), _p(x), _p(L), _p(z), self.perdir, maxlevels)
+        if self._ctx.ml_levels(self._h) <= 2:  # WaterLily's constructor asserts length(levels) > 2
+            self._ctx.ml_destroy(self._h)
+            self._h = None
+            raise IfadvError("MultiLevelPoisson requires size=a2ⁿ, where n>2")
+        self.n, self.r2 = [], []
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                self._ctx.ml_destroy(self._h)
+        except Exception:
+            pass
+
+    @property
+    def levels(self) -> int:
+        return self._ctx.ml_levels(self._h)
+
+    def level(self, l, name) -> torch.Tensor:
+        ptr, ng = self._ctx.ml_level_array(self._h, l, self._NAMES[name])
+        D = self.x.dim()
+        shape = tuple(ng[:D]) + ((D,) if name == "L" else ())
+        t = torch.as_tensor(_DevView(ptr, tuple(reversed(shape)), self.x.dtype), device=self.x.device)
+        return t.permute(*reversed(range(len(shape))))
+
+
+def Vcycle(ml: MultiLevelPoisson):
+    """Vcycle!(ml) (WaterLily MultiLevelPoisson.jl)."""
+    return ml._ctx.ml_vcycle(ml._h, _stream(ml.x))
+
+
+def smooth(ml: MultiLevelPoisson, level=0):
+    """smooth!(ml.levels[level+1]) = pcg!(p;it=6)."""
+    return ml._ctx.ml_smooth(ml._h, _stream(ml.x), level)
+
+
+def residual(ml: MultiLevelPoisson):
+    """residual!(ml): r = z - A x on level 1, mean removed."""
+    return ml._ctx.ml_residual(ml._h, _stream(ml.x))
+
+
+def solver(ml: MultiLevelPoisson, tol=1e-4, itmx=32):
+    """solver!(ml;tol=1e-4,itmx=32) -> V-cycles."""
+    n, r2 = ml._ctx.ml_solver(ml._h, _stream(ml.x), tol, itmx)
+    ml.n.append(n); ml.r2.append(r2)
+    return n
 
 
 # ---- post-processing (SURVEY §8f row 4) --------------------------------------------------------------------------------------------
@@ -554,7 +633,7 @@ def MPFMomStep(a: Flow, b, c: cVOF, d=None, dt=None, project: Optional[Callable]
     forcing=True runs the reference's whole sequence except the Poisson solve -- viscSurfTenρu!, updateU!, BC!, updateL! on the B200
     kernels too (mom_step_forcing) -- and `project` then stands for update!(b); myproject! only."""
     dt = a.dt[-1] if dt is None else dt
-    if project is None and forcing and isinstance(b, Poisson):
+    if project is None and forcing and isinstance(b, (Poisson, MultiLevelPoisson)):
         project = project_with(b)  # the reference's own projection on the B200 kernels (SURVEY §8f row 2)
     if forcing:
         mom_step_forcing(a, c, dt, project=project, check=check)

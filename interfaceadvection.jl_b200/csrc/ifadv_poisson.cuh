@@ -32,6 +32,9 @@ struct PoisCtl {
   double acc[4];    // pois_fin_kernel applies the scalar step -- identical values, hence identical decisions, on every rank
   unsigned ticket[4];
   double part[3][IFADV_POIS_MAXB];
+  // pcg! smoother of the multigrid levels (ifadv_mlpoisson.cuh): step length, "still iterating", "r2 belongs to the current r"
+  double alpha;
+  int live, r2_valid;
 };
 
 template <class T> struct teps;

@@ -220,7 +220,7 @@ template <class T> void pois_pcg_smooth(const Grid& g, const Pois<T>& p, int it 
     perBC(g, p.eps, p.perdir);
     loop(r_inside(g), [&](I3 I) { p.z(I) = pois_mult(g, I, p.L, p.D, p.eps); });
     const T alpha = rho / pois_dot(g, p.z, p.eps);
-    if (std::abs(alpha) < T(1e-2) || std::abs(alpha) > T(1e3)) return;  // alpha should be O(1)
+    if (std::abs((double)alpha) < 1e-2 || std::abs((double)alpha) > 1e3) return;  // alpha should be O(1); Float64 literals in the reference
     loop(r_inside(g), [&](I3 I) {
       p.x(I) += alpha * p.eps(I);
       p.r(I) -= alpha * p.z(I);

@@ -108,6 +108,11 @@ def oracle_mom_step_hook(st, f, u, dt, dirO, hook, lam="Koren", scheme="WH"):
     return a["rhou"]
 
 
+def _oproject(u, pois, dt):
+    """myproject! on the oracle: both inproject! methods (Poisson / MultiLevelPoisson, flow.jl:343-353)."""
+    return O.ml_myproject(u, pois, dt) if isinstance(pois, O.MultiLevelPoisson) else O.myproject(u, pois, dt)
+
+
 def oracle_mom_step_forcing(st, a, f, u, dt, dirO, mu, lam_mu, eta, g, lam="Koren", scheme="WH", pois=None):
     """MPFMomStep! with its explicit forcing (flow.jl:60-107) on the oracle; pois=None leaves the Poisson solve out (:81-82,:105-106),
     pois = O.Poisson(p, a["mu0"], a["Phi"]) runs update!(b); myproject!(a,b[,1/2]); BC! at its two places.
@@ -127,7 +132,7 @@ def oracle_mom_step_forcing(st, a, f, u, dt, dirO, mu, lam_mu, eta, g, lam="Kore
     O.BC(u, uBC, False, pd)                                                                             # :79
     O.updateL(a["mu0"], f0, lr, pd)                                                                     # :80
     if pois is not None:
-        pois.update(); O.myproject(u, pois, T(0.5) * T(dt)); O.BC(u, uBC, False, pd)                    # :81-82
+        pois.update(); _oproject(u, pois, T(0.5) * T(dt)); O.BC(u, uBC, False, pd)                    # :81-82
     f0[...] = f                                                                                         # :89
     O.u2rhou(a["rhou"], u0, f, lr); O.BC(a["rhou"], uBC, False, pd)                                     # :91
     O.advectVOFrhouu(f, a["ff"], a["alpha"], a["nhat"], u, u, dt, a["cbar"], a["rhou"], a["r"], a["Phi"], a["rhouf"], a["nhat"], u0,
@@ -140,5 +145,5 @@ def oracle_mom_step_forcing(st, a, f, u, dt, dirO, mu, lam_mu, eta, g, lam="Kore
     O.BC(u, uBC, False, pd)                                                                             # :103
     O.updateL(a["mu0"], f, lr, pd)                                                                      # :104
     if pois is not None:
-        pois.update(); O.myproject(u, pois, T(1) * T(dt)); O.BC(u, uBC, False, pd)                      # :105-106
+        pois.update(); _oproject(u, pois, T(1) * T(dt)); O.BC(u, uBC, False, pd)                      # :105-106
     return a["rhou"]
