@@ -40,6 +40,7 @@ struct ifadv_ml {
   cudaGraphExec_t cycle_exec;
   int64_t cycle_launches;
   int use_graph;
+  int bottom;  // first level (>= 1) of the single-CTA bottom kernel; lv.size(): none
 };
 
 namespace {
@@ -119,8 +120,20 @@ template <class T, int D> void vcycle_t(ifadv_ml* m, cudaStream_t st, size_t l) 
   increment_lv<T, D>(m, f, st);
   ml_restrict_kernel<T, D><<<c.nb, 256, 0, st>>>((T*)c.r, (T*)c.x, c.g, (const T*)f.r, f.g, 2, kz1_of(c, D));    // restrict!; fill!(coarse.x,0)
   c.c->launches++;
-  if (l + 2 < m->lv.size()) vcycle_t<T, D>(m, st, l + 1);
-  smooth_lv<T, D>(m, c, st);
+  if ((int)l + 1 >= m->bottom) {  // [Vcycle!(l+1)]; smooth!(coarse) for all remaining levels in one CTA
+    MLBottom<T> P{};
+    P.n = (int)m->lv.size() - (int)(l + 1);
+    P.per = m->per;
+    for (int k = 0; k < P.n; ++k) {
+      const MLLevel& v = m->lv[l + 1 + k];
+      P.lv[k] = MLDev<T>{v.g, (const T*)v.L, (const T*)v.D, (const T*)v.iD, (T*)v.x, (T*)v.eps, (T*)v.r, (T*)v.z};
+    }
+    ml_bottom_kernel<T, D><<<1, 1024, 0, st>>>(P);
+    c.c->launches++;
+  } else {
+    if (l + 2 < m->lv.size()) vcycle_t<T, D>(m, st, l + 1);
+    smooth_lv<T, D>(m, c, st);
+  }
   ml_prolongate_kernel<T, D><<<f.nb, 256, 0, st>>>((T*)f.eps, f.g, (const T*)c.x, c.g, 2, kz1_of(f, D));         // prolongate!
   f.c->launches++;
   increment_lv<T, D>(m, f, st);
@@ -285,6 +298,12 @@ int ifadv_ml_create(ifadv_ctx* c, ifadv_ml** out, void* stream, void* x, void* L
     ifadv_ctx* lc = nullptr;
     if (ifadv_create(&lc, c->D, Na, c->dtype, c->device) != 0) return fail(-3, "context of a multigrid level");
     if (!add_level(lc, nullptr, nullptr, nullptr)) return fail(-3, "out of device memory for the multigrid levels");
+  }
+  {  // levels of at most IFADV_ML_BOTTOM entries (default 8000, e.g. 18^3; 0: none) run in the single-CTA bottom kernel
+    const char* e = getenv("IFADV_ML_BOTTOM");
+    const long long cap = e ? atoll(e) : 8000;
+    m->bottom = (int)m->lv.size();
+    for (int l = (int)m->lv.size() - 1; l >= 1 && m->lv[l].g.S <= cap && (int)m->lv.size() - l <= IFADV_ML_BOTTOM_MAX; --l) m->bottom = l;
   }
   if (cudaMallocHost(&m->host_r2, sizeof(double)) != cudaSuccess) return fail(-3, "pinned memory");
   if (cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(-3, "stream");

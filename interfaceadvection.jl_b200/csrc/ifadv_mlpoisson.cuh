@@ -294,4 +294,146 @@ template <class T, int D> __global__ void __launch_bounds__(256) ml_r2_kernel(co
   }
 }
 
+// ---- the bottom of the V-cycle in ONE CTA -------------------------------------------------------------------------------------------
+// Levels of a few thousand cells are pure launch latency in the multi-kernel form (~35 launches of ~2.5 us per level and cycle, for
+// microseconds of work).  ml_bottom_kernel runs "[Vcycle!(l = b)]; smooth!(level b)" for all levels from b down to the coarsest in a
+// single CTA of 1024 threads: __syncthreads() stands where the kernel boundaries were, the smoother's scalars are block-uniform
+// registers, dot products are block reductions in Float64 (fixed order).  Same per-cell arithmetic as the kernels above.  Arrays
+// written inside the launch (x, ϵ, r, z) are read with plain loads; L, D, iD are constant here and go through the read-only path.
+#define IFADV_ML_BOTTOM_MAX 8
+template <class T> struct MLDev {
+  Geo g;
+  const T *L, *D, *iD;
+  T *x, *eps, *r, *z;
+};
+template <class T> struct MLBottom {
+  MLDev<T> lv[IFADV_ML_BOTTOM_MAX];
+  int n;
+  unsigned per;
+};
+
+template <int D, class F> IFADV_DI void bt_inside(const Geo& g, F&& fn) {
+  const int nx = g.n[0] - 2, ny = g.n[1] - 2, nz = (D == 3) ? g.n[2] - 2 : 1;
+  const int tot = nx * ny * nz;
+  for (int t = threadIdx.x; t < tot; t += blockDim.x) {
+    const int ix = t % nx, q = t / nx, iy = q % ny, iz = q / ny;
+    fn(2 + ix, 2 + iy, (D == 3) ? 2 + iz : 1, lin3(g, 2 + ix, 2 + iy, (D == 3) ? 2 + iz : 1));
+  }
+}
+// block sum, returned to every thread; two barriers inside, so everything written before the call is visible after it
+IFADV_DI double bt_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double t = (lane < nw) ? sh[lane] : 0.0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    if (lane == 0) sh[32] = t;
+  }
+  __syncthreads();
+  const double r = sh[32];
+  __syncthreads();
+  return r;
+}
+// perBC!(a,perdir) by the whole CTA (closed form of the sequential plane copies, as perbc_kernel); barrier before and after
+template <class T, int D> IFADV_DI void bt_perbc(T* a, const Geo& g, unsigned per) {
+  if (!per) return;
+  __syncthreads();
+  const long long n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
+  const long long c0 = (per & 1u) ? 2 * n1 * n2 : 0, c1 = (per & 2u) ? 2 * n0 * n2 : 0, c2 = (D == 3 && (per & 4u)) ? 2 * n0 * n1 : 0;
+  for (long long t = threadIdx.x; t < c0 + c1 + c2; t += blockDim.x) {
+    int xx, yy, zz;
+    if (t < c0) { const long long q = t >> 1; xx = (t & 1) ? (int)n0 : 1; yy = (int)(q % n1) + 1; zz = (int)(q / n1) + 1; }
+    else if (t < c0 + c1) { const long long u_ = t - c0, q = u_ >> 1; yy = (u_ & 1) ? (int)n1 : 1; xx = (int)(q % n0) + 1; zz = (int)(q / n0) + 1; }
+    else { const long long u_ = t - c0 - c1, q = u_ >> 1; zz = (u_ & 1) ? (int)n2 : 1; xx = (int)(q % n0) + 1; yy = (int)(q / n0) + 1; }
+    const int mx = (per & 1u) ? wrapc(xx, g.n[0]) : xx, my = (per & 2u) ? wrapc(yy, g.n[1]) : yy, mz = (D == 3 && (per & 4u)) ? wrapc(zz, g.n[2]) : zz;
+    a[lin3(g, xx, yy, zz)] = a[lin3(g, mx, my, mz)];
+  }
+  __syncthreads();
+}
+// increment!(p): perBC!(ϵ); r -= Aϵ; x += ϵ
+template <class T, int D> IFADV_DI void bt_increment(const MLDev<T>& v, unsigned per) {
+  __syncthreads();
+  bt_perbc<T, D>(v.eps, v.g, per);
+  bt_inside<D>(v.g, [&](int, int, int, long long l) {
+    v.r[l] = v.r[l] - pois_mult_plain<T, D>(v.L, v.D, v.eps, v.g, l);
+    v.x[l] = v.x[l] + v.eps[l];
+  });
+  __syncthreads();
+}
+// smooth!(p) = pcg!(p;it=6); block-uniform control flow
+template <class T, int D> IFADV_DI void bt_smooth(const MLDev<T>& v, unsigned per, double* sh) {
+  double acc = 0.0;
+  bt_inside<D>(v.g, [&](int, int, int, long long l) {
+    const T rv = v.r[l], zv = rv * __ldg(v.iD + l);
+    v.z[l] = zv;
+    v.eps[l] = zv;
+    acc += (double)rv * (double)zv;
+  });
+  T rho = (T)bt_sum(acc, sh);
+  if (t_abs(rho) < T(10) * teps<T>::v) return;
+  for (int i = 1; i <= 6; ++i) {
+    bt_perbc<T, D>(v.eps, v.g, per);
+    acc = 0.0;
+    bt_inside<D>(v.g, [&](int, int, int, long long l) {
+      const T w = pois_mult_plain<T, D>(v.L, v.D, v.eps, v.g, l);
+      v.z[l] = w;
+      acc += (double)w * (double)v.eps[l];
+    });
+    const T alpha = rho / (T)bt_sum(acc, sh);
+    const double aa = fabs((double)alpha);
+    if (aa < 1e-2 || aa > 1e3) return;
+    acc = 0.0;
+    const bool last = (i == 6);
+    bt_inside<D>(v.g, [&](int, int, int, long long l) {
+      v.x[l] = v.x[l] + alpha * v.eps[l];
+      const T rn = v.r[l] - alpha * v.z[l];
+      v.r[l] = rn;
+      if (!last) {
+        const T zn = rn * __ldg(v.iD + l);
+        v.z[l] = zn;
+        acc += (double)rn * (double)zn;
+      }
+    });
+    if (last) { __syncthreads(); return; }
+    const T rho2 = (T)bt_sum(acc, sh);
+    if (t_abs(rho2) < T(10) * teps<T>::v) return;
+    const T beta = rho2 / rho;
+    bt_inside<D>(v.g, [&](int, int, int, long long l) { v.eps[l] = beta * v.eps[l] + v.z[l]; });
+    rho = rho2;
+    __syncthreads();
+  }
+}
+template <class T, int D> __global__ void __launch_bounds__(1024) ml_bottom_kernel(const MLBottom<T> P) {
+  __shared__ double sh[40];
+  const int n = P.n;
+  for (int k = 0; k + 1 < n; ++k) {  // down: Jacobi!(fine); restrict!(coarse.r, fine.r); fill!(coarse.x, 0)
+    const MLDev<T>& f = P.lv[k];
+    const MLDev<T>& c = P.lv[k + 1];
+    bt_inside<D>(f.g, [&](int, int, int, long long l) { f.eps[l] = f.r[l] * __ldg(f.iD + l); });
+    bt_increment<T, D>(f, P.per);
+    bt_inside<D>(c.g, [&](int xc, int y, int zc, long long l) {
+      T s = T(0);
+      for (int c2 = 0; c2 <= ((D == 3) ? 1 : 0); ++c2)
+        for (int c1 = 0; c1 <= 1; ++c1)
+          for (int c0 = 0; c0 <= 1; ++c0) s = s + f.r[lin3(f.g, 2 * xc - 2 + c0, 2 * y - 2 + c1, (D == 3) ? 2 * zc - 2 + c2 : 1)];
+      c.r[l] = s;
+      c.x[l] = T(0);
+    });
+    __syncthreads();
+  }
+  bt_smooth<T, D>(P.lv[n - 1], P.per, sh);
+  for (int k = n - 2; k >= 0; --k) {  // up: prolongate!(fine.ϵ, coarse.x); increment!(fine); then smooth! of that level (its parent's call)
+    const MLDev<T>& f = P.lv[k];
+    const MLDev<T>& c = P.lv[k + 1];
+    __syncthreads();
+    bt_inside<D>(f.g, [&](int xc, int y, int zc, long long l) { f.eps[l] = c.x[lin3(c.g, (xc + 2) >> 1, (y + 2) >> 1, (D == 3) ? (zc + 2) >> 1 : 1)]; });
+    bt_increment<T, D>(f, P.per);
+    bt_smooth<T, D>(f, P.per, sh);
+  }
+}
+
 }  // namespace ifadv

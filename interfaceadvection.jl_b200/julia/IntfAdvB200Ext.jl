@@ -173,7 +173,7 @@ function updateL!(μ₀::CuArray{T}, f::CuArray{T}, λρ; perdir=()) where {T<:U
 end
 
 # ---- pressure projection on WaterLily's Poisson (src/flow.jl:300-347): update!, psolver!, myproject! -------------------------------
-# b.L ≡ a.μ₀, b.x ≡ a.p, b.z ≡ a.σ; MultiLevelPoisson keeps WaterLily's own solver!.
+# b.L ≡ a.μ₀, b.x ≡ a.p, b.z ≡ a.σ; MultiLevelPoisson: next block.
 const CuPoisson{T} = WaterLily.Poisson{T,<:CuArray{T},<:CuArray{T}}
 function WaterLily.update!(b::CuPoisson{T}) where {T<:Union{Float32,Float64}}
     ctx = context(b.x)
@@ -199,6 +199,40 @@ function myproject!(a::Flow{n,T}, b::CuPoisson{T}, w=1) where {n,T<:Union{Float3
                      ctx, stream_ptr(), dptr(a.u), dptr(b.x), dptr(b.ϵ), dptr(b.r), dptr(b.z), dptr(b.L), dptr(b.D), dptr(b.iD),
                      Cdouble(T(w) * last(a.Δt)), perdir_mask(b.perdir), it, r₂))
     push!(b.n, it[]); nothing
+end
+
+# ---- WaterLily.MultiLevelPoisson (WaterLily's default psolver; inproject!'s second method, src/flow.jl:343-347) -----------------------
+# The library keeps the coarse levels (and level 1's D, iD, ϵ, r) in a handle built from ml.x ≡ a.p, ml.L ≡ a.μ₀, ml.z ≡ a.σ; one handle per
+# ml object, destroyed with it.  ml.levels[2:end] of the Julia object are not used by the methods below.
+const CuMLPoisson{T} = WaterLily.MultiLevelPoisson{T,<:CuArray{T},<:CuArray{T}}
+const ML_HANDLES = IdDict{Any,Ptr{Cvoid}}()
+function ml_handle(ml::CuMLPoisson{T}) where {T<:Union{Float32,Float64}}
+    get!(ML_HANDLES, ml) do
+        ctx = context(ml.x)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ctx, ccall((:ifadv_ml_create, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cuint, Cint),
+                         ctx, h, stream_ptr(), dptr(ml.x), dptr(ml.L), dptr(ml.z), perdir_mask(ml.perdir), Cint(10)))
+        finalizer(ml) do m
+            hh = pop!(ML_HANDLES, m, C_NULL)
+            hh == C_NULL || ccall((:ifadv_ml_destroy, LIB), Cint, (Ptr{Cvoid},), hh)
+        end
+        h[]
+    end
+end
+function WaterLily.update!(ml::CuMLPoisson{T}) where {T<:Union{Float32,Float64}}
+    check(context(ml.x), ccall((:ifadv_ml_update, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ml_handle(ml), stream_ptr())); nothing
+end
+function WaterLily.solver!(ml::CuMLPoisson{T}; log=false, tol=1e-4, itmx=32) where {T<:Union{Float32,Float64}}
+    n = Ref{Cint}(0); r₂ = Ref{Cdouble}(0)
+    check(context(ml.x), ccall((:ifadv_ml_solver, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Cint}, Ptr{Cdouble}),
+                               ml_handle(ml), stream_ptr(), Cdouble(tol), Cint(itmx), n, r₂))
+    push!(ml.n, n[]); nothing
+end
+function myproject!(a::Flow{n,T}, ml::CuMLPoisson{T}, w=1) where {n,T<:Union{Float32,Float64}}
+    it = Ref{Cint}(0); r₂ = Ref{Cdouble}(0)
+    check(context(ml.x), ccall((:ifadv_ml_myproject, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cint}, Ptr{Cdouble}),
+                               ml_handle(ml), stream_ptr(), dptr(a.u), Cdouble(T(w) * last(a.Δt)), it, r₂))
+    push!(ml.n, it[]); nothing
 end
 
 # ---- post-processing: level-set redistancing (src/redistaning.jl:31-87) and metric sums (src/metrics.jl) ---------------------------
