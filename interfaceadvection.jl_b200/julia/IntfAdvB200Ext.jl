@@ -213,25 +213,28 @@ function ml_handle(ml::CuMLPoisson{T}) where {T<:Union{Float32,Float64}}
         check(ctx, ccall((:ifadv_ml_create, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cuint, Cint),
                          ctx, h, stream_ptr(), dptr(ml.x), dptr(ml.L), dptr(ml.z), perdir_mask(ml.perdir), Cint(10)))
         finalizer(ml) do m
-            hh = pop!(ML_HANDLES, m, C_NULL)
-            hh == C_NULL || ccall((:ifadv_ml_destroy, LIB), Cint, (Ptr{Cvoid},), hh)
+            ctxml = pop!(ML_HANDLES, m, C_NULL)
+            ctxml == C_NULL || ccall((:ifadv_ml_destroy, LIB), Cint, (Ptr{Cvoid},), ctxml)
         end
         h[]
     end
 end
 function WaterLily.update!(ml::CuMLPoisson{T}) where {T<:Union{Float32,Float64}}
-    check(context(ml.x), ccall((:ifadv_ml_update, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ml_handle(ml), stream_ptr())); nothing
+    ctxml = ml_handle(ml)
+    check(context(ml.x), ccall((:ifadv_ml_update, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctxml, stream_ptr())); nothing
 end
 function WaterLily.solver!(ml::CuMLPoisson{T}; log=false, tol=1e-4, itmx=32) where {T<:Union{Float32,Float64}}
     n = Ref{Cint}(0); r₂ = Ref{Cdouble}(0)
+    ctxml = ml_handle(ml)
     check(context(ml.x), ccall((:ifadv_ml_solver, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Cint}, Ptr{Cdouble}),
-                               ml_handle(ml), stream_ptr(), Cdouble(tol), Cint(itmx), n, r₂))
+                               ctxml, stream_ptr(), Cdouble(tol), Cint(itmx), n, r₂))
     push!(ml.n, n[]); nothing
 end
 function myproject!(a::Flow{n,T}, ml::CuMLPoisson{T}, w=1) where {n,T<:Union{Float32,Float64}}
     it = Ref{Cint}(0); r₂ = Ref{Cdouble}(0)
+    ctxml = ml_handle(ml)
     check(context(ml.x), ccall((:ifadv_ml_myproject, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cint}, Ptr{Cdouble}),
-                               ml_handle(ml), stream_ptr(), dptr(a.u), Cdouble(T(w) * last(a.Δt)), it, r₂))
+                               ctxml, stream_ptr(), dptr(a.u), Cdouble(T(w) * last(a.Δt)), it, r₂))
     push!(ml.n, it[]); nothing
 end
 

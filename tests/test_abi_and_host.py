@@ -139,7 +139,8 @@ def test_julia_ccall_signatures_match_header():
         assert kinds == protos[name], (name, kinds, protos[name])
         seen.add(name)
     assert {"ifadv_create", "ifadv_advect_vof", "ifadv_advect_vof_rhouu", "ifadv_u2rhou_advect_vof_rhouu", "ifadv_u2rhou", "ifadv_rhou2u",
-            "ifadv_mpcfl", "ifadv_last_error", "ifadv_poisson_update", "ifadv_psolver", "ifadv_myproject"} <= seen
+            "ifadv_mpcfl", "ifadv_last_error", "ifadv_poisson_update", "ifadv_psolver", "ifadv_myproject", "ifadv_ml_create", "ifadv_ml_destroy",
+            "ifadv_ml_update", "ifadv_ml_solver", "ifadv_ml_myproject"} <= seen
     # report struct: field order and C types
     c_fields = re.search(r"typedef struct \{(.*?)\} ifadv_report;", hdr_nc, flags=re.S).group(1)
     c_names = re.findall(r"\b(maxf|minf|argmax|argmin|dir|status|div_u0|div_u)\b", c_fields)
