@@ -27,6 +27,7 @@ struct MLLevel {
   void *L, *D, *iD, *x, *eps, *r, *z;
   PoisCtl* ctl;
   unsigned nb;   // CTAs of the row-walking kernels
+  unsigned nb_mult, nb_inc;  // persistent grids of the two stencil kernels: SM count x resident CTAs of that kernel (as psolver_t does)
 };
 }  // namespace
 
@@ -53,6 +54,17 @@ inline unsigned lv_blocks(const MLLevel& v, int D) {
   return (unsigned)std::max<long long>(1, std::min<long long>((rows + 7) / 8, std::min(148LL * 6, (long long)IFADV_POIS_MAXB)));
 }
 inline int kz1_of(const MLLevel& v, int D) { return D == 3 ? v.g.n[2] : 2; }
+template <class K> unsigned lv_resident(const MLLevel& v, int D, int device, K kernel) {
+  int occ = 0, sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0) != cudaSuccess || occ < 1) occ = 2;
+  const long long rows = (long long)(v.g.n[1] - 2) * (D == 3 ? v.g.n[2] - 2 : 1);
+  return (unsigned)std::max<long long>(1, std::min<long long>((rows + 7) / 8, std::min<long long>((long long)sms * occ, IFADV_POIS_MAXB)));
+}
+template <class T, int D> void lv_grids(MLLevel& v, int device) {
+  v.nb_mult = lv_resident(v, D, device, ml_pcg_mult_kernel<T, D>);
+  v.nb_inc = lv_resident(v, D, device, ml_increment_kernel<T, D>);
+}
 
 template <class T, int D> int perbc_lv(MLLevel& v, cudaStream_t st, T* a, unsigned per) {
   Geo g = v.g;
@@ -90,7 +102,7 @@ template <class T, int D> int ml_update_t(ifadv_ml* m, cudaStream_t st) {
 // increment!(p): perBC!(ϵ); r -= Aϵ; x += ϵ
 template <class T, int D> void increment_lv(ifadv_ml* m, MLLevel& v, cudaStream_t st) {
   perbc_lv<T, D>(v, st, (T*)v.eps, m->per);
-  ml_increment_kernel<T, D><<<v.nb, 256, 0, st>>>((T*)v.x, (T*)v.r, (const T*)v.eps, (const T*)v.L, (const T*)v.D, v.g, 2, kz1_of(v, D));
+  ml_increment_kernel<T, D><<<v.nb_inc, 256, 0, st>>>((T*)v.x, (T*)v.r, (const T*)v.eps, (const T*)v.L, (const T*)v.D, v.g, 2, kz1_of(v, D));
   v.c->launches++;
 }
 
@@ -103,7 +115,7 @@ template <class T, int D> void smooth_lv(ifadv_ml* m, MLLevel& v, cudaStream_t s
   v.c->launches++;
   for (int i = 1; i <= it; ++i) {
     perbc_lv<T, D>(v, st, eps, m->per);
-    ml_pcg_mult_kernel<T, D><<<v.nb, 256, 0, st>>>(z, eps, L, Dg, v.g, v.ctl, 2, k1);
+    ml_pcg_mult_kernel<T, D><<<v.nb_mult, 256, 0, st>>>(z, eps, L, Dg, v.g, v.ctl, 2, k1);
     ml_pcg_update_kernel<T, D><<<v.nb, 256, 0, st>>>(x, r, z, eps, iD, v.g, v.ctl, i == it ? 1 : 0, 2, k1);
     v.c->launches += 2;
     if (i == it) break;
@@ -289,6 +301,9 @@ int ifadv_ml_create(ifadv_ctx* c, ifadv_ml** out, void* stream, void* x, void* L
     if (!px && !(zalloc(&w.L, S * c->D) && zalloc(&w.x, S) && zalloc(&w.z, S))) return false;
     if (!(zalloc(&w.D, S) && zalloc(&w.iD, S) && zalloc(&w.eps, S) && zalloc(&w.r, S) && zalloc((void**)&w.ctl, sizeof(PoisCtl)))) return false;
     w.nb = lv_blocks(w, c->D);
+    if (getenv("IFADV_ML_GRID888")) w.nb_mult = w.nb_inc = w.nb;  // measurement knob: the common grid for the stencil kernels too
+    else if (c->dtype == IFADV_F32) { if (c->D == 2) lv_grids<float, 2>(w, c->device); else lv_grids<float, 3>(w, c->device); }
+    else { if (c->D == 2) lv_grids<double, 2>(w, c->device); else lv_grids<double, 3>(w, c->device); }
     return true;
   };
   if (!add_level(c, x, L, z)) return fail(-3, "out of device memory for the multigrid levels");
