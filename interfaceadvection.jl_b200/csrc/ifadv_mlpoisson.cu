@@ -42,6 +42,8 @@ struct ifadv_ml {
   int64_t cycle_launches;
   int use_graph;
   int bottom;  // first level (>= 1) of the single-CTA bottom kernel; lv.size(): none
+  long long march_minS;  // levels of at least this many entries use the marching form (0 when IFADV_POIS_MARCH is set explicitly)
+  int march, march_occ;  // IFADV_POIS_MARCH: planes per chunk of the marching mult kernel (0: row form), its resident CTAs per SM
 };
 
 namespace {
@@ -115,6 +117,11 @@ template <class T, int D> void smooth_lv(ifadv_ml* m, MLLevel& v, cudaStream_t s
   v.c->launches++;
   for (int i = 1; i <= it; ++i) {
     perbc_lv<T, D>(v, st, eps, m->per);
+    if (D == 3 && m->march > 0 && v.g.S >= m->march_minS) {  // marching form of z = Aϵ on the large levels (ifadv_poisson.cuh; IFADV_POIS_MARCH=0: row form)
+      const long long items = (long long)((v.g.n[0] - 2 + 31) / 32) * ((v.g.n[1] - 2 + 7) / 8) * ((k1 - 2 + m->march - 1) / m->march);
+      const unsigned nbm = (unsigned)std::max<long long>(1, std::min<long long>(items, std::min<long long>(148LL * m->march_occ, IFADV_POIS_MAXB)));
+      pois_mult_march_kernel<T, 1><<<nbm, 256, 0, st>>>(z, eps, L, Dg, v.g, v.ctl, 2, k1, m->march);
+    } else
     ml_pcg_mult_kernel<T, D><<<v.nb_mult, 256, 0, st>>>(z, eps, L, Dg, v.g, v.ctl, 2, k1);
     ml_pcg_update_kernel<T, D><<<v.nb, 256, 0, st>>>(x, r, z, eps, iD, v.g, v.ctl, i == it ? 1 : 0, 2, k1);
     v.c->launches += 2;
@@ -319,6 +326,15 @@ int ifadv_ml_create(ifadv_ctx* c, ifadv_ml** out, void* stream, void* x, void* L
     const long long cap = e ? atoll(e) : 8000;
     m->bottom = (int)m->lv.size();
     for (int l = (int)m->lv.size() - 1; l >= 1 && m->lv[l].g.S <= cap && (int)m->lv.size() - l <= IFADV_ML_BOTTOM_MAX; --l) m->bottom = l;
+  }
+  {
+    const char* e = getenv("IFADV_POIS_MARCH");
+    m->march = e ? atoi(e) : 32;
+    m->march_minS = e ? 0 : 4000000;
+    int occ = 0;
+    cudaError_t oe = c->dtype == IFADV_F32 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pois_mult_march_kernel<float, 1>, 256, 0)
+                                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pois_mult_march_kernel<double, 1>, 256, 0);
+    m->march_occ = (oe == cudaSuccess && occ >= 1) ? occ : 2;
   }
   if (cudaMallocHost(&m->host_r2, sizeof(double)) != cudaSuccess) return fail(-3, "pinned memory");
   if (cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(-3, "stream");

@@ -309,6 +309,70 @@ _Pragma("unroll")
   }
 }
 
+// The same product, marching: a thread owns a column (x, y) and walks a chunk of z planes with ϵ(z-1), ϵ(z), ϵ(z+1) and the two z-face
+// coefficients in registers -- 11 loads per cell instead of 14, the three dropped ones being L2 hits in the row form (3-D only).  Lanes run
+// along x, the 8 warps of a CTA along y (their y-neighbours meet in L1).  Identical per-cell arithmetic; MODE 0: psolver! (gate `done`,
+// scalar step fin_mult), MODE 1: the multigrid smoother (gate `live`, alpha and its range check, ifadv_mlpoisson.cuh).
+template <class T, int MODE> IFADV_DI void fin_mult_mode(PoisCtl* ctl, double ze) {
+  if (MODE == 0) {
+    if (ctl->slab) ctl->acc[0] = ze;
+    else fin_mult<T>(ctl, ze);
+  } else {
+    const T alpha = (T)ctl->rho / (T)ze;
+    ctl->alpha = (double)alpha;
+    const double aa = fabs((double)alpha);
+    if (aa < 1e-2 || aa > 1e3) ctl->live = 0;
+  }
+}
+template <class T, int MODE> __global__ void __launch_bounds__(256) pois_mult_march_kernel(T* __restrict__ z, const T* __restrict__ eps,
+                                                                                           const T* __restrict__ L, const T* __restrict__ Dg,
+                                                                                           const Geo g, PoisCtl* ctl, int kz0, int kz1, int chunk) {
+  if (MODE == 0 ? (ctl->done != 0) : (ctl->live == 0)) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nx = g.n[0] - 2, ny = g.n[1] - 2;
+  const int xseg = (nx + 31) >> 5, ygrp = (ny + 7) >> 3, nzc = (kz1 - kz0 + chunk - 1) / chunk;
+  const long long items = (long long)xseg * ygrp * nzc;
+  const long long s1 = g.s1, s2 = g.s2;
+  const T* __restrict__ Lx = L;
+  const T* __restrict__ Ly = L + g.S;
+  const T* __restrict__ Lz = L + 2 * g.S;
+  double acc[1] = {0.0};
+  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+    const int xs = (int)(it % xseg);
+    const long long q = it / xseg;
+    const int yg = (int)(q % ygrp), zc = (int)(q / ygrp);
+    const int x = 2 + (xs << 5) + lane, y = 2 + (yg << 3) + wid;
+    if (x > g.n[0] - 1 || y > g.n[1] - 1) continue;
+    const int za = kz0 + zc * chunk, zb = min(kz1, za + chunk);
+    long long l = lin3(g, x, y, za);
+    T em = __ldg(eps + l - s2), ec = __ldg(eps + l), lzc = __ldg(Lz + l);
+    // the 11 loads of plane zz+1 are issued before the arithmetic of plane zz (two planes of loads in flight per thread)
+    T ep = __ldg(eps + l + s2), lzp = __ldg(Lz + l + s2);
+    T exm = __ldg(eps + l - 1), exp_ = __ldg(eps + l + 1), eym = __ldg(eps + l - s1), eyp = __ldg(eps + l + s1);
+    T lx = __ldg(Lx + l), lxp = __ldg(Lx + l + 1), ly = __ldg(Ly + l), lyp = __ldg(Ly + l + s1), dg = __ldg(Dg + l);
+    for (int zz = za; zz < zb; ++zz, l += s2) {
+      T n_ep = T(0), n_lzp = T(0), n_exm = T(0), n_exp = T(0), n_eym = T(0), n_eyp = T(0), n_lx = T(0), n_lxp = T(0), n_ly = T(0), n_lyp = T(0),
+        n_dg = T(0);
+      if (zz + 1 < zb) {
+        const long long ln = l + s2;
+        n_ep = __ldg(eps + ln + s2); n_lzp = __ldg(Lz + ln + s2);
+        n_exm = __ldg(eps + ln - 1); n_exp = __ldg(eps + ln + 1); n_eym = __ldg(eps + ln - s1); n_eyp = __ldg(eps + ln + s1);
+        n_lx = __ldg(Lx + ln); n_lxp = __ldg(Lx + ln + 1); n_ly = __ldg(Ly + ln); n_lyp = __ldg(Ly + ln + s1); n_dg = __ldg(Dg + ln);
+      }
+      T lo = T(0), up = T(0);
+      lo = lo + lx * exm; lo = lo + ly * eym; lo = lo + lzc * em;
+      up = up + lxp * exp_; up = up + lyp * eyp; up = up + lzp * ep;
+      const T v = ec * dg + lo + up;
+      z[l] = v;
+      acc[0] += (double)v * (double)ec;
+      em = ec; ec = ep; lzc = lzp;
+      ep = n_ep; lzp = n_lzp; exm = n_exm; exp_ = n_exp; eym = n_eym; eyp = n_eyp; lx = n_lx; lxp = n_lxp; ly = n_ly; lyp = n_lyp; dg = n_dg;
+    }
+  }
+  double tot[1];
+  if (grid_reduce<1>(acc, ctl, 2, tot) && threadIdx.x == 0) fin_mult_mode<T, MODE>(ctl, tot[0]);
+}
+
 // x += alpha ϵ; r -= alpha z; z = r·iD;  Σ r·z, Σ r·r; last CTA: the scalar recurrence and the loop condition   (flow.jl:313-321)
 template <class T, int D> __global__ void __launch_bounds__(256) pois_update_kernel(T* __restrict__ x, T* __restrict__ r, T* __restrict__ z,
                                                                                     const T* __restrict__ eps, const T* __restrict__ iD, const Geo g,

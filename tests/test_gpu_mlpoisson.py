@@ -223,3 +223,28 @@ def test_simulation_with_multilevel_projection_runs(ia):
     u = ia.to_numpy(sim.flow.u)
     div = (u[2:, 1:-1, 0] - u[1:-1, 1:-1, 0]) + (u[1:-1, 2:, 1] - u[1:-1, 1:-1, 1])
     assert (div ** 2).sum() <= 4e-4
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("Ng,perdir", [((34, 18, 18), ()), ((18, 34, 18), (1, 2)), ((18, 18, 34), (3,))])
+def test_marching_product_equals_row_form(ia, Ng, perdir, T, monkeypatch):
+    """z = Aϵ as a march along z (pois_mult_march_kernel, the default on large 3-D grids) against the row form, forced on small grids
+    through IFADV_POIS_MARCH: the Jacobi-PCG psolver! and the multigrid solver! give the same iterates up to the summation order of
+    the dot products (chunks of 5 planes: ragged last chunk, several chunks per column)."""
+    out = {}
+    monkeypatch.setenv("IFADV_POIS_COOP", "0")                      # small grids: the three-kernel form of psolver!, not the cooperative launch
+    for march in ("0", "5"):
+        monkeypatch.setenv("IFADV_POIS_MARCH", march)
+        L = make_L(Ng, perdir, T, seed=51, lam_rho=1e-1)
+        z = _source(Ng, T, 52)
+        pd = ia.Poisson(ia.from_numpy(O.zeros(Ng, T)), ia.from_numpy(L), ia.from_numpy(z), perdir)
+        n = ia.psolver(pd, itmx=7)
+        md = ia.MultiLevelPoisson(ia.from_numpy(O.zeros(Ng, T)), ia.from_numpy(L), ia.from_numpy(z), perdir)
+        c = ia.solver(md, tol=1e-4 if T == np.float32 else 1e-10, itmx=64)
+        out[march] = (n, ia.to_numpy(pd.x).astype(np.float64), c, ia.to_numpy(md.x).astype(np.float64), md.r2[-1])
+    a, b = out["0"], out["5"]
+    tol = 1e-11 if T == np.float64 else 2e-4
+    assert a[0] == b[0] == 7 and np.abs(a[1] - b[1]).max() <= tol * max(1.0, np.abs(a[1]).max())
+    assert abs(a[2] - b[2]) <= 1 and b[4] < (1e-4 if T == np.float32 else 1e-10)
+    if a[2] == b[2]:
+        assert np.abs(a[3] - b[3]).max() <= (1e-7 if T == np.float64 else 5e-2) * max(1.0, np.abs(a[3]).max())
