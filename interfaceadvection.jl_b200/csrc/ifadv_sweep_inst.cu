@@ -161,7 +161,17 @@ static int launch_along_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
 // v4: lean register-marching kernel (static ring slots, one barrier per plane) for sweeps along y / z (3-D only)
 template <class T, int J, int CPT, bool MOM, bool FUSED, bool KOREN, int MINB, bool SAMEU = false>
 static int launch_along2_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
-  constexpr int NT = 256, TC = (NT / 32) * CPT;
+  // Float64 (196 registers at 256 threads = 8 warps per SM): the fused first sweep fits 168 registers without spills, so it runs 384
+  // threads per CTA (12 warps: 256^3 y 1.16 -> 0.98 ms, z 1.13 -> 0.93 ms); the standard sweep spills ~12 doubles at 168 (1.14 -> 1.21 ms)
+  // and stays at 256 threads, like the fused sweep with a limiter other than Koren (9..12 warps per SM all cap at 168 registers: 3 warps
+  // per scheduler) -- tools/runs/gpurun_run64.sh
+#ifndef IFADV_XP_A2NT64
+#define IFADV_XP_A2NT64 256
+#endif
+#ifndef IFADV_XP_A2NT64F
+#define IFADV_XP_A2NT64F 384
+#endif
+  constexpr int NT = (sizeof(T) == 8) ? ((MOM && FUSED && KOREN) ? IFADV_XP_A2NT64F : IFADV_XP_A2NT64) : 256, TC = (NT / 32) * CPT;
   using TL = ATile<TC>;
   SweepP<T> P;
   fill_params<T>(c, q, J, P);
