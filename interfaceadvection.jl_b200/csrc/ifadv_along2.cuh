@@ -1,6 +1,6 @@
 // ifadv_along2.cuh -- fused directional sweep along y or z (J = 1, 2) for 3-D grids: LEAN register marching.
 //
-// Same tile / shared-memory layout and the same arithmetic (expression by expression) as ifadv_along.cuh, restructured
+// Same tile / shared-memory layout and the same arithmetic (expression by expression) as its retired first generation, restructured
 // so that the interior of the domain runs a branch-free body with compile-time ring slots and ONE barrier per plane:
 //   * software skew: step k evaluates the VOF / mass flux of face k+2 and the dilation of plane k+1 (written to the
 //     shared M / Dil rings for the x-1 / c-1 neighbours) and, in the same step, the SynDRoM fluxes of face k+1 and the
@@ -14,11 +14,22 @@
 //   * face densities ρ(f̄) of the three faces of a cell are evaluated once (for u★) and carried in registers for the
 //     SynDRoM donor density of the next two faces and for the fused u2ρu! product;
 //   * fill-error extrema by FMNMX (NaN-propagating max); the location is only tracked for cells outside [0,1].
-// Reference lines as in ifadv_along.cuh / ifadv_march.cuh / ifadv_sweep.cuh.
+// Reference lines as in ifadv_march.cuh / ifadv_sweep.cuh.
 #pragma once
-#include "ifadv_along.cuh"
+#include "ifadv_march.cuh"
 
 namespace ifadv {
+
+// tile of the register-marching kernels: 32 columns along x, TCT rows along the cross direction c, halo of 1 below / 2 above in both
+template <int TCT> struct ATile {  // TCT = tile extent along c (rows) = 8 * columns-per-thread
+  static constexpr int WX = 35, WC = TCT + 3, PLH = WX * WC, NC = 32 * TCT, NH = PLH - NC, NHU = 32 + TCT;
+  static constexpr int RF = 8, RU = 4, RR = 4, RO = 2;
+  // halo planes: F, U, U0, M x2, FX (+ Dil x2) ; core planes (CMOM): ρu, uOld ; + interface list + counter
+  template <class T> static constexpr size_t smem_bytes(bool mom) {
+    return sizeof(T) * ((size_t)PLH * (RF + 2 * RU + 3 + (mom ? 2 : 0)) + (mom ? (size_t)NC * 3 * (RR + RO) : 0)) + sizeof(int) * (PLH + 4);
+  }
+};
+
 
 template <bool B> struct BoolC { static constexpr bool value = B; };
 template <int V> struct IntC { static constexpr int value = V; };

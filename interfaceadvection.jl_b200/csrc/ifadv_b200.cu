@@ -893,7 +893,7 @@ int ifadv_create(ifadv_ctx** out, int D, const int64_t Ng[3], int dtype, int dev
     const char* e = getenv("IFADV_KERNEL");
     // default: register-marching (y,z sweeps) + plane-marching (x sweep); "march": plane-marching for all; "tile": v1
     c->use_march = (e && std::string(e) == "tile") ? 0 : ((e && std::string(e) == "march") ? 2 : 1);
-    c->use_along2 = (e && std::string(e) == "along1") ? 0 : 1;  // "along1": the first register-marching kernel for y/z sweeps
+    c->use_along2 = 1;  // y/z sweeps: the lean register-marching kernel (its first generation, IFADV_KERNEL=along1, is retired)
     c->use_xrow = (e && std::string(e) == "xsweep") ? 0 : 1;    // "xsweep": the plane-marching kernel for CMOM x sweeps
     const char* ev = getenv("IFADV_VOF_KERNEL");
     c->use_vofcell = (e || (ev && std::string(ev) == "lean")) ? 0 : 1;  // pure VOF, 3-D: cell-parallel kernel unless an older generation is asked for

@@ -61,7 +61,7 @@ struct ifadv_ctx {
   int host_slabs;              // z-slabs it was pipelined over (1 = single pass)
   // optional per-launch CUDA-event timing of the fused sweep (ifadv_profile)
   int use_march;  // 1: register-marching (y,z) + plane-marching (x) kernels (default); 2: plane-marching only; 0: v1 tile kernel
-  int use_along2;  // 1 (default): lean register-marching kernel ifadv_along2.cuh for y/z sweeps; 0: ifadv_along.cuh
+  int use_along2;  // 1: lean register-marching kernel ifadv_along2.cuh for y/z sweeps (always; the first generation is retired)
   int use_vofcell; // 1 (default): cell-parallel kernel ifadv_vofcell.cuh for 3-D pure-VOF sweeps; 0 (IFADV_VOF_KERNEL=lean or any IFADV_KERNEL): along2 / xrow
   int use_xrow;    // 1 (default): warp-autonomous row kernel ifadv_xrow.cuh for CMOM x sweeps; 0: ifadv_xsweep.cuh
   int prof_on, prof_n;

@@ -1,7 +1,7 @@
 // ifadv_sweep_inst.cu -- instantiates the fused sweep kernels for ONE (T, D, MOM, family) combination, chosen with
 // -DIFADV_T=float|double -DIFADV_D=2|3 -DIFADV_MOM=0|1 -DIFADV_FAM=0..6, so that the instantiations compile in parallel:
 //   FAM 0  dispatcher (launch_sweep_dim) + v1 tile kernel        FAM 1  plane-marching kernel (march)
-//   FAM 2  register-marching kernel (along)                      FAM 3  lean register marching (along2), y / z sweeps
+//   FAM 3  lean register marching (along2), y / z sweeps   (FAM 2, its first generation `along`, is retired)
 //   FAM 4  lean plane marching along x (xsweep, CMOM only)       FAM 5  warp-autonomous rows along x (xrow, CMOM only)
 //   FAM 6  cell-parallel pure-VOF sweep (vofcell, advect! only)
 //   families 1-6 exist for 3-D grids only
@@ -22,8 +22,6 @@
 #endif
 #elif IFADV_FAM == 1
 #include "ifadv_march.cuh"
-#elif IFADV_FAM == 2
-#include "ifadv_along.cuh"
 #elif IFADV_FAM == 3
 #include "ifadv_along2.cuh"
 #elif IFADV_FAM == 4
@@ -113,39 +111,6 @@ static int launch_march_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
   int chunk = 64;
   while (chunk > 8 && tiles * ((nc + chunk - 1) / chunk) < 148 * 6) chunk >>= 1;
   dim3 grid((unsigned)((nx + tx - 1) / tx), (unsigned)((no + to - 1) / to), (unsigned)((nc + chunk - 1) / chunk));
-  const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
-  if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
-  kern<<<grid, NT, smem, st>>>(P, chunk);
-  if (prof) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], st); c->prof_tag[c->prof_n] = (unsigned char)((q.fused ? 1 : 0) | ((2 * q.j + (q.fused ? 1 : 0)) << 1)); c->prof_n++; }
-  c->launches++;
-  CU_CHECK(c, cudaGetLastError());
-  return 0;
-}
-
-#endif
-
-#if IFADV_FAM == 2
-// v3: register-marching kernel for sweeps along y / z (3-D only)
-template <class T, int J, int CPT, bool MOM, bool FUSED, int MINB>
-static int launch_along_t(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
-  constexpr int NT = 256, TC = (NT / 32) * CPT;
-  using TL = ATile<TC>;
-  SweepP<T> P;
-  fill_params<T>(c, q, J, P);
-  const size_t smem = TL::template smem_bytes<T>(MOM);
-  auto kern = along_kernel<T, J, CPT, MOM, FUSED, NT, MINB>;
-  // per device (one context per device): opt in to the large dynamic shared-memory carve-out once
-  static unsigned long long attr_devs = 0ull;
-  if (!((attr_devs >> (c->device & 63)) & 1ull)) {
-    CU_CHECK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_devs |= 1ull << (c->device & 63);
-  }
-  constexpr int DCC = (J == 1) ? 2 : 1;
-  const int nx = c->g.n[0] - 2, ncc = c->g.n[DCC] - 2, na = c->g.n[J] - 2;
-  const long long tiles = (long long)((nx + 31) / 32) * ((ncc + TC - 1) / TC);
-  int chunk = 128;  // 4 warm-up planes per chunk
-  while (chunk > 16 && tiles * ((na + chunk - 1) / chunk) < 148 * 8) chunk >>= 1;
-  dim3 grid((unsigned)((nx + 31) / 32), (unsigned)((ncc + TC - 1) / TC), (unsigned)((na + chunk - 1) / chunk));
   const bool prof = c->prof_on && c->prof_ev && c->prof_n < IFADV_PROF_MAX;
   if (prof) cudaEventRecord(c->prof_ev[2 * c->prof_n], st);
   kern<<<grid, NT, smem, st>>>(P, chunk);
@@ -335,7 +300,6 @@ template <class T, int J, bool SAMEU> static int launch_vofcell_t(ifadv_ctx* c, 
 
 // per-family entry points (3-D only), each defined and explicitly instantiated in its own translation unit
 template <class T, bool MOM> int launch_fam_march(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
-template <class T, bool MOM> int launch_fam_along(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 template <class T, bool MOM> int launch_fam_along2(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 template <class T, bool MOM> int launch_fam_xsweep(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
 template <class T, bool MOM> int launch_fam_xrow(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q);
@@ -364,7 +328,6 @@ template <class T, int D, bool MOM> int launch_sweep_dim(ifadv_ctx* c, cudaStrea
       if (c->use_xrow && xrow_ok<T>(c, q)) return launch_fam_xrow<T, MOM>(c, st, q);
       if constexpr (MOM) return launch_fam_xsweep<T, MOM>(c, st, q);
     }
-    if (c->use_march == 1 && q.j != 0) return launch_fam_along<T, MOM>(c, st, q);
     if (c->use_march) return launch_fam_march<T, MOM>(c, st, q);
   }
   if constexpr (D == 2) {
@@ -466,19 +429,6 @@ template <class T, bool MOM> int launch_fam_march(ifadv_ctx* c, cudaStream_t st,
   return launch_march_t<T, 2, TO, 32, MOM, false, MB>(c, st, q);
 }
 template int launch_fam_march<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
-
-#elif IFADV_FAM == 2
-template <class T, bool MOM> int launch_fam_along(ifadv_ctx* c, cudaStream_t st, const SweepCfg<T>& q) {
-  // Float32: two columns per thread (2 CTAs/SM, twice the ILP, half the per-plane overhead); Float64: one
-  constexpr int CP = (sizeof(T) == 4) ? 2 : 1;
-  if (MOM && q.fused) {
-    if (q.j == 1) return launch_along_t<T, 1, CP, MOM, MOM, 2>(c, st, q);
-    return launch_along_t<T, 2, CP, MOM, MOM, 2>(c, st, q);
-  }
-  if (q.j == 1) return launch_along_t<T, 1, CP, MOM, false, 2>(c, st, q);
-  return launch_along_t<T, 2, CP, MOM, false, 2>(c, st, q);
-}
-template int launch_fam_along<IFADV_T, (IFADV_MOM != 0)>(ifadv_ctx*, cudaStream_t, const SweepCfg<IFADV_T>&);
 
 #elif IFADV_FAM == 3
 #ifndef IFADV_XP_A2CPT
