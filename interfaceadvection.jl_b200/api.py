@@ -229,7 +229,8 @@ class Flow:
 
 class TwoPhaseSimulation:
     """TwoPhaseSimulation(dims, u_BC, L; T, λμ, λρ, η, InterfaceSDF, λ, normalScheme, kwargs...)
-    (src/InterfaceAdvection.jl:64-85).  The Poisson solver and body stay with WaterLily (out of scope)."""
+    (src/InterfaceAdvection.jl:64-85).  psolver: "Poisson" (the Jacobi-PCG psolver! of flow.jl:300), "MultiLevelPoisson" (WaterLily's
+    default, inproject!'s second method) or None (no projection object); bodies stay with WaterLily (out of scope)."""
 
     def __init__(self, dims, u_BC, L, T=torch.float32, lam_mu=1e-2, lam_rho=1e-3, eta=None, InterfaceSDF=None, lam="Koren",
                  normalScheme="WH", U=None, dt=0.25, nu=0.0, g=None, u0=None, perdir=(), exitBC=False, device="cuda", psolver=None):
