@@ -315,7 +315,7 @@ int ifadv_ml_create(ifadv_ctx* c, ifadv_ml** out, void* stream, void* x, void* L
     return true;
   };
   if (!add_level(c, x, L, z)) return fail(-3, "out of device memory for the multigrid levels");
-  while (ml_divisible(m->lv.back().g, c->D) && (int)m->lv.size() <= maxlevels) {  // restrictML: Na = 1 + N÷2 with N = size - 2... = n/2 + 1
+  while (ml_divisible(m->lv.back().g, c->D) && (int)m->lv.size() <= maxlevels) {  // restrictML: Na = 1 + N÷2, N the interior extent (n - 2), i.e. n/2 + 1 with ghosts
     const Geo& gf = m->lv.back().g;
     int64_t Na[3] = {1 + gf.n[0] / 2, 1 + gf.n[1] / 2, c->D == 3 ? 1 + gf.n[2] / 2 : 1};
     ifadv_ctx* lc = nullptr;
